@@ -1,0 +1,411 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU/fp32 restatement of the reference's DUSt3R two-view path.
+
+This is the *checker* for the CUDA product in `uniception_b200/`; nothing in the product
+path may import it (only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s
+`cpu_baseline` / `--impl reference` legs do).
+
+Parity status: PINNED by differential tests against the real reference
+(castacks/UniCeption @ 802ebc17, imported from /root/reference in the build container by
+`oracle/make_golden.py`); the resulting vectors are committed under `tests/golden/`.  The
+reference's only known-answer test (examples/models/dust3r/dust3r.py:198-230,
+`03_head_output.npz`) ships no fixtures, so its *metric form* (max-abs + relative L2) is
+what `parity()` below implements.
+
+It is a functional restatement: every function takes plain tensors and a flat
+`state_dict` with the reference's key names, and cites the reference
+file:line whose arithmetic it follows.  All math runs in whatever dtype the inputs carry
+(fp32 for the goldens, fp64 for tighter checks).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+SD = Dict[str, Tensor]
+
+
+# --------------------------------------------------------------------------------------
+# parity metric -- form taken from examples/models/dust3r/dust3r.py:223-230
+# --------------------------------------------------------------------------------------
+def parity(x: Tensor, ref: Tensor) -> Tuple[float, float]:
+    """(max-abs error, relative L2 error ||x-ref||_2 / ||ref||_2)."""
+    x = x.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    diff = x - ref
+    denom = float(ref.norm())
+    return float(diff.abs().max()) if diff.numel() else 0.0, float(diff.norm()) / (denom if denom > 0 else 1.0)
+
+
+# --------------------------------------------------------------------------------------
+# integer / index ops (bit-exact)
+# --------------------------------------------------------------------------------------
+def patch_positions(b: int, h: int, w: int, device="cpu") -> Tensor:
+    """(y, x) integer grid, row-major with y outer.  libs/croco/patch_embed.py:25-31,
+    utils/positional_encoding.py:8-23 (cartesian_prod(arange(h), arange(w)))."""
+    ys = torch.arange(h, device=device).repeat_interleave(w)
+    xs = torch.arange(w, device=device).repeat(h)
+    return torch.stack([ys, xs], dim=-1).view(1, h * w, 2).expand(b, -1, -1).clone()
+
+
+def feature_take_indices(num_features: int, indices=None) -> Tuple[List[int], int]:
+    """utils/intermediate_feature_return.py:47-85: None -> all, int n -> last n, list (negatives ok)."""
+    if indices is None:
+        indices = num_features
+    if isinstance(indices, int):
+        assert 0 < indices <= num_features
+        take = [num_features - indices + i for i in range(indices)]
+    else:
+        take = []
+        for i in indices:
+            idx = num_features + i if i < 0 else i
+            assert 0 <= idx < num_features
+            take.append(idx)
+    return take, max(take)
+
+
+def is_symmetrized(inst1: Sequence, inst2: Sequence) -> bool:
+    """factory/dust3r.py:21-30."""
+    if len(inst1) == len(inst2) and len(inst1) == 1:
+        return False
+    ok = True
+    for i in range(0, len(inst1), 2):
+        ok = ok and (inst1[i] == inst2[i + 1]) and (inst1[i + 1] == inst2[i])
+    return ok
+
+
+def interleave(t1: Tensor, t2: Tensor) -> Tuple[Tensor, Tensor]:
+    """factory/dust3r.py:33-37."""
+    r1 = torch.stack((t1, t2), dim=1).flatten(0, 1)
+    r2 = torch.stack((t2, t1), dim=1).flatten(0, 1)
+    return r1, r2
+
+
+def pixel_shuffle(x: Tensor, p: int) -> Tensor:
+    """out[b,c,p*h+i,p*w+j] = in[b, c*p*p + i*p + j, h, w]  (prediction_heads/linear.py:81-82)."""
+    b, cpp, h, w = x.shape
+    c = cpp // (p * p)
+    return x.view(b, c, p, p, h, w).permute(0, 1, 4, 2, 5, 3).reshape(b, c, h * p, w * p)
+
+
+# --------------------------------------------------------------------------------------
+# float ops
+# --------------------------------------------------------------------------------------
+def rope2d(tokens: Tensor, positions: Tensor, base: float = 100.0, f0: float = 1.0) -> Tensor:
+    """2-D rotary embedding on tokens [B,H,N,D], positions [B,N,2] (y,x) integers.
+
+    Formula of the native kernel, libs/croco/curope/kernels.cu:39-80 / curope.cpp:21-41
+    (identical to the PyTorch fallback libs/croco/pos_embed.py:116-155 in fp32):
+    D = 4Q; for half X in {0:y, 1:x}, i < Q: theta = pos[b,n,X] * f0 / base**(i/Q);
+    (u, v) = (t[2QX+i], t[2QX+Q+i]) -> (u cos - v sin, v cos + u sin).
+    Backward is the same map with f0 -> -f0 (curope2d.py:24-28)."""
+    B, H, N, D = tokens.shape
+    assert D % 4 == 0
+    Q = D // 4
+    i = torch.arange(Q, device=tokens.device, dtype=torch.float32)
+    inv_freq = (f0 / torch.pow(torch.tensor(base, dtype=torch.float32, device=tokens.device), i / Q))
+    ang = positions.to(torch.float32)[..., None] * inv_freq  # [B,N,2,Q] fp32 angle math
+    cos = ang.cos().to(tokens.dtype)[:, None]  # [B,1,N,2,Q]
+    sin = ang.sin().to(tokens.dtype)[:, None]
+    t = tokens.reshape(B, H, N, 2, 2, Q)
+    u, v = t[..., 0, :], t[..., 1, :]
+    out = torch.stack((u * cos - v * sin, v * cos + u * sin), dim=-2)
+    return out.reshape(B, H, N, D)
+
+
+def layer_norm(x: Tensor, w: Tensor, b: Tensor, eps: float = 1e-6) -> Tensor:
+    """nn.LayerNorm(C, eps=1e-6), biased variance (encoders/croco.py:32)."""
+    mu = x.mean(dim=-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * w + b
+
+
+def gelu_erf(x: Tensor) -> Tensor:
+    """nn.GELU() exact-erf form (libs/croco/blocks.py:67)."""
+    return 0.5 * x * (1.0 + torch.erf(x * (1.0 / math.sqrt(2.0))))
+
+
+def linear(x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
+    y = x @ w.t()
+    return y if b is None else y + b
+
+
+def sdpa(q: Tensor, k: Tensor, v: Tensor) -> Tensor:
+    """softmax(q k^T d^-0.5) v per (b,h); the reference's naive path, libs/croco/blocks.py:117-120."""
+    s = (q @ k.transpose(-2, -1)) * (q.shape[-1] ** -0.5)
+    return s.softmax(dim=-1) @ v
+
+
+def mlp(sd: SD, p: str, x: Tensor) -> Tensor:
+    """fc2(GELU(fc1 x)), libs/croco/blocks.py:80-86, utils/transformer_blocks.py:82-89."""
+    return linear(gelu_erf(linear(x, sd[p + "fc1.weight"], sd[p + "fc1.bias"])), sd[p + "fc2.weight"], sd[p + "fc2.bias"])
+
+
+def self_attention(sd: SD, p: str, x: Tensor, pos: Optional[Tensor], heads: int, base: float) -> Tensor:
+    """libs/croco/blocks.py:105-130 == utils/transformer_blocks.py:208-257 (DUSt3R flags)."""
+    B, N, C = x.shape
+    d = C // heads
+    qkv = linear(x, sd[p + "qkv.weight"], sd.get(p + "qkv.bias")).view(B, N, 3, heads, d).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    if pos is not None:
+        q, k = rope2d(q, pos, base), rope2d(k, pos, base)
+    o = sdpa(q, k, v).transpose(1, 2).reshape(B, N, C)
+    return linear(o, sd[p + "proj.weight"], sd[p + "proj.bias"])
+
+
+def cross_attention(sd: SD, p: str, xq: Tensor, y: Tensor, qpos, kpos, heads: int, base: float) -> Tensor:
+    """utils/transformer_blocks.py:320-386."""
+    B, Nq, C = xq.shape
+    Nk = y.shape[1]
+    d = C // heads
+    q = linear(xq, sd[p + "projq.weight"], sd.get(p + "projq.bias")).view(B, Nq, heads, d).permute(0, 2, 1, 3)
+    k = linear(y, sd[p + "projk.weight"], sd.get(p + "projk.bias")).view(B, Nk, heads, d).permute(0, 2, 1, 3)
+    v = linear(y, sd[p + "projv.weight"], sd.get(p + "projv.bias")).view(B, Nk, heads, d).permute(0, 2, 1, 3)
+    if qpos is not None:
+        q, k = rope2d(q, qpos, base), rope2d(k, kpos, base)
+    o = sdpa(q, k, v).transpose(1, 2).reshape(B, Nq, C)
+    return linear(o, sd[p + "proj.weight"], sd[p + "proj.bias"])
+
+
+def encoder_block(sd: SD, p: str, x: Tensor, pos: Tensor, heads: int, base: float) -> Tensor:
+    """libs/croco/blocks.py:158-161."""
+    x = x + self_attention(sd, p + "attn.", layer_norm(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"]), pos, heads, base)
+    x = x + mlp(sd, p + "mlp.", layer_norm(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"]))
+    return x
+
+
+def decoder_block(sd: SD, p: str, x: Tensor, y: Tensor, xpos, ypos, heads: int, base: float) -> Tensor:
+    """utils/transformer_blocks.py:643-646 (LayerScale/DropPath are Identity for DUSt3R)."""
+    x = x + self_attention(sd, p + "attn.", layer_norm(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"]), xpos, heads, base)
+    y_ = layer_norm(y, sd[p + "norm_y.weight"], sd[p + "norm_y.bias"])
+    x = x + cross_attention(
+        sd, p + "cross_attn.", layer_norm(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"]), y_, xpos, ypos, heads, base
+    )
+    x = x + mlp(sd, p + "mlp.", layer_norm(x, sd[p + "norm3.weight"], sd[p + "norm3.bias"]))
+    return x
+
+
+def patch_embed(sd: SD, p: str, img: Tensor, patch: int) -> Tuple[Tensor, Tensor]:
+    """Conv2d(3,C,k=s=patch)+bias, flatten(2).transpose(1,2) (libs/croco/patch_embed.py:68-82),
+    restated as unfold + matmul (kernel == stride so patches do not overlap)."""
+    B, Cin, H, W = img.shape
+    assert H % patch == 0 and W % patch == 0
+    h, w = H // patch, W // patch
+    cols = img.view(B, Cin, h, patch, w, patch).permute(0, 2, 4, 1, 3, 5).reshape(B, h * w, Cin * patch * patch)
+    wgt = sd[p + "proj.weight"]
+    x = cols @ wgt.reshape(wgt.shape[0], -1).t() + sd[p + "proj.bias"]
+    return x, patch_positions(B, h, w, img.device)
+
+
+def croco_encoder(
+    sd: SD, p: str, img: Tensor, depth: int, heads: int, patch: int = 16, base: float = 100.0,
+    indices=None, norm_intermediate: bool = True,
+):
+    """encoders/croco.py:147-182 (and the IFR variant :260-327 when `indices` is given).
+    Returns BCHW features (and a list of intermediate BCHW features)."""
+    B, _, H, W = img.shape
+    x, pos = patch_embed(sd, p + "patch_embed.", img, patch)
+    take = feature_take_indices(depth, indices)[0] if indices is not None else []
+    inter = []
+    for i in range(depth):
+        x = encoder_block(sd, f"{p}enc_blocks.{i}.", x, pos, heads, base)
+        if i in take:
+            inter.append(layer_norm(x, sd[p + "enc_norm.weight"], sd[p + "enc_norm.bias"]) if norm_intermediate else x)
+    x = layer_norm(x, sd[p + "enc_norm.weight"], sd[p + "enc_norm.bias"])
+    C = x.shape[-1]
+
+    def to_bchw(t):
+        return t.permute(0, 2, 1).reshape(B, C, H // patch, W // patch).contiguous()
+
+    if indices is not None:
+        return to_bchw(x), [to_bchw(t) for t in inter]
+    return to_bchw(x)
+
+
+def info_sharing(
+    sd: SD, p: str, feats: List[Tensor], depth: int, heads: int, base: float = 100.0,
+    indices=None, norm_intermediate: bool = True,
+):
+    """info_sharing/cross_attention_transformer.py:191-275 (IFR: :390-505).  Each view's block
+    at depth k reads the *other* views' tokens from depth k-1."""
+    nv = len(feats)
+    B, _, h, w = feats[0].shape
+    toks = [f.permute(0, 2, 3, 1).reshape(B, h * w, f.shape[1]) for f in feats]
+    pos = [patch_positions(B, h, w, f.device) for f in feats]
+    if (p + "proj_embed.weight") in sd:
+        toks = [linear(t, sd[p + "proj_embed.weight"], sd[p + "proj_embed.bias"]) for t in toks]
+    take = feature_take_indices(depth, indices)[0] if indices is not None else []
+    inter = []
+    nw, nb = sd[p + "norm.weight"], sd[p + "norm.bias"]
+    for k in range(depth):
+        new = []
+        for v in range(nv):
+            others = torch.cat([toks[i] for i in range(nv) if i != v], dim=1)
+            opos = torch.cat([pos[i] for i in range(nv) if i != v], dim=1)
+            new.append(decoder_block(sd, f"{p}multi_view_branches.{v}.{k}.", toks[v], others, pos[v], opos, heads, base))
+        toks = new
+        if k in take:
+            inter.append([layer_norm(t, nw, nb) if norm_intermediate else t for t in toks])
+    dim = toks[0].shape[-1]
+
+    def to_bchw(t):
+        return t.reshape(B, h, w, dim).permute(0, 3, 1, 2).contiguous()
+
+    out = [to_bchw(layer_norm(t, nw, nb)) for t in toks]
+    if indices is not None:
+        return out, [[to_bchw(t) for t in lvl] for lvl in inter]
+    return out
+
+
+def linear_head(sd: SD, p: str, feat: Tensor, patch: int) -> Tensor:
+    """1x1 conv C -> out*p^2 then pixel_shuffle(p) (prediction_heads/linear.py:47-54, :81-82)."""
+    w = sd[p + "linear.weight"]
+    y = torch.einsum("bchw,oc->bohw", feat, w.reshape(w.shape[0], -1)) + sd[p + "linear.bias"][None, :, None, None]
+    return pixel_shuffle(y, patch)
+
+
+def pointmap_conf_adaptor(x: Tensor, depth_mode=("exp", -math.inf, math.inf), conf_mode=("exp", 1.0, math.inf)):
+    """PointMapWithConfidenceAdaptor: prediction_heads/adaptors.py:1217-1230 -> PointMapAdaptor
+    :318-355 (exp: xyz/clip(d,1e-8)*expm1(d)) + ConfidenceAdaptor :1068-1083 (vmin + exp(x).clip(max=vmax-vmin))."""
+    xyz, c = x[:, :3], x[:, 3:4]
+    mode, vmin, vmax = depth_mode
+    if mode == "linear":
+        pts = xyz
+    else:
+        d = xyz.norm(dim=1, keepdim=True)
+        unit = xyz / d.clip(min=1e-8)
+        if mode == "exp":
+            pts = unit * torch.expm1(d)
+        elif mode == "square":
+            pts = unit * d.square()
+        else:
+            raise ValueError(mode)
+    if not (vmin == -math.inf and vmax == math.inf):
+        pts = pts.clip(vmin, vmax)
+    cmode, cmin, cmax = conf_mode
+    assert cmode == "exp"
+    conf = cmin + c.exp().clip(max=cmax - cmin)
+    return pts, conf
+
+
+def depth_adaptor(x: Tensor, mode: str = "exp", vmin=-math.inf, vmax=math.inf) -> Tensor:
+    """prediction_heads/adaptors.py:233-257."""
+    if mode == "exp":
+        y = torch.exp(x)
+    elif mode == "square":
+        y = x * x
+    else:
+        y = x
+    if not (vmin == -math.inf and vmax == math.inf):
+        y = y.clip(vmin, vmax)
+    return y
+
+
+# --------------------------------------------------------------------------------------
+# DPT head (prediction_heads/dpt.py:94-232, :271-311; libs/croco/dpt_block.py:114-255)
+# --------------------------------------------------------------------------------------
+def _rcu(sd: SD, p: str, z: Tensor) -> Tensor:
+    """ResidualConvUnit_custom: z + conv3x3(relu(conv3x3(relu(z)))) (dpt_block.py:114-177, ReLU not in-place)."""
+    o = F.conv2d(F.relu(z), sd[p + "conv1.weight"], sd[p + "conv1.bias"], padding=1)
+    o = F.conv2d(F.relu(o), sd[p + "conv2.weight"], sd[p + "conv2.bias"], padding=1)
+    return o + z
+
+
+def _fusion(sd: SD, p: str, a: Tensor, b: Optional[Tensor]) -> Tensor:
+    """FeatureFusionBlock_custom (dpt_block.py:225-255): a [+ RCU1(b)] -> RCU2 -> bilinear x2 (align_corners) -> 1x1."""
+    out = a
+    if b is not None:
+        out = out + _rcu(sd, p + "resConfUnit1.", b)
+    out = _rcu(sd, p + "resConfUnit2.", out)
+    out = F.interpolate(out, scale_factor=2, mode="bilinear", align_corners=True)
+    return F.conv2d(out, sd[p + "out_conv.weight"], sd[p + "out_conv.bias"])
+
+
+def dpt_feature(sd: SD, p: str, feats: List[Tensor]) -> Tensor:
+    """DPTFeature.forward (dpt.py:180-232) for hooks [0,1,2,3]."""
+    layers = []
+    for j, f in enumerate(feats):
+        q = f"{p}input_process.{j}.0."
+        x = F.conv2d(f, sd[q + "0.weight"], sd[q + "0.bias"])  # 1x1 C_j -> L_j
+        if j == 0:
+            x = F.conv_transpose2d(x, sd[q + "1.weight"], sd[q + "1.bias"], stride=4)
+        elif j == 1:
+            x = F.conv_transpose2d(x, sd[q + "1.weight"], sd[q + "1.bias"], stride=2)
+        elif j == 3:
+            x = F.conv2d(x, sd[q + "1.weight"], sd[q + "1.bias"], stride=2, padding=1)
+        layers.append(F.conv2d(x, sd[f"{p}scratch.layer_rn.{j}.weight"], None, padding=1))
+    l0, l1, l2, l3 = layers
+    p4 = _fusion(sd, p + "scratch.refinenet4.", l3, None)[:, :, : l2.shape[2], : l2.shape[3]]
+    p3 = _fusion(sd, p + "scratch.refinenet3.", p4, l2)
+    p2 = _fusion(sd, p + "scratch.refinenet2.", p3, l1)
+    return _fusion(sd, p + "scratch.refinenet1.", p2, l0)
+
+
+def dpt_regressor(sd: SD, p: str, x: Tensor, out_hw: Tuple[int, int]) -> Tensor:
+    """DPTRegressionProcessor.forward (dpt.py:285-311)."""
+    x = F.conv2d(x, sd[p + "conv1.weight"], sd[p + "conv1.bias"], padding=1)
+    x = F.interpolate(x, size=out_hw, mode="bilinear", align_corners=True)
+    x = F.relu(F.conv2d(x, sd[p + "conv2.0.weight"], sd[p + "conv2.0.bias"], padding=1))
+    return F.conv2d(x, sd[p + "conv2.2.weight"], sd[p + "conv2.2.bias"])
+
+
+# --------------------------------------------------------------------------------------
+# whole model: factory/dust3r.py:250-332
+# --------------------------------------------------------------------------------------
+def dust3r_forward(
+    sd: SD, img1: Tensor, img2: Tensor, *, enc_depth=24, enc_heads=16, dec_depth=12, dec_heads=12,
+    patch=16, base=100.0, head="linear", instances=None,
+) -> Tuple[Dict[str, Tensor], Dict[str, Tensor]]:
+    B, _, H, W = img1.shape
+    sym = instances is not None and is_symmetrized(instances[0], instances[1])
+    a, b = (img1[::2], img2[::2]) if sym else (img1, img2)
+    if head == "linear":
+        feat = croco_encoder(sd, "encoder.", torch.cat((a, b), 0), enc_depth, enc_heads, patch, base)
+    else:
+        feat = croco_encoder(sd, "encoder.", torch.cat((a, b), 0), enc_depth, enc_heads, patch, base)
+    f1, f2 = feat.chunk(2, dim=0)
+    if sym:
+        f1, f2 = interleave(f1, f2)
+    if head == "linear":
+        d1, d2 = info_sharing(sd, "info_sharing.", [f1, f2], dec_depth, dec_heads, base)
+        o1 = linear_head(sd, "head1.", d1, patch)
+        o2 = linear_head(sd, "head2.", d2, patch)
+    else:
+        (d1, d2), inter = info_sharing(sd, "info_sharing.", [f1, f2], dec_depth, dec_heads, base,
+                                       indices=[5, 8], norm_intermediate=False)
+        o1 = dpt_regressor(sd, "dpt_regressor_head1.", dpt_feature(sd, "dpt_feature_head1.", [f1, inter[0][0], inter[1][0], d1]), (H, W))
+        o2 = dpt_regressor(sd, "dpt_regressor_head2.", dpt_feature(sd, "dpt_feature_head2.", [f2, inter[0][1], inter[1][1], d2]), (H, W))
+    p1, c1 = pointmap_conf_adaptor(o1)
+    p2, c2 = pointmap_conf_adaptor(o2)
+    res1 = {"pts3d": p1.permute(0, 2, 3, 1).contiguous(), "conf": c1.permute(0, 2, 3, 1).contiguous()}
+    res2 = {"pts3d_in_other_view": p2.permute(0, 2, 3, 1).contiguous(), "conf": c2.permute(0, 2, 3, 1).contiguous()}
+    return res1, res2
+
+
+def bench_loss(res1, res2) -> Tensor:
+    """The `.sum().backward()` idiom of encoders/utils.py:29-31 applied to all four outputs."""
+    return res1["pts3d"].sum() + res1["conf"].sum() + res2["pts3d_in_other_view"].sum() + res2["conf"].sum()
+
+
+def seeded_state_dict(shapes: Dict[str, Sequence[int]], seed: int, dtype=torch.float32) -> SD:
+    """Deterministic, machine-independent weights for goldens: numpy RandomState stream in key order.
+    Matrices ~ U(-a, a) with the xavier bound, biases small non-zero, LayerNorm weights near 1."""
+    import numpy as np
+
+    rs = np.random.RandomState(seed)
+    sd = {}
+    for k in sorted(shapes):
+        shp = tuple(shapes[k])
+        if len(shp) >= 2:
+            fan_out, fan_in = shp[0], int(np.prod(shp[1:]))
+            a = math.sqrt(6.0 / (fan_in + fan_out))
+            v = rs.uniform(-a, a, size=shp)
+        elif "norm" in k and k.endswith("weight"):
+            v = 1.0 + 0.1 * rs.standard_normal(shp)
+        else:
+            v = 0.02 * rs.standard_normal(shp)
+        sd[k] = torch.from_numpy(np.ascontiguousarray(v)).to(dtype)
+    return sd

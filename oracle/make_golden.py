@@ -1,0 +1,262 @@
+"""TEST INFRASTRUCTURE ONLY -- generate `tests/golden/*.npz` from the REAL reference.
+
+Run once in the build container (where /root/reference exists):
+    python oracle/make_golden.py
+It imports castacks/UniCeption @ 802ebc17 (pure PyTorch, CPU fp32), builds small instances of
+the hot-path modules with *seeded, machine-independent* weights
+(`dust3r_oracle.seeded_state_dict`, numpy RandomState), runs the reference's own forward /
+backward, and stores inputs + outputs (+ gradient digests).  It also asserts that the
+restatement in `oracle/dust3r_oracle.py` reproduces every vector (fp32, <= 2e-5 rel), which is
+what pins the oracle.  The fixtures carry only tensors and the config -- weights are
+re-derived from the seed by the tests.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import dust3r_oracle as O  # noqa: E402
+import ref_import  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def _img(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g).clamp_(-1, 1)
+
+
+def _load_seeded(module: nn.Module, seed: int):
+    shapes = {k: tuple(v.shape) for k, v in module.state_dict().items()}
+    sd = O.seeded_state_dict(shapes, seed)
+    module.load_state_dict(sd)
+    return {k: v.clone() for k, v in module.state_dict().items()}, shapes
+
+
+def _save(name, cfg, arrays):
+    os.makedirs(OUT, exist_ok=True)
+    arrays = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in arrays.items()}
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), cfg=json.dumps(cfg), **arrays)
+    print(f"wrote {name}.npz ({sum(a.nbytes for a in arrays.values())/1e6:.2f} MB raw)")
+
+
+def _check(tag, got, ref, tol=2e-5):
+    ma, rel = O.parity(got, ref)
+    print(f"  oracle vs reference [{tag}]: max-abs {ma:.3e} rel-L2 {rel:.3e}")
+    assert rel <= tol, (tag, ma, rel)
+
+
+def _grad_digest(params: dict):
+    """Per-parameter (sum, l2) digest of .grad, key-sorted, plus full grads of a few small tensors."""
+    keys = sorted(params)
+    dig = np.array([[float(params[k].grad.double().sum()), float(params[k].grad.double().norm())] for k in keys])
+    return keys, dig
+
+
+def golden_rope():
+    from uniception.models.libs.croco.pos_embed import RoPE2D
+
+    g = torch.Generator().manual_seed(7)
+    B, H, h, w, D = 2, 3, 5, 7, 64
+    tok = torch.randn(B, H, h * w, D, generator=g)
+    pos = O.patch_positions(B, h, w)
+    rope = RoPE2D(freq=100.0)
+    out = rope(tok, pos)
+    _check("rope2d fwd", O.rope2d(tok, pos, 100.0, 1.0), out, 1e-6)
+    # backward of the native module == forward with -F0 (curope2d.py:24-28): check via autograd on the fallback
+    t2 = tok.clone().requires_grad_(True)
+    gout = torch.randn(B, H, h * w, D, generator=g)
+    rope(t2, pos).backward(gout)
+    _check("rope2d bwd", O.rope2d(gout, pos, 100.0, -1.0), t2.grad, 1e-6)
+    arrays = dict(tokens=tok, positions=pos, out=out, grad_out=gout, grad_in=t2.grad)
+    # native CPU path of the reference (curope.cpp:11-47), when oracle/_ref was built
+    try:
+        sys.path.insert(0, os.path.join(HERE, "_ref"))
+        import curope  # type: ignore
+
+        t3 = tok.transpose(1, 2).contiguous().clone()  # [B,N,H,D] as curope2d.py:38 passes it
+        curope.rope_2d(t3, pos, 100.0, 1.0)
+        _check("rope2d vs native curope CPU", O.rope2d(tok, pos, 100.0, 1.0), t3.transpose(1, 2), 1e-6)
+        arrays["out_native_cpu"] = t3.transpose(1, 2).contiguous()
+    except Exception as e:  # pragma: no cover
+        print("  (native curope CPU not available:", repr(e)[:80], ")")
+    _save("rope2d", dict(base=100.0, B=B, H=H, h=h, w=w, D=D), arrays)
+
+
+def golden_index_ops():
+    from uniception.models.utils.intermediate_feature_return import feature_take_indices
+    from uniception.models.libs.croco.patch_embed import PositionGetter
+    from uniception.models.factory.dust3r import interleave, is_symmetrized
+    import torch.nn.functional as F
+
+    pos = PositionGetter()(2, 3, 5, "cpu")
+    assert torch.equal(pos, O.patch_positions(2, 3, 5))
+    x = torch.arange(2 * 16 * 3 * 2, dtype=torch.float32).view(2, 16, 3, 2)
+    ps = F.pixel_shuffle(x, 2)
+    assert torch.equal(ps, O.pixel_shuffle(x, 2))
+    cases = [(12, None), (12, 4), (12, [5, 8]), (24, [5, 11, 17, 23]), (12, [-1, -3])]
+    take = []
+    for n, ind in cases:
+        r = feature_take_indices(n, ind)
+        assert (list(r[0]), r[1]) == (O.feature_take_indices(n, ind)[0], O.feature_take_indices(n, ind)[1])
+        take.append(list(r[0]))
+    a, b = torch.arange(6.0).view(3, 2), -torch.arange(6.0).view(3, 2)
+    i1, i2 = interleave(a, b)
+    o1, o2 = O.interleave(a, b)
+    assert torch.equal(i1, o1) and torch.equal(i2, o2)
+    sym_cases = [([1], [2]), ([1, 2], [2, 1]), ([1, 2, 3, 4], [2, 1, 4, 3]), ([1, 2, 3, 4], [5, 6, 7, 8])]
+    sym = []
+    for s1, s2 in sym_cases:
+        r = is_symmetrized({"instance": s1}, {"instance": s2})
+        assert r == O.is_symmetrized(s1, s2)
+        sym.append(bool(r))
+    _save("index_ops", dict(take_cases=[[n, ind] for n, ind in cases], take=take, sym_cases=sym_cases, sym=sym),
+          dict(positions_2_3_5=pos, pixel_shuffle_in=x, pixel_shuffle_out=ps, inter_a=a, inter_b=b, inter_1=i1, inter_2=i2))
+
+
+def golden_encoder(name, C, depth, heads, hw, B, seed, indices=None):
+    from uniception.models.encoders.base import ViTEncoderInput
+    from uniception.models.encoders.croco import CroCoEncoder, CroCoIntermediateFeatureReturner
+
+    kw = dict(name="enc", data_norm_type="dust3r", img_size=hw, enc_embed_dim=C, enc_depth=depth, enc_num_heads=heads)
+    enc = CroCoEncoder(**kw) if indices is None else CroCoIntermediateFeatureReturner(indices=indices, intermediates_only=False, **kw)
+    sd, shapes = _load_seeded(enc, seed)
+    img = _img((B, 3, *hw), seed + 1)
+    out = enc(ViTEncoderInput(image=img, data_norm_type="dust3r"))
+    sdp = {"encoder." + k: v for k, v in sd.items()}
+    arrays = dict(img=img)
+    if indices is None:
+        feat = out.features
+        _check(name, O.croco_encoder(sdp, "encoder.", img, depth, heads), feat)
+    else:
+        feat, inter = out[0].features, [o.features for o in out[1]]
+        of, oi = O.croco_encoder(sdp, "encoder.", img, depth, heads, indices=indices)
+        _check(name, of, feat)
+        for i, (a, b) in enumerate(zip(oi, inter)):
+            _check(f"{name} inter{i}", a, b)
+            arrays[f"inter{i}"] = b
+    arrays["features"] = feat
+    _save(name, dict(C=C, depth=depth, heads=heads, hw=list(hw), B=B, seed=seed, indices=indices,
+                     shapes={k: list(v) for k, v in shapes.items()}), arrays)
+
+
+def _tiny_dust3r(head, C_enc, enc_depth, enc_heads, C_dec, dec_depth, dec_heads, hw, ifr_indices=(0, 1)):
+    """A real reference `DUSt3R` object with small sub-modules: bypass __init__ (which hard-codes
+    ViT-L) and run the reference's own unmodified `forward` (factory/dust3r.py:250-332)."""
+    from uniception.models.encoders.croco import CroCoEncoder
+    from uniception.models.factory.dust3r import DUSt3R
+    from uniception.models.info_sharing.cross_attention_transformer import (
+        MultiViewCrossAttentionTransformer, MultiViewCrossAttentionTransformerIFR)
+    from uniception.models.libs.croco.pos_embed import RoPE2D
+    from uniception.models.prediction_heads.adaptors import PointMapWithConfidenceAdaptor
+    from uniception.models.prediction_heads.dpt import DPTFeature, DPTRegressionProcessor
+    from uniception.models.prediction_heads.linear import LinearFeature
+
+    m = DUSt3R.__new__(DUSt3R)
+    nn.Module.__init__(m)
+    m.pred_head_type = head
+    m.rope = RoPE2D(freq=100.0)
+    m.encoder = CroCoEncoder(name="e", data_norm_type="dust3r", img_size=hw, enc_embed_dim=C_enc,
+                             enc_depth=enc_depth, enc_num_heads=enc_heads)
+    common = dict(name="i", input_embed_dim=C_enc, num_views=2, depth=dec_depth, dim=C_dec, num_heads=dec_heads,
+                  custom_positional_encoding=m.rope)
+    if head == "linear":
+        m.info_sharing = MultiViewCrossAttentionTransformer(**common)
+        m.head1 = LinearFeature(input_feature_dim=C_dec, output_dim=4, patch_size=16)
+        m.head2 = LinearFeature(input_feature_dim=C_dec, output_dim=4, patch_size=16)
+    else:
+        m.info_sharing = MultiViewCrossAttentionTransformerIFR(indices=list(ifr_indices), norm_intermediate=False, **common)
+        for k in (1, 2):
+            f = DPTFeature(patch_size=16, hooks=[0, 1, 2, 3], input_feature_dims=[C_enc] + [C_dec] * 3,
+                           layer_dims=[12, 24, 48, 96], feature_dim=32)
+            r = DPTRegressionProcessor(input_feature_dim=32, output_dim=4)
+            setattr(m, f"dpt_feature_head{k}", f)
+            setattr(m, f"dpt_regressor_head{k}", r)
+            setattr(m, f"head{k}", nn.Sequential(f, r))
+    m.adaptor = PointMapWithConfidenceAdaptor(name="pointmap", pointmap_mode="exp", pointmap_vmin=-float("inf"),
+                                              pointmap_vmax=float("inf"), confidence_type="exp",
+                                              confidence_vmin=1, confidence_vmax=float("inf"))
+    return m
+
+
+def golden_dust3r(name, head, seed, B=2, hw=(32, 48), C_enc=192, enc_depth=2, enc_heads=3, C_dec=128, dec_depth=3,
+                  dec_heads=2, symmetrized=False):
+    m = _tiny_dust3r(head, C_enc, enc_depth, enc_heads, C_dec, dec_depth, dec_heads, hw, ifr_indices=(0, 1))
+    sd, shapes = _load_seeded(m, seed)
+    img1, img2 = _img((B, 3, *hw), seed + 1), _img((B, 3, *hw), seed + 2)
+    if symmetrized:  # pairs (a,b),(b,a)
+        img1 = torch.stack((img1[0], img2[0]), 0).repeat(B // 2, 1, 1, 1)
+        img2 = torch.stack((img2[0], img1[0]), 0).repeat(B // 2, 1, 1, 1)
+        inst1, inst2 = ["a", "b"] * (B // 2), ["b", "a"] * (B // 2)
+    else:
+        inst1, inst2 = [str(i) for i in range(B)], [str(B + i) for i in range(B)]
+    v1 = {"img": img1, "instance": inst1, "data_norm_type": "dust3r"}
+    v2 = {"img": img2, "instance": inst2, "data_norm_type": "dust3r"}
+    r1, r2 = m(v1, v2)
+    loss = O.bench_loss(r1, r2)
+    loss.backward()
+    params = dict(m.named_parameters())  # (aliases de-duplicated by named_parameters)
+    gkeys, gdig = _grad_digest(params)
+
+    # the oracle on the same weights / inputs
+    osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    if head == "dpt":  # oracle heads read the un-aliased names
+        pass
+    o1, o2 = O.dust3r_forward(osd, img1, img2, enc_depth=enc_depth, enc_heads=enc_heads, dec_depth=dec_depth,
+                              dec_heads=dec_heads, head=head, instances=(inst1, inst2)) if head == "linear" else \
+        _oracle_dpt_forward(osd, img1, img2, enc_depth, enc_heads, dec_depth, dec_heads)
+    for k in r1:
+        _check(f"{name} res1.{k}", o1[k], r1[k])
+    for k in r2:
+        _check(f"{name} res2.{k}", o2[k], r2[k])
+    O.bench_loss(o1, o2).backward()
+    for k in ("encoder.patch_embed.proj.weight", "encoder.enc_blocks.0.attn.qkv.weight",
+              "info_sharing.multi_view_branches.1.0.cross_attn.projk.weight", "info_sharing.norm.weight"):
+        _check(f"{name} grad {k}", osd[k].grad, params[k].grad, 1e-4)
+    arrays = dict(img1=img1, img2=img2, pts3d_1=r1["pts3d"], conf_1=r1["conf"], pts3d_2=r2["pts3d_in_other_view"],
+                  conf_2=r2["conf"], loss=loss.detach(), grad_digest=gdig,
+                  grad_qkv0=params["encoder.enc_blocks.0.attn.qkv.weight"].grad,
+                  grad_patch=params["encoder.patch_embed.proj.weight"].grad,
+                  grad_projk=params["info_sharing.multi_view_branches.1.0.cross_attn.projk.weight"].grad)
+    _save(name, dict(head=head, seed=seed, B=B, hw=list(hw), C_enc=C_enc, enc_depth=enc_depth, enc_heads=enc_heads,
+                     C_dec=C_dec, dec_depth=dec_depth, dec_heads=dec_heads, inst1=inst1, inst2=inst2,
+                     ifr_indices=[0, 1], grad_keys=gkeys, shapes={k: list(v) for k, v in shapes.items()}), arrays)
+
+
+def _oracle_dpt_forward(sd, img1, img2, enc_depth, enc_heads, dec_depth, dec_heads):
+    """dust3r_forward(head='dpt') but with the tiny fixture's IFR indices (0,1) instead of (5,8)."""
+    B, _, H, W = img1.shape
+    feat = O.croco_encoder(sd, "encoder.", torch.cat((img1, img2), 0), enc_depth, enc_heads)
+    f1, f2 = feat.chunk(2, dim=0)
+    (d1, d2), inter = O.info_sharing(sd, "info_sharing.", [f1, f2], dec_depth, dec_heads, indices=[0, 1],
+                                     norm_intermediate=False)
+    o1 = O.dpt_regressor(sd, "dpt_regressor_head1.", O.dpt_feature(sd, "dpt_feature_head1.", [f1, inter[0][0], inter[1][0], d1]), (H, W))
+    o2 = O.dpt_regressor(sd, "dpt_regressor_head2.", O.dpt_feature(sd, "dpt_feature_head2.", [f2, inter[0][1], inter[1][1], d2]), (H, W))
+    p1, c1 = O.pointmap_conf_adaptor(o1)
+    p2, c2 = O.pointmap_conf_adaptor(o2)
+    return ({"pts3d": p1.permute(0, 2, 3, 1), "conf": c1.permute(0, 2, 3, 1)},
+            {"pts3d_in_other_view": p2.permute(0, 2, 3, 1), "conf": c2.permute(0, 2, 3, 1)})
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    ref_import.import_reference()
+    golden_index_ops()
+    golden_rope()
+    golden_encoder("encoder_tiny", C=128, depth=2, heads=2, hw=(32, 48), B=2, seed=11)
+    golden_encoder("encoder_tiny_ifr", C=128, depth=4, heads=2, hw=(48, 32), B=1, seed=12, indices=[1, 3])
+    # BASELINE.json configs[0]: ViT-B/16 encoder, one 224x224 image, CPU
+    golden_encoder("encoder_vitb16_224", C=768, depth=12, heads=12, hw=(224, 224), B=1, seed=13)
+    golden_dust3r("dust3r_tiny_linear", "linear", seed=21)
+    golden_dust3r("dust3r_tiny_linear_sym", "linear", seed=22, B=4, symmetrized=True)
+    golden_dust3r("dust3r_tiny_dpt", "dpt", seed=23, hw=(32, 32))
+
+
+if __name__ == "__main__":
+    main()
