@@ -1,0 +1,246 @@
+/* libuc_b200 -- C ABI of the B200-native DUSt3R two-view hot path.
+ *
+ * Drop-in boundary.  The reference (castacks/UniCeption @ 802ebc17) is pure
+ * PyTorch with ONE native entry point, the pybind function
+ *     curope.rope_2d(tokens[B,N,H,D], positions[B,N,2] int64, base, +-F0)        (curope.cpp:49-69)
+ * which `uc_rope2d` replaces 1:1.  Every other entry point below replaces a torch library call made
+ * by a reference module on the path; the file:line of the call it replaces is cited per function.
+ *
+ * Conventions (all functions):
+ *   - plain C, no torch types; raw DEVICE pointers + explicit sizes / leading dimensions (in elements);
+ *   - the caller allocates every output and workspace and passes its CUDA stream
+ *     (`torch.cuda.current_stream().cuda_stream`); functions are asynchronous, never synchronise,
+ *     never allocate device memory, and are CUDA-graph capturable;
+ *   - return 0 on success or a negative UC_ERR_* code; `uc_last_error` returns the message of the
+ *     last failure on the calling thread;
+ *   - there is NO CPU fallback: on a machine without an sm_100 GPU every compute call fails with
+ *     UC_ERR_CUDA.
+ */
+#ifndef UC_B200_H
+#define UC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* uc_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define UC_API __attribute__((visibility("default")))
+#else
+#define UC_API
+#endif
+
+#define UC_OK 0
+#define UC_ERR_BAD_SHAPE (-1)
+#define UC_ERR_BAD_DTYPE (-2)
+#define UC_ERR_CUDA (-3)
+#define UC_ERR_UNSUPPORTED (-4)
+
+#define UC_DTYPE_BF16 0
+#define UC_DTYPE_F32 1
+#define UC_DTYPE_F16 2
+
+UC_API int uc_version(void);
+/* Copies the last error message of this thread into buf (NUL-terminated); returns its length. */
+UC_API size_t uc_last_error(char* buf, size_t cap);
+/* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
+UC_API uint64_t uc_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * GEMM with fused epilogue: the tcgen05 tensor-core kernel behind every nn.Linear / 1x1 conv /
+ * patch-embed conv of the path (libs/croco/blocks.py:74-77,97-99; utils/transformer_blocks.py:76-79,
+ * 191-199,305-311; info_sharing/cross_attention_transformer.py:116; prediction_heads/linear.py:47-54;
+ * libs/croco/patch_embed.py:47) and their autograd dgrad / wgrad.
+ *
+ *   C[m,n] = epilogue( sum_k A(m,k) * B(n,k) )          bf16 operands, fp32 accumulation in TMEM
+ *
+ *   a_layout 0: A stored [m][k] (k contiguous, lda = row pitch)   1: A stored [k][m] (m contiguous)
+ *   b_layout 0: B stored [n][k] (k contiguous, ldb = row pitch)   1: B stored [k][n] (n contiguous)
+ *     forward  y = x W^T : A=x (0),  B=W (0)
+ *     dgrad   dx = dy W  : A=dy (0), B=W (1)   [k = out features]
+ *     wgrad   dW = dy^T x: A=dy (1), B=x (1)   [k = tokens], fp32 output, split-k + atomics
+ * Epilogue, applied in this order on the fp32 accumulator v (row m, column n):
+ *   UC_EPI_BIAS       v += bias[n]                          (fp32 bias)
+ *   UC_EPI_ROPE       2-D RoPE on columns n < rope_cols (head_dim 64; q|k thirds of a packed qkv):
+ *                     pair (i, i+16) inside each 32-column half-head rotated by
+ *                     rope_table[pos[m][half]][i] = (cos, sin)   (curope/kernels.cu:39-80)
+ *   UC_EPI_GELU       aux_out[m,n] = bf16(v);  v = gelu_erf(bf16(v))     (blocks.py:80-86)
+ *   UC_EPI_GELU_BWD   v *= gelu_erf'(aux_in[m,n])
+ *   UC_EPI_RESIDUAL   v += residual[m,n]                    (bf16, pitch ldc)
+ *   UC_EPI_ATOMIC     C += v with red.global.add (fp32 C only; implied when split_k > 1)
+ * ------------------------------------------------------------------------------------------ */
+#define UC_EPI_BIAS 1
+#define UC_EPI_ROPE 2
+#define UC_EPI_GELU 4
+#define UC_EPI_GELU_BWD 8
+#define UC_EPI_RESIDUAL 16
+#define UC_EPI_ATOMIC 32
+
+typedef struct {
+  const void* a;
+  const void* b;
+  void* c;
+  int32_t m, n, k;
+  int32_t a_layout, b_layout;
+  int64_t lda, ldb, ldc;
+  int32_t c_dtype;  /* UC_DTYPE_BF16 or UC_DTYPE_F32 */
+  int32_t epilogue; /* UC_EPI_* flags */
+  int32_t split_k;  /* >= 1; 0 = choose */
+  int32_t rope_cols;
+  const float* bias;          /* [n] fp32 */
+  const void* residual;       /* [m][ldc] bf16 */
+  void* aux_out;              /* [m][ldc] bf16 (UC_EPI_GELU pre-activation) */
+  const void* aux_in;         /* [m][ldc] bf16 (UC_EPI_GELU_BWD pre-activation) */
+  const int32_t* positions;   /* [m][2] int32 (y,x) per row (UC_EPI_ROPE) */
+  const float* rope_table;    /* [P][16][2] fp32 (cos,sin) from uc_rope2d_table */
+} uc_gemm_params;
+
+UC_API int uc_gemm(const uc_gemm_params* p, uc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 2-D RoPE.  uc_rope2d == curope.rope_2d (curope.cpp:49-69, kernels.cu:17-108): in place on
+ * tokens [B,N,H,D] (element strides given, so the [B,H,N,D] view of curope2d.py:38 works),
+ * positions [B,N,2] int64, fwd = +F0 (forward) / -F0 (backward).  fp32 angle math.
+ * uc_rope2d_table fills table[p][i] = (cos, sin)(p * fwd / base^(i/Q)) for p < P, i < Q.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  void* tokens;
+  const int64_t* positions;
+  int32_t B, N, H, D;
+  int64_t stride_b, stride_n, stride_h; /* element strides of tokens; D is contiguous */
+  int32_t dtype;
+  float base, fwd;
+} uc_rope2d_params;
+UC_API int uc_rope2d(const uc_rope2d_params* p, uc_stream_t stream);
+UC_API int uc_rope2d_table(float* table, int32_t P, int32_t Q, float base, float fwd, uc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LayerNorm over the last dim (nn.LayerNorm(C, eps=1e-6): encoders/croco.py:32,127;
+ * libs/croco/blocks.py:148,154; utils/transformer_blocks.py:569,587,589,607).
+ * fwd: y = (x-mean)*rstd*gamma + beta; x bf16/fp32 [rows][C], y bf16/fp32, stats fp32 [rows].
+ * bwd: dx = LN'(dy) (+ dres);  dgamma/dbeta are ACCUMULATED (atomicAdd) into fp32 [C] buffers.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* x;
+  void* y;
+  const float* gamma;
+  const float* beta;
+  float* mean;
+  float* rstd;
+  int32_t rows, C;
+  int32_t x_dtype, y_dtype;
+  float eps;
+} uc_layernorm_fwd_params;
+UC_API int uc_layernorm_fwd(const uc_layernorm_fwd_params* p, uc_stream_t stream);
+
+typedef struct {
+  const void* dy;   /* [rows][C] */
+  const void* x;    /* [rows][C] LN input */
+  const void* dres; /* optional [rows][C] bf16: extra gradient added to dx (residual path) */
+  void* dx;         /* [rows][C] bf16 */
+  const float* gamma;
+  const float* mean;
+  const float* rstd;
+  float* dgamma; /* [C] fp32, accumulated */
+  float* dbeta;  /* [C] fp32, accumulated */
+  int32_t rows, C;
+  int32_t dy_dtype, x_dtype;
+} uc_layernorm_bwd_params;
+UC_API int uc_layernorm_bwd(const uc_layernorm_bwd_params* p, uc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Attention core softmax(q k^T * scale) v, head_dim 64, no mask, replacing
+ * F.scaled_dot_product_attention (libs/croco/blocks.py:123; utils/transformer_blocks.py:244,373).
+ * q/k/v/o are token-major bf16 matrices: element (b, token, head, d) at
+ *   base + (b*N + token) * ld + head*64 + d     (so a packed qkv [B*N, 3C] works with 3 base pointers).
+ * RoPE has already been applied to q and k (fused into the producing GEMM's epilogue).
+ * lse [B][H][Nq] fp32 = log-sum-exp of the scaled scores (natural log), saved for backward.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;
+  float* lse;
+  int32_t B, H, Nq, Nk;
+  int64_t ldq, ldk, ldv, ldo;
+  float scale;
+} uc_attn_fwd_params;
+UC_API int uc_attn_fwd(const uc_attn_fwd_params* p, uc_stream_t stream);
+
+typedef struct {
+  const void* q;
+  const void* k;
+  const void* v;
+  const void* o;
+  const void* d_o;
+  const float* lse;
+  float* delta;   /* workspace [B][H][Nq] fp32 */
+  float* dq_acc;  /* workspace [B*Nq][H*64] fp32, zeroed by the call */
+  void* dq;
+  void* dk;
+  void* dv;       /* bf16 outputs, same addressing as q/k/v with lddq/lddk/lddv */
+  int32_t B, H, Nq, Nk;
+  int64_t ldq, ldk, ldv, ldo, lddq, lddk, lddv;
+  float scale;
+  /* optional inverse RoPE on dq / dk (gradient w.r.t. the un-rotated projections) */
+  const int32_t* q_positions; /* [B*Nq][2] or NULL */
+  const int32_t* k_positions; /* [B*Nk][2] or NULL */
+  const float* rope_table;    /* forward table; the kernel uses (cos, -sin) */
+} uc_attn_bwd_params;
+UC_API int uc_attn_bwd(const uc_attn_bwd_params* p, uc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Patch-embed front end (libs/croco/patch_embed.py:68-82): gathers non-overlapping p x p patches of
+ * an fp32 NCHW image into bf16 rows [B*h*w][3*p*p] (column order c, i, j == conv weight layout),
+ * so that the conv is `uc_gemm`.  Bit-exact gather + one bf16 rounding.
+ * ------------------------------------------------------------------------------------------ */
+UC_API int uc_patchify(const float* img, void* cols_bf16, int32_t B, int32_t C, int32_t H, int32_t W, int32_t patch,
+                uc_stream_t stream);
+
+/* column sums of a [rows][cols] matrix (bias gradients), ACCUMULATED into fp32 out[cols] */
+UC_API int uc_colsum(const void* x, int32_t x_dtype, int64_t ld, int32_t rows, int32_t cols, float* out, uc_stream_t stream);
+
+/* fp32 -> bf16 cast (weights), optionally transposing a [rows][cols] matrix */
+UC_API int uc_cast_bf16(const float* src, void* dst, int64_t n, uc_stream_t stream);
+/* bf16 [rows][C] <-> fp32 NCHW [B][C][hw] layout converters used at module boundaries
+ * (encoders/croco.py:177-180; info_sharing/cross_attention_transformer.py:222-225, :270-273) */
+UC_API int uc_nlc_to_nchw(const void* src, int32_t src_dtype, float* dst, int32_t B, int32_t L, int32_t C, uc_stream_t stream);
+UC_API int uc_nchw_to_nlc(const float* src, void* dst, int32_t dst_dtype, int32_t B, int32_t L, int32_t C, uc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Linear-head post-processing: pixel_shuffle(p) (prediction_heads/linear.py:81-82, bit-exact gather)
+ * fused with PointMapWithConfidenceAdaptor in exp/exp mode (prediction_heads/adaptors.py:337-342,
+ * :1080-1083) and the BCHW->BHWC permutes of factory/dust3r.py:323-330.
+ *   y  [B*h*w][4*p*p] fp32 (head GEMM output, column = c*p*p + i*p + j)
+ *   pts [B][h*p][w*p][3], conf [B][h*p][w*p][1] fp32
+ * bwd: dy from (dpts, dconf) and y.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* y;
+  float* pts;
+  float* conf;
+  int32_t B, h, w, patch;
+  float conf_min, conf_max; /* confidence = conf_min + min(exp(x), conf_max - conf_min) */
+} uc_head_post_fwd_params;
+UC_API int uc_head_post_fwd(const uc_head_post_fwd_params* p, uc_stream_t stream);
+
+typedef struct {
+  const float* y;
+  const float* dpts;
+  const float* dconf;
+  void* dy; /* [B*h*w][4*p*p] */
+  int32_t dy_dtype;
+  int32_t B, h, w, patch;
+  float conf_min, conf_max;
+} uc_head_post_bwd_params;
+UC_API int uc_head_post_bwd(const uc_head_post_bwd_params* p, uc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UC_B200_H */

@@ -1,0 +1,333 @@
+"""GPU bring-up probe: runs each kernel check in its OWN subprocess (a device trap poisons the CUDA
+context), with a timeout, and prints parity numbers against fp32 torch math on the same bf16 inputs.
+
+    python tools/probe.py            # all checks, each in a subprocess
+    python tools/probe.py gemm_tn    # one check in-process
+"""
+import math
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def _err(x, ref):
+    x, ref = x.double(), ref.double()
+    d = (x - ref)
+    return float(d.abs().max()), float(d.norm() / ref.norm().clamp_min(1e-30))
+
+
+def _report(name, x, ref, tol):
+    ma, rel = _err(x, ref)
+    ok = rel <= tol and math.isfinite(rel)
+    print(f"[{ 'OK ' if ok else 'BAD'}] {name}: max-abs {ma:.3e} rel-L2 {rel:.3e} (tol {tol:g})", flush=True)
+    return ok
+
+
+def _time(fn, iters=20, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def check_gemm_tn():
+    import torch
+    from uniception_b200 import ops
+    ok = True
+    for (m, n, k) in [(128, 256, 64), (256, 256, 128), (300, 384, 192), (3136, 1024, 768), (4096, 3072, 1024)]:
+        torch.manual_seed(0)
+        a = torch.randn(m, k, device="cuda").bfloat16()
+        b = torch.randn(n, k, device="cuda").bfloat16()
+        bias = torch.randn(n, device="cuda")
+        out = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(a, b, out, bias=bias)
+        ref = a.float() @ b.float().t() + bias
+        ok &= _report(f"gemm_tn {m}x{n}x{k} bf16 out", out.float(), ref, 5e-3)
+        out32 = torch.empty(m, n, device="cuda", dtype=torch.float32)
+        ops.gemm(a, b, out32)
+        ok &= _report(f"gemm_tn {m}x{n}x{k} f32 out", out32, a.float() @ b.float().t(), 1e-5)
+    return ok
+
+
+def check_gemm_dgrad():
+    import torch
+    from uniception_b200 import ops
+    ok = True
+    for (m, n, k) in [(128, 128, 64), (256, 256, 256), (300, 192, 384), (4096, 1024, 3072)]:
+        torch.manual_seed(1)
+        dy = torch.randn(m, k, device="cuda").bfloat16()       # [tokens, out]
+        w = torch.randn(k, n, device="cuda").bfloat16()        # W [out, in] stored [k][n]
+        out = torch.empty(m, n, device="cuda", dtype=torch.float32)
+        ops.gemm(dy, w, out, b_layout=1)
+        ok &= _report(f"gemm_dgrad {m}x{n}x{k}", out, dy.float() @ w.float(), 1e-5)
+    return ok
+
+
+def check_gemm_wgrad():
+    import torch
+    from uniception_b200 import ops
+    ok = True
+    for (tok, nout, nin) in [(64, 128, 128), (256, 128, 256), (392, 384, 192), (4096, 1024, 1024), (16384, 768, 3072)]:
+        torch.manual_seed(2)
+        dy = torch.randn(tok, nout, device="cuda").bfloat16()
+        x = torch.randn(tok, nin, device="cuda").bfloat16()
+        ref = dy.float().t() @ x.float()
+        out = torch.empty(nout, nin, device="cuda", dtype=torch.float32)
+        ops.gemm(dy, x, out, a_layout=1, b_layout=1, split_k=1)
+        ok &= _report(f"gemm_wgrad {nout}x{nin} over {tok} (store)", out, ref, 5e-5)
+        out.zero_()
+        ops.gemm(dy, x, out, a_layout=1, b_layout=1, atomic=True)
+        ok &= _report(f"gemm_wgrad {nout}x{nin} over {tok} (split-k atomic)", out, ref, 5e-5)
+    return ok
+
+
+def check_gemm_epilogues():
+    import torch
+    import dust3r_oracle as O
+    from uniception_b200 import ops
+    ok = True
+    torch.manual_seed(3)
+    m, n, k = 392, 512, 256
+    a = torch.randn(m, k, device="cuda").bfloat16()
+    b = (torch.randn(n, k, device="cuda") / math.sqrt(k)).bfloat16()
+    bias = torch.randn(n, device="cuda") * 0.1
+    res = torch.randn(m, n, device="cuda").bfloat16()
+    acc = a.float() @ b.float().t() + bias
+    out = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, out, bias=bias, residual=res)
+    ok &= _report("epilogue bias+residual", out.float(), acc + res.float(), 5e-3)
+    pre = torch.empty_like(out)
+    ops.gemm(a, b, out, bias=bias, gelu=True, aux_out=pre)
+    ok &= _report("epilogue gelu: pre-activation", pre.float(), acc, 5e-3)
+    ok &= _report("epilogue gelu: activation", out.float(), O.gelu_erf(pre.float()), 5e-3)
+    h = torch.randn(m, n, device="cuda").bfloat16()
+    hf = h.float().requires_grad_(True)
+    O.gelu_erf(hf).backward(torch.ones_like(hf))
+    ops.gemm(a, b, out, gelu_bwd=True, aux_in=h)
+    ok &= _report("epilogue gelu_bwd", out.float(), (a.float() @ b.float().t()) * hf.grad, 5e-3)
+    # RoPE epilogue on a packed qkv: heads of 64, q|k thirds rotated, v untouched
+    Bb, hh, ww, H = 2, 14, 14, 4
+    Cc = H * 64
+    N = hh * ww
+    x = torch.randn(Bb * N, k, device="cuda").bfloat16()
+    wqkv = (torch.randn(3 * Cc, k, device="cuda") / math.sqrt(k)).bfloat16()
+    bq = torch.randn(3 * Cc, device="cuda") * 0.1
+    pos = O.patch_positions(Bb, hh, ww, "cuda")
+    table = ops.rope2d_table(max(hh, ww), 100.0, 1.0, "cuda")
+    qkv = torch.empty(Bb * N, 3 * Cc, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(x, wqkv, qkv, bias=bq, positions=pos.reshape(-1, 2).int().contiguous(), rope_table=table, rope_cols=2 * Cc)
+    raw = (x.float() @ wqkv.float().t() + bq).view(Bb, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    refq, refk, refv = O.rope2d(raw[0], pos, 100.0), O.rope2d(raw[1], pos, 100.0), raw[2]
+    got = qkv.float().view(Bb, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ok &= _report("epilogue rope q", got[0], refq, 5e-3)
+    ok &= _report("epilogue rope k", got[1], refk, 5e-3)
+    ok &= _report("epilogue rope v (untouched)", got[2], refv, 5e-3)
+    return ok
+
+
+def check_elementwise():
+    import torch
+    import dust3r_oracle as O
+    from uniception_b200 import ops
+    ok = True
+    torch.manual_seed(4)
+    # rope2d standalone, fp32 + bf16, [B,H,N,D] view
+    B, H, hh, ww, D = 2, 3, 5, 7, 64
+    tok = torch.randn(B, H, hh * ww, D, device="cuda")
+    pos = O.patch_positions(B, hh, ww, "cuda")
+    t = tok.clone()
+    ops.rope2d_(t.transpose(1, 2), pos, 100.0, 1.0)
+    ok &= _report("rope2d fp32", t, O.rope2d(tok, pos, 100.0, 1.0), 1e-6)
+    ops.rope2d_(t.transpose(1, 2), pos, 100.0, -1.0)
+    ok &= _report("rope2d round trip", t, tok, 1e-6)
+    tb = tok.bfloat16()
+    ref = O.rope2d(tb.float(), pos, 100.0, 1.0)
+    ops.rope2d_(tb.transpose(1, 2), pos, 100.0, 1.0)
+    ok &= _report("rope2d bf16", tb.float(), ref, 4e-3)
+    # layernorm
+    for Cc in (128, 768, 1024):
+        x = (torch.randn(777, Cc, device="cuda") * 2 + 0.5).bfloat16()
+        g, bt = torch.randn(Cc, device="cuda"), torch.randn(Cc, device="cuda")
+        y, mean, rstd = ops.layernorm_fwd(x, g, bt, 1e-6, torch.float32)
+        ok &= _report(f"layernorm fwd C={Cc}", y, O.layer_norm(x.float(), g, bt), 1e-5)
+        xf = x.float().requires_grad_(True)
+        gp, bp = g.clone().requires_grad_(True), bt.clone().requires_grad_(True)
+        dy = torch.randn(777, Cc, device="cuda").bfloat16()
+        dres = torch.randn(777, Cc, device="cuda").bfloat16()
+        O.layer_norm(xf, gp, bp).backward(dy.float())
+        dg, db = torch.zeros(Cc, device="cuda"), torch.zeros(Cc, device="cuda")
+        dx = ops.layernorm_bwd(dy, x, g, mean, rstd, dg, db, dres=dres)
+        ok &= _report(f"layernorm bwd dx C={Cc}", dx.float(), xf.grad + dres.float(), 5e-3)
+        ok &= _report(f"layernorm bwd dgamma C={Cc}", dg, gp.grad, 1e-4)
+        ok &= _report(f"layernorm bwd dbeta C={Cc}", db, bp.grad, 1e-4)
+    # patchify (bit-exact gather + bf16 rounding)
+    img = torch.randn(2, 3, 32, 48, device="cuda")
+    cols = ops.patchify(img, 16)
+    ref = img.view(2, 3, 2, 16, 3, 16).permute(0, 2, 4, 1, 3, 5).reshape(12, 768).bfloat16()
+    print(f"[{'OK ' if torch.equal(cols, ref) else 'BAD'}] patchify bit-exact", flush=True)
+    ok &= torch.equal(cols, ref)
+    # colsum
+    x = torch.randn(1000, 768, device="cuda").bfloat16()
+    out = torch.zeros(768, device="cuda")
+    ops.colsum_(x, out)
+    ok &= _report("colsum", out, x.float().sum(0), 1e-5)
+    # cast, layout
+    w = torch.randn(1000, 37, device="cuda")
+    e = torch.equal(ops.cast_bf16(w), w.bfloat16())
+    print(f"[{'OK ' if e else 'BAD'}] cast_bf16 bit-exact", flush=True)
+    ok &= e
+    xl = torch.randn(2, 35, 72, device="cuda")
+    e = torch.equal(ops.nlc_to_nchw(xl, 5, 7), xl.permute(0, 2, 1).reshape(2, 72, 5, 7))
+    e &= torch.equal(ops.nchw_to_nlc(xl.permute(0, 2, 1).reshape(2, 72, 5, 7).contiguous(), torch.float32), xl)
+    print(f"[{'OK ' if e else 'BAD'}] nlc<->nchw bit-exact", flush=True)
+    ok &= e
+    # head post
+    Bb, hh, ww, p = 2, 3, 2, 16
+    y = torch.randn(Bb * hh * ww, 4 * p * p, device="cuda")
+    pts, conf = ops.head_post_fwd(y, Bb, hh, ww, p)
+    yr = y.clone().requires_grad_(True)
+    ybchw = yr.view(Bb, hh, ww, 4 * p * p).permute(0, 3, 1, 2)
+    rp, rc = O.pointmap_conf_adaptor(O.pixel_shuffle(ybchw, p))
+    ok &= _report("head_post pts", pts, rp.permute(0, 2, 3, 1), 1e-5)
+    ok &= _report("head_post conf", conf, rc.permute(0, 2, 3, 1), 1e-5)
+    gp_, gc_ = torch.randn_like(pts), torch.randn_like(conf)
+    (rp.permute(0, 2, 3, 1) * gp_).sum().add((rc.permute(0, 2, 3, 1) * gc_).sum()).backward()
+    dy = ops.head_post_bwd(y, gp_, gc_, Bb, hh, ww, p, dtype=torch.float32)
+    ok &= _report("head_post bwd", dy, yr.grad, 1e-5)
+    return ok
+
+
+def _attn_ref(q, k, v, scale):
+    s = (q @ k.transpose(-2, -1)) * scale
+    return s.softmax(-1) @ v
+
+
+def check_attn_fwd():
+    import torch
+    from uniception_b200 import ops
+    ok = True
+    for (B, H, Nq, Nk) in [(1, 1, 128, 128), (2, 3, 256, 256), (2, 2, 196, 196), (1, 2, 100, 300), (2, 4, 1024, 1024)]:
+        torch.manual_seed(5)
+        Cc = H * 64
+        qkv = torch.randn(B * max(Nq, Nk), 3 * Cc, device="cuda").bfloat16()
+        q, k, v = qkv[: B * Nq, :Cc], qkv[: B * Nk, Cc:2 * Cc], qkv[: B * Nk, 2 * Cc:]
+        o, lse = ops.attn_fwd(q, k, v, B, H, Nq, Nk, 0.125)
+        qf = q.float().reshape(B, Nq, H, 64).transpose(1, 2)
+        kf = k.float().reshape(B, Nk, H, 64).transpose(1, 2)
+        vf = v.float().reshape(B, Nk, H, 64).transpose(1, 2)
+        ref = _attn_ref(qf, kf, vf, 0.125).transpose(1, 2).reshape(B * Nq, Cc)
+        ok &= _report(f"attn_fwd B{B} H{H} Nq{Nq} Nk{Nk}", o.float(), ref, 6e-3)
+        lref = torch.logsumexp((qf @ kf.transpose(-2, -1)) * 0.125, dim=-1)
+        ok &= _report(f"attn_fwd lse", lse, lref, 1e-4)
+    return ok
+
+
+def check_attn_bwd():
+    import torch
+    import dust3r_oracle as O
+    from uniception_b200 import ops
+    ok = True
+    for (B, H, Nq, Nk, rope) in [(1, 1, 128, 128, False), (2, 2, 256, 256, False), (2, 2, 196, 196, True), (1, 2, 100, 300, False),
+                                 (1, 4, 1024, 1024, True)]:
+        torch.manual_seed(6)
+        Cc = H * 64
+        q = torch.randn(B * Nq, Cc, device="cuda").bfloat16()
+        k = torch.randn(B * Nk, Cc, device="cuda").bfloat16()
+        v = torch.randn(B * Nk, Cc, device="cuda").bfloat16()
+        do = torch.randn(B * Nq, Cc, device="cuda").bfloat16()
+        o, lse = ops.attn_fwd(q, k, v, B, H, Nq, Nk, 0.125)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        kw = {}
+        if rope:
+            hh = ww = int(math.isqrt(Nq))
+            pos = O.patch_positions(B, hh, ww, "cuda")
+            kw = dict(q_positions=pos.reshape(-1, 2).int().contiguous(), k_positions=pos.reshape(-1, 2).int().contiguous(),
+                      rope_table=ops.rope2d_table(hh, 100.0, 1.0, "cuda"))
+        ops.attn_bwd(q, k, v, o, do, lse, B, H, Nq, Nk, 0.125, dq, dk, dv, **kw)
+        qf = q.float().reshape(B, Nq, H, 64).transpose(1, 2).requires_grad_(True)
+        kf = k.float().reshape(B, Nk, H, 64).transpose(1, 2).requires_grad_(True)
+        vf = v.float().reshape(B, Nk, H, 64).transpose(1, 2).requires_grad_(True)
+        _attn_ref(qf, kf, vf, 0.125).backward(do.float().reshape(B, Nq, H, 64).transpose(1, 2))
+        gq, gk, gv = qf.grad, kf.grad, vf.grad
+        if rope:  # gradient w.r.t. the un-rotated tensors = inverse rotation of the gradient
+            gq, gk = O.rope2d(gq, pos, 100.0, -1.0), O.rope2d(gk, pos, 100.0, -1.0)
+        tag = f"attn_bwd B{B} H{H} Nq{Nq} Nk{Nk} rope={rope}"
+        ok &= _report(tag + " dq", dq.float(), gq.transpose(1, 2).reshape(B * Nq, Cc), 8e-3)
+        ok &= _report(tag + " dk", dk.float(), gk.transpose(1, 2).reshape(B * Nk, Cc), 8e-3)
+        ok &= _report(tag + " dv", dv.float(), gv.transpose(1, 2).reshape(B * Nk, Cc), 8e-3)
+    return ok
+
+
+def check_perf():
+    import torch
+    from uniception_b200 import ops
+    for (m, n, k) in [(16384, 3072, 1024), (16384, 1024, 1024), (16384, 4096, 1024), (16384, 1024, 4096), (8192, 768, 768), (8192, 3072, 768)]:
+        a = torch.randn(m, k, device="cuda").bfloat16()
+        b = torch.randn(n, k, device="cuda").bfloat16()
+        out = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+        bias = torch.zeros(n, device="cuda")
+        ms = _time(lambda: ops.gemm(a, b, out, bias=bias))
+        ms_t = _time(lambda: torch.nn.functional.linear(a, b))
+        print(f"[perf] gemm fwd {m}x{n}x{k}: {ms*1e3:.1f} us = {2*m*n*k/ms/1e9:.0f} TFLOP/s   (torch/cuBLAS {ms_t*1e3:.1f} us = {2*m*n*k/ms_t/1e9:.0f})", flush=True)
+        bt = b.t().contiguous()  # [k][n] -> dgrad-style B
+        out2 = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+        ms = _time(lambda: ops.gemm(a, bt, out2, b_layout=1))
+        print(f"[perf] gemm dgrad-layout {m}x{n}x{k}: {ms*1e3:.1f} us = {2*m*n*k/ms/1e9:.0f} TFLOP/s", flush=True)
+        dy = torch.randn(m, n, device="cuda").bfloat16()
+        dw = torch.zeros(n, k, device="cuda")
+        ms = _time(lambda: ops.gemm(dy, a, dw, a_layout=1, b_layout=1, atomic=True))
+        print(f"[perf] gemm wgrad {n}x{k} over {m}: {ms*1e3:.1f} us = {2*m*n*k/ms/1e9:.0f} TFLOP/s", flush=True)
+    for (B, H, N) in [(16, 16, 1024), (8, 12, 1024), (16, 16, 196)]:
+        Cc = H * 64
+        qkv = torch.randn(B * N, 3 * Cc, device="cuda").bfloat16()
+        q, k, v = qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:]
+        o, lse = ops.attn_fwd(q, k, v, B, H, N, N, 0.125)
+        ms = _time(lambda: ops.attn_fwd(q, k, v, B, H, N, N, 0.125, out=o))
+        fl = 4.0 * B * H * N * N * 64
+        print(f"[perf] attn_fwd B{B} H{H} N{N}: {ms*1e3:.1f} us = {fl/ms/1e9:.0f} TFLOP/s", flush=True)
+        do = torch.randn_like(o)
+        dqkv = torch.empty_like(qkv)
+        ms = _time(lambda: ops.attn_bwd(q, k, v, o, do, lse, B, H, N, N, 0.125, dqkv[:, :Cc], dqkv[:, Cc:2 * Cc], dqkv[:, 2 * Cc:]))
+        print(f"[perf] attn_bwd B{B} H{H} N{N}: {ms*1e3:.1f} us = {2.5*fl/ms/1e9:.0f} TFLOP/s", flush=True)
+        qh = q.reshape(B, N, H, 64).transpose(1, 2)
+        kh = k.reshape(B, N, H, 64).transpose(1, 2)
+        vh = v.reshape(B, N, H, 64).transpose(1, 2)
+        ms_t = _time(lambda: torch.nn.functional.scaled_dot_product_attention(qh, kh, vh))
+        print(f"[perf]   torch SDPA fwd: {ms_t*1e3:.1f} us = {fl/ms_t/1e9:.0f} TFLOP/s", flush=True)
+    x = torch.randn(16384, 1024, device="cuda").bfloat16()
+    g = torch.ones(1024, device="cuda")
+    ms = _time(lambda: ops.layernorm_fwd(x, g, g, 1e-6))
+    print(f"[perf] layernorm fwd 16384x1024: {ms*1e3:.1f} us = {2*x.numel()*2/ms/1e6:.0f} GB/s", flush=True)
+    return True
+
+
+CHECKS = ["gemm_tn", "gemm_dgrad", "gemm_wgrad", "gemm_epilogues", "elementwise", "attn_fwd", "attn_bwd", "perf"]
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] != "all":
+        import torch  # noqa: F401
+        ok = globals()["check_" + sys.argv[1]]()
+        sys.exit(0 if ok else 1)
+    results = {}
+    for name in CHECKS:
+        t0 = time.time()
+        print(f"===== {name} =====", flush=True)
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), name], timeout=300)
+            results[name] = r.returncode
+        except subprocess.TimeoutExpired:
+            results[name] = "timeout"
+        print(f"===== {name}: rc={results[name]} ({time.time()-t0:.0f}s) =====", flush=True)
+    print("SUMMARY", results)

@@ -1,0 +1,419 @@
+// Fused attention backward (uc_attn_bwd): dQ, dK, dV of softmax(q k^T * scale) v with recomputation,
+// head_dim 64.  Three kernels:
+//   1. attn_bwd_delta  : delta[q] = sum_d dO[q,d] * O[q,d]                       (memory-bound)
+//   2. attn_bwd_main   : one CTA per (128-key tile, batch*head), loop over 128-query tiles, all five
+//                        GEMMs on tcgen05, transposed formulation so that thread == key row:
+//        S^T  = K  Q_i^T     (SS)      dP^T = V dO_i^T     (SS)
+//        P^T  = exp2(S^T c - lse_i),   dS^T = P^T o (dP^T - delta_i)            (registers)
+//        dV  += P^T  dO_i    (TS: P^T  from TMEM, dO_i MN-major from the same smem tile)
+//        dK  += dS^T Q_i     (TS: dS^T from TMEM, Q_i  MN-major)
+//        dQ_i = dS   K       (SS: dS written to smem as an MN-major A tile, K MN-major) -> fp32 red.add
+//   3. attn_bwd_finish : dq = bf16(scale * dq_acc) with optional inverse 2-D RoPE  (memory-bound)
+// dK gets `scale` and the optional inverse RoPE in the main kernel's epilogue.
+//   warp 0: TMA producer | warp 1: MMA issuer | warps 2..5: softmax/dS (thread == key) |
+//   warps 6..9: dQ drain (TMEM -> red.global.add.v4.f32)
+// TMEM columns: S^T/P^T [0,128) | dP^T/dS^T [128,256) | dV [256,320) | dK [320,384) | dQ [384,448).
+#include "common.cuh"
+
+namespace uc {
+
+int make_head_map(CUtensorMap* m, const void* base, int H, int N, int B, long long ld, int box_rows);
+
+namespace {
+
+constexpr int BW_THREADS = 320;
+constexpr uint32_t BW_TILE = 128 * 64 * 2;  // 16 KB
+// smem: K, V, 2 x (Q, dO), dS (32 KB), 2 x (lse2, delta) floats, barriers
+constexpr uint32_t BW_OFF_K = 0, BW_OFF_V = BW_TILE, BW_OFF_QDO = 2 * BW_TILE, BW_OFF_DS = 6 * BW_TILE,
+                   BW_OFF_STATS = 8 * BW_TILE, BW_OFF_BAR = 8 * BW_TILE + 2048;
+constexpr uint32_t BW_SMEM = BW_OFF_BAR + 256 + 1024;
+constexpr uint32_t BT_SP = 0, BT_DP = 128, BT_DV = 256, BT_DK = 320, BT_DQ = 384, BT_COLS = 512;
+
+struct AttnBwdArgs {
+  const float* lse;
+  const float* delta;
+  float* dq_acc;
+  __nv_bfloat16* dk;
+  __nv_bfloat16* dv;
+  int B, H, Nq, Nk;
+  long long lddk, lddv;
+  float scale, scale_log2;
+  const int* k_positions;
+  const float* rope_table;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// delta[b][h][q] = sum_d dO * O ; 8 lanes per (token, head), 8 elements per lane
+__global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, float* __restrict__ delta,
+                                      int B, int H, int N, long long ldo, long long lddo) {
+  const long long total = (long long)B * N * H * 8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int sub = idx & 7;
+    const long long th = idx >> 3;
+    const int h = th % H;
+    const long long tok = th / H;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(o + tok * ldo + h * 64 + sub * 8));
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(d_o + tok * lddo + h * 64 + sub * 8));
+    float s = bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) + bf16_hi(a.y) * bf16_hi(g.y) +
+              bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) + bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (sub == 0) {
+      const int n = tok % N;
+      const int b = tok / N;
+      delta[((long long)b * H + h) * N + n] = s;
+    }
+  }
+}
+
+// dq = bf16(scale * dq_acc) with optional inverse RoPE; one thread per (token, head, 8-pair group)
+__global__ void attn_bwd_finish_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, long long rows, int H, long long lddq,
+                                       float scale, const int* __restrict__ pos, const float* __restrict__ table) {
+  // each thread: one 32-wide half-head: 16 (u,v) pairs
+  const long long total = rows * H * 2;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int half = idx & 1;
+    const int h = (idx >> 1) % H;
+    const long long row = (idx >> 1) / H;
+    const float4* src = reinterpret_cast<const float4*>(acc + row * (long long)H * 64 + h * 64 + half * 32);
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 t = __ldg(src + i);
+      v[4 * i] = t.x * scale; v[4 * i + 1] = t.y * scale; v[4 * i + 2] = t.z * scale; v[4 * i + 3] = t.w * scale;
+    }
+    if (pos) {
+      const float* tr = table + (long long)pos[2 * row + half] * 32;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float c = tr[2 * i], s = -tr[2 * i + 1];  // inverse rotation
+        const float u = v[i], w = v[i + 16];
+        v[i] = u * c - w * s;
+        v[i + 16] = w * c + u * s;
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(dq + row * lddq + h * 64 + half * 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 t;
+      t.x = pack_bf16(v[8 * i], v[8 * i + 1]); t.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+      t.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]); t.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+      dst[i] = t;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(BW_THREADS, 1)
+attn_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const AttnBwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sK = smem_base + BW_OFF_K, sV = smem_base + BW_OFF_V, sDS = smem_base + BW_OFF_DS;
+  auto sQ = [&](int st) { return smem_base + BW_OFF_QDO + st * 2 * BW_TILE; };
+  auto sdO = [&](int st) { return smem_base + BW_OFF_QDO + st * 2 * BW_TILE + BW_TILE; };
+  float* stats = reinterpret_cast<float*>(smem_gen + BW_OFF_STATS);  // [2 stages][2][128]
+  const uint32_t bar = smem_base + BW_OFF_BAR;
+  const uint32_t kv_full = bar;
+  auto qdo_full = [&](int st) { return bar + 8u * (1 + st); };
+  auto qdo_empty = [&](int st) { return bar + 8u * (3 + st); };
+  const uint32_t sdp_full = bar + 8u * 5, ds_ready = bar + 8u * 6, dq_full = bar + 8u * 7, dq_free = bar + 8u * 8,
+                 fin_full = bar + 8u * 9, tmem_slot = bar + 8u * 10;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv0 = blockIdx.x * 128;
+  const int bh = blockIdx.y;
+  const int b = bh / a.H, h = bh % a.H;
+  const int num_q_tiles = (a.Nq + 127) / 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(qdo_full(s), 1); mbar_init(qdo_empty(s), 1); }
+    mbar_init(sdp_full, 1);
+    mbar_init(ds_ready, 4);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_free, 4);
+    mbar_init(fin_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BT_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_full, 2 * BW_TILE);
+      tma_load_3d(sK, &tmK, kv_full, h * 64, kv0, b);
+      tma_load_3d(sV, &tmV, kv_full, h * 64, kv0, b);
+      for (int i = 0; i < num_q_tiles; ++i) {
+        const int st = i & 1;
+        mbar_wait(qdo_empty(st), ((i >> 1) & 1) ^ 1u);
+        mbar_arrive_expect_tx(qdo_full(st), 2 * BW_TILE);
+        tma_load_3d(sQ(st), &tmQ, qdo_full(st), h * 64, i * 128, b);
+        tma_load_3d(sdO(st), &tmdO, qdo_full(st), h * 64, i * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);   // K-major x K-major
+      const uint32_t id_ts = umma_idesc_bf16(128, 64, 0, 1);   // A in TMEM, B MN-major
+      const uint32_t id_dq = umma_idesc_bf16(128, 64, 1, 1);   // A MN-major (dS in smem), B MN-major
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i < num_q_tiles; ++i) {
+        const int st = i & 1;
+        mbar_wait(qdo_full(st), (i >> 1) & 1);
+        tc_fence_after();
+        const uint64_t kd = umma_desc_kmajor(sK), vd = umma_desc_kmajor(sV);
+        const uint64_t qd = umma_desc_kmajor(sQ(st)), dod = umma_desc_kmajor(sdO(st));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tmem_base + BT_SP, kd + uint64_t(k * 2), qd + uint64_t(k * 2), id_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tmem_base + BT_DP, vd + uint64_t(k * 2), dod + uint64_t(k * 2), id_s, k > 0);
+        umma_commit(sdp_full);
+        mbar_wait(ds_ready, i & 1);
+        if (i > 0) mbar_wait(dq_free, (i - 1) & 1);
+        tc_fence_after();
+        const uint64_t do_mn = umma_desc_mnmajor(sdO(st), 8192), q_mn = umma_desc_mnmajor(sQ(st), 8192);
+        const uint64_t ds_mn = umma_desc_mnmajor(sDS, 16384), k_mn = umma_desc_mnmajor(sK, 8192);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ts(tmem_base + BT_DV, tmem_base + BT_SP + k * 8, do_mn + uint64_t(k * 128), id_ts, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ts(tmem_base + BT_DK, tmem_base + BT_DP + k * 8, q_mn + uint64_t(k * 128), id_ts, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_ss(tmem_base + BT_DQ, ds_mn + uint64_t(k * 128), k_mn + uint64_t(k * 128), id_dq, k > 0);
+        umma_commit(dq_full);
+        umma_commit(qdo_empty(st));
+      }
+      umma_commit(fin_full);
+    }
+  } else if (warp < 6) {
+    // ===================== softmax / dS: thread <-> key row =====================
+    const int lane_group = warp & 3;
+    const uint32_t lane_addr = uint32_t(lane_group * 32) << 16;
+    const int r = lane_group * 32 + lane;   // key row inside the tile
+    const int ct = threadIdx.x - 64;        // 0..127
+    const uint32_t ds_row = sDS + r * 128;
+    for (int i = 0; i < num_q_tiles; ++i) {
+      const int st = i & 1;
+      float* lse2 = stats + st * 256;
+      float* dl = lse2 + 128;
+      {
+        const int q = i * 128 + ct;
+        const bool ok = q < a.Nq;
+        const long long off = ((long long)b * a.H + h) * a.Nq + q;
+        lse2[ct] = ok ? a.lse[off] * 1.4426950408889634f : INFINITY;
+        dl[ct] = ok ? a.delta[off] : 0.f;
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(sdp_full, i & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32], dp[32];
+        tmem_ld32(tmem_base + lane_addr + BT_SP + c * 32, s);
+        tmem_ld32(tmem_base + lane_addr + BT_DP + c * 32, dp);
+        tmem_ld_wait();
+        uint32_t pk[16], dk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int q = c * 32 + 2 * j;
+          const float p0 = fast_exp2(__uint_as_float(s[2 * j]) * a.scale_log2 - lse2[q]);
+          const float p1 = fast_exp2(__uint_as_float(s[2 * j + 1]) * a.scale_log2 - lse2[q + 1]);
+          const float d0 = p0 * (__uint_as_float(dp[2 * j]) - dl[q]);
+          const float d1 = p1 * (__uint_as_float(dp[2 * j + 1]) - dl[q + 1]);
+          pk[j] = pack_bf16(p0, p1);
+          dk[j] = pack_bf16(d0, d1);
+        }
+        tmem_st16(tmem_base + lane_addr + BT_SP + c * 16, pk);
+        tmem_st16(tmem_base + lane_addr + BT_DP + c * 16, dk);
+        // dS -> smem as MN-major A tile: [q-block of 64][key row r][64 q] with the 128B swizzle
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int q8 = c * 4 + g;                  // 16-byte chunk index along q (0..15)
+          const uint32_t addr = ds_row + (q8 >> 3) * 16384 + (((q8 & 7) ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(dk[4 * g]), "r"(dk[4 * g + 1]),
+                       "r"(dk[4 * g + 2]), "r"(dk[4 * g + 3])
+                       : "memory");
+        }
+      }
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_ready);
+    }
+    // ---- epilogue: dV, dK (x scale, inverse RoPE) ----
+    mbar_wait(fin_full, 0);
+    tc_fence_after();
+    const int kv = kv0 + r;
+    const bool ok = kv < a.Nk;
+    const long long tok = (long long)b * a.Nk + kv;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + lane_addr + BT_DV + c * 32, v);
+      tmem_ld_wait();
+      if (ok) {
+        uint4* dst = reinterpret_cast<uint4*>(a.dv + tok * a.lddv + h * 64 + c * 32);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 t;
+          t.x = pack_bf16(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1]));
+          t.y = pack_bf16(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]));
+          t.z = pack_bf16(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
+          t.w = pack_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
+          dst[g] = t;
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + lane_addr + BT_DK + c * 32, raw);
+      tmem_ld_wait();
+      if (ok) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * a.scale;
+        if (a.k_positions) {
+          const float* tr = a.rope_table + (long long)a.k_positions[2 * tok + c] * 32;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float cs = tr[2 * j], sn = -tr[2 * j + 1];
+            const float u = v[j], w = v[j + 16];
+            v[j] = u * cs - w * sn;
+            v[j + 16] = w * cs + u * sn;
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(a.dk + tok * a.lddk + h * 64 + c * 32);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 t;
+          t.x = pack_bf16(v[8 * g], v[8 * g + 1]); t.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
+          t.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); t.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
+          dst[g] = t;
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== dQ drain: TMEM -> fp32 red.add =====================
+    const int lane_group = warp & 3;
+    const uint32_t lane_addr = uint32_t(lane_group * 32) << 16;
+    for (int i = 0; i < num_q_tiles; ++i) {
+      mbar_wait(dq_full, i & 1);
+      tc_fence_after();
+      const int q = i * 128 + lane_group * 32 + lane;
+      float* dst = a.dq_acc + ((long long)b * a.Nq + q) * (a.H * 64) + h * 64;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + lane_addr + BT_DQ + c * 32, v);
+        tmem_ld_wait();
+        if (q < a.Nq) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c * 32 + 4 * g), "f"(__uint_as_float(v[4 * g])),
+                         "f"(__uint_as_float(v[4 * g + 1])), "f"(__uint_as_float(v[4 * g + 2])), "f"(__uint_as_float(v[4 * g + 3]))
+                         : "memory");
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_free);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BT_COLS);
+  }
+}
+
+}  // namespace
+}  // namespace uc
+
+extern "C" int uc_attn_bwd(const uc_attn_bwd_params* p, uc_stream_t stream_) {
+  using namespace uc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  UC_REQUIRE(p && p->q && p->k && p->v && p->o && p->d_o && p->lse && p->delta && p->dq_acc && p->dq && p->dk && p->dv,
+             UC_ERR_BAD_SHAPE, "uc_attn_bwd: null pointer");
+  UC_REQUIRE(p->B > 0 && p->H > 0 && p->Nq > 0 && p->Nk > 0, UC_ERR_BAD_SHAPE, "uc_attn_bwd: bad shape");
+  UC_REQUIRE(p->ldq % 8 == 0 && p->ldk % 8 == 0 && p->ldv % 8 == 0 && p->ldo % 8 == 0 && p->lddq % 8 == 0 && p->lddk % 8 == 0 &&
+                 p->lddv % 8 == 0,
+             UC_ERR_BAD_SHAPE, "uc_attn_bwd: leading dimensions must be multiples of 8");
+  UC_REQUIRE((p->q_positions == nullptr && p->k_positions == nullptr) || p->rope_table, UC_ERR_BAD_SHAPE,
+             "uc_attn_bwd: positions given without rope_table");
+  const long long rows_q = (long long)p->B * p->Nq;
+  {
+    const long long total = rows_q * p->H * 8;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    attn_bwd_delta_kernel<<<(int)blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(p->o),
+                                                           static_cast<const __nv_bfloat16*>(p->d_o), p->delta, p->B, p->H, p->Nq,
+                                                           p->ldo, p->ldo);
+    int r = check_launch("uc_attn_bwd(delta)");
+    if (r) return r;
+  }
+  cudaError_t e = cudaMemsetAsync(p->dq_acc, 0, sizeof(float) * rows_q * p->H * 64, stream);
+  UC_REQUIRE(e == cudaSuccess, UC_ERR_CUDA, "uc_attn_bwd: memset failed: %s", cudaGetErrorString(e));
+
+  CUtensorMap tmQ, tmK, tmV, tmdO;
+  int r;
+  if ((r = make_head_map(&tmQ, p->q, p->H, p->Nq, p->B, p->ldq, 128))) return r;
+  if ((r = make_head_map(&tmK, p->k, p->H, p->Nk, p->B, p->ldk, 128))) return r;
+  if ((r = make_head_map(&tmV, p->v, p->H, p->Nk, p->B, p->ldv, 128))) return r;
+  if ((r = make_head_map(&tmdO, p->d_o, p->H, p->Nq, p->B, p->ldo, 128))) return r;
+  static bool configured = false;
+  if (!configured) {
+    e = cudaFuncSetAttribute(attn_bwd_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM);
+    UC_REQUIRE(e == cudaSuccess, UC_ERR_CUDA, "uc_attn_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  AttnBwdArgs a;
+  a.lse = p->lse; a.delta = p->delta; a.dq_acc = p->dq_acc;
+  a.dk = static_cast<__nv_bfloat16*>(p->dk);
+  a.dv = static_cast<__nv_bfloat16*>(p->dv);
+  a.B = p->B; a.H = p->H; a.Nq = p->Nq; a.Nk = p->Nk;
+  a.lddk = p->lddk; a.lddv = p->lddv;
+  a.scale = p->scale;
+  a.scale_log2 = p->scale * 1.4426950408889634f;
+  a.k_positions = p->k_positions;
+  a.rope_table = p->rope_table;
+  dim3 grid((p->Nk + 127) / 128, p->B * p->H);
+  attn_bwd_main_kernel<<<grid, BW_THREADS, BW_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, a);
+  if ((r = check_launch("uc_attn_bwd(main)"))) return r;
+  {
+    const long long total = rows_q * p->H * 2;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    attn_bwd_finish_kernel<<<(int)blocks, 256, 0, stream>>>(p->dq_acc, static_cast<__nv_bfloat16*>(p->dq), rows_q, p->H, p->lddq,
+                                                            p->scale, p->q_positions, p->rope_table);
+    r = check_launch("uc_attn_bwd(finish)");
+  }
+  return r;
+}

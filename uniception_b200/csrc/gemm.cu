@@ -1,0 +1,404 @@
+// tcgen05 GEMM with fused epilogue (uc_gemm): the kernel behind every Linear / 1x1-conv / patch-embed
+// of the DUSt3R path and their dgrad / wgrad.
+//
+//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier full/empty)
+//   warp 1      : MMA issuer     (one thread: tcgen05.mma kind::f16, 128 x BN x 16, fp32 accum in TMEM)
+//   warps 2..9  : epilogue       (tcgen05.ld -> bias / RoPE / GELU / GELU' / residual -> global)
+// Persistent CTAs (grid = #SMs), two TMEM accumulator buffers so the epilogue of tile i overlaps the
+// main loop of tile i+1.  Both operands may be K-major or MN-major (UMMA descriptor major bits), so
+// forward (x W^T), dgrad (dy W) and wgrad (dy^T x, split-K + fp32 red.add) share this one kernel without
+// any transposition pass.
+#include "common.cuh"
+
+namespace uc {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + NUM_EPI_WARPS * 32;
+
+struct GemmArgs {
+  int m, n, k;
+  int a_mn, b_mn;
+  int num_m, num_n, num_kb, split_k, kb_per_split;
+  int epilogue, c_f32, rope_cols;
+  long long ldc;
+  void* c;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* aux_out;
+  const __nv_bfloat16* aux_in;
+  const int* positions;
+  const float* rope_table;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr uint32_t A_BYTES = BM * BK * 2;
+  static constexpr uint32_t B_BYTES = BN * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;
+};
+
+__device__ __forceinline__ void load_row32_bf16(const __nv_bfloat16* p, float (&v)[32]) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 t = __ldg(q + i);
+    v[8 * i + 0] = bf16_lo(t.x); v[8 * i + 1] = bf16_hi(t.x);
+    v[8 * i + 2] = bf16_lo(t.y); v[8 * i + 3] = bf16_hi(t.y);
+    v[8 * i + 4] = bf16_lo(t.z); v[8 * i + 5] = bf16_hi(t.z);
+    v[8 * i + 6] = bf16_lo(t.w); v[8 * i + 7] = bf16_hi(t.w);
+  }
+}
+__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* p, const float (&v)[32]) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 t;
+    t.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
+    t.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+    t.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+    t.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+    q[i] = t;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int total = g.num_m * g.num_n * g.split_k;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const int split = item % g.split_k;
+        const int tile = item / g.split_k;
+        const int m0 = (tile % g.num_m) * BM;
+        const int n0 = (tile / g.num_m) * BN;
+        const int kb0 = split * g.kb_per_split;
+        const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + C::A_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          if (!g.a_mn) {
+            tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, full_bar(stage), m0 + j * 64, kb * BK);
+          }
+          if (!g.b_mn) {
+            tma_load_2d(sb, &tmB, full_bar(stage), kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, full_bar(stage), n0 + j * 64, kb * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(BM, BN, g.a_mn, g.b_mn);
+      const uint32_t a_step = g.a_mn ? (2048u >> 4) : (32u >> 4);  // descriptor start-address step per UMMA_K
+      const uint32_t b_step = g.b_mn ? (2048u >> 4) : (32u >> 4);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const int split = item % g.split_k;
+        const int kb0 = split * g.kb_per_split;
+        const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
+        if (kb0 >= kb1) continue;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint64_t adesc = g.a_mn ? umma_desc_mnmajor(sa, 8192) : umma_desc_kmajor(sa);
+          const uint64_t bdesc = g.b_mn ? umma_desc_mnmajor(sb, 8192) : umma_desc_kmajor(sb);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_ss(d_tmem, adesc + uint64_t(k * a_step), bdesc + uint64_t(k * b_step), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int e = warp - 2;
+    const int lane_group = warp & 3;          // TMEM lanes this warp may touch: 32*(warp%4)..
+    const int col_half = e >> 2;              // 0 / 1: which half of the BN columns
+    constexpr int CHUNKS = BN / 2 / 32;       // 32-column chunks per warp
+    const int epi = g.epilogue;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+      const int split = item % g.split_k;
+      const int tile = item / g.split_k;
+      const int m0 = (tile % g.num_m) * BM;
+      const int n0 = (tile / g.num_m) * BN;
+      const int kb0 = split * g.kb_per_split;
+      const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
+      if (kb0 >= kb1) continue;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m0 + lane_group * 32 + lane;
+      const bool row_ok = row < g.m;
+      int pos_y = 0, pos_x = 0;
+      if ((epi & UC_EPI_ROPE) && row_ok) {
+        pos_y = g.positions[2 * row];
+        pos_x = g.positions[2 * row + 1];
+      }
+#pragma unroll 1
+      for (int ch = 0; ch < CHUNKS; ++ch) {
+        const int col = col_half * (BN / 2) + ch * 32;
+        const int n = n0 + col;
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + (uint32_t(lane_group * 32) << 16) + uint32_t(acc * BN + col), r);
+        tmem_ld_wait();
+        if (n >= g.n || !row_ok) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (epi & UC_EPI_BIAS) {
+          const float4* b4 = reinterpret_cast<const float4*>(g.bias + n);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 b = __ldg(b4 + j);
+            v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        if ((epi & UC_EPI_ROPE) && n < g.rope_cols) {
+          const int p = ((n >> 5) & 1) ? pos_x : pos_y;
+          const float4* t4 = reinterpret_cast<const float4*>(g.rope_table + (size_t)p * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 cs = __ldg(t4 + j);  // (cos_{2j}, sin_{2j}, cos_{2j+1}, sin_{2j+1})
+            float u0 = v[2 * j], w0 = v[2 * j + 16];
+            v[2 * j] = u0 * cs.x - w0 * cs.y;
+            v[2 * j + 16] = w0 * cs.x + u0 * cs.y;
+            float u1 = v[2 * j + 1], w1 = v[2 * j + 17];
+            v[2 * j + 1] = u1 * cs.z - w1 * cs.w;
+            v[2 * j + 17] = w1 * cs.z + u1 * cs.w;
+          }
+        }
+        const size_t off = (size_t)row * g.ldc + n;
+        if (epi & UC_EPI_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = round_bf16(v[j]);
+          store_row32_bf16(g.aux_out + off, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (epi & UC_EPI_GELU_BWD) {
+          float h[32];
+          load_row32_bf16(g.aux_in + off, h);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(h[j]);
+        }
+        if (epi & UC_EPI_RESIDUAL) {
+          float h[32];
+          load_row32_bf16(g.residual + off, h);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += h[j];
+        }
+        if (g.c_f32) {
+          float* cp = reinterpret_cast<float*>(g.c) + off;
+          if (epi & UC_EPI_ATOMIC) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + 4 * j), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                           "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<float4*>(cp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        } else {
+          store_row32_bf16(reinterpret_cast<__nv_bfloat16*>(g.c) + off, v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, int grid, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM);
+    UC_REQUIRE(e == cudaSuccess, UC_ERR_CUDA, "uc_gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  gemm_kernel<BN><<<grid, GEMM_THREADS, Cfg<BN>::SMEM, stream>>>(tmA, tmB, g);
+  return check_launch("uc_gemm");
+}
+
+}  // namespace
+
+}  // namespace uc
+
+extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
+  using namespace uc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  UC_REQUIRE(p && p->a && p->b && p->c, UC_ERR_BAD_SHAPE, "uc_gemm: null operand");
+  UC_REQUIRE(p->m > 0 && p->n > 0 && p->k > 0, UC_ERR_BAD_SHAPE, "uc_gemm: bad sizes m=%d n=%d k=%d", p->m, p->n, p->k);
+  UC_REQUIRE(p->n % 64 == 0, UC_ERR_BAD_SHAPE, "uc_gemm: n=%d must be a multiple of 64", p->n);
+  UC_REQUIRE(p->lda % 8 == 0 && p->ldb % 8 == 0 && p->ldc % 8 == 0, UC_ERR_BAD_SHAPE,
+             "uc_gemm: leading dimensions must be multiples of 8 elements (lda=%lld ldb=%lld ldc=%lld)", (long long)p->lda,
+             (long long)p->ldb, (long long)p->ldc);
+  UC_REQUIRE(((uintptr_t)p->a % 16 == 0) && ((uintptr_t)p->b % 16 == 0) && ((uintptr_t)p->c % 16 == 0), UC_ERR_BAD_SHAPE,
+             "uc_gemm: operands must be 16-byte aligned");
+  UC_REQUIRE(p->c_dtype == UC_DTYPE_BF16 || p->c_dtype == UC_DTYPE_F32, UC_ERR_BAD_DTYPE, "uc_gemm: c_dtype %d", p->c_dtype);
+  const int epi = p->epilogue;
+  UC_REQUIRE(!(epi & UC_EPI_BIAS) || p->bias, UC_ERR_BAD_SHAPE, "uc_gemm: UC_EPI_BIAS without bias");
+  UC_REQUIRE(!(epi & UC_EPI_RESIDUAL) || p->residual, UC_ERR_BAD_SHAPE, "uc_gemm: UC_EPI_RESIDUAL without residual");
+  UC_REQUIRE(!(epi & UC_EPI_GELU) || (p->aux_out && p->c_dtype == UC_DTYPE_BF16), UC_ERR_BAD_SHAPE,
+             "uc_gemm: UC_EPI_GELU needs aux_out and bf16 C");
+  UC_REQUIRE(!(epi & UC_EPI_GELU_BWD) || p->aux_in, UC_ERR_BAD_SHAPE, "uc_gemm: UC_EPI_GELU_BWD without aux_in");
+  UC_REQUIRE(!(epi & UC_EPI_ROPE) || (p->positions && p->rope_table && p->rope_cols % 64 == 0), UC_ERR_BAD_SHAPE,
+             "uc_gemm: UC_EPI_ROPE needs positions, rope_table and rope_cols %% 64 == 0");
+  UC_REQUIRE(!(epi & UC_EPI_ATOMIC) || p->c_dtype == UC_DTYPE_F32, UC_ERR_BAD_DTYPE, "uc_gemm: atomic epilogue needs fp32 C");
+
+  const int num_m = (p->m + BM - 1) / BM;
+  const int num_kb = (p->k + BK - 1) / BK;
+  const int sms = sm_count();
+  // tile width: maximise (wave efficiency) x (per-tile MMA efficiency; narrow tiles are smem-bandwidth bound)
+  const bool atomic = (epi & UC_EPI_ATOMIC) != 0;
+  int bn = 64;
+  {
+    double best = -1.0;
+    const int cand[3] = {256, 128, 64};
+    const double rate[3] = {1.0, 0.9, 0.6};
+    for (int i = 0; i < 3; ++i) {
+      if (p->n % cand[i] != 0) continue;
+      const long long tiles = (long long)num_m * (p->n / cand[i]);
+      const long long waves = (tiles + sms - 1) / sms;
+      // split-K (wgrad) fills the machine by itself, so only the MMA efficiency matters there
+      const double eff = (atomic ? 1.0 : double(tiles) / double(waves * sms)) * rate[i];
+      if (eff > best) { best = eff; bn = cand[i]; }
+    }
+    if (best < 0) bn = 32;
+  }
+  UC_REQUIRE(bn != 32, UC_ERR_BAD_SHAPE, "uc_gemm: n=%d must be a multiple of 64", p->n);
+  const int num_n = p->n / bn;
+  int split_k = p->split_k;
+  if (split_k <= 0) {
+    split_k = 1;
+    if (atomic) {
+      const long long tiles = (long long)num_m * num_n;
+      split_k = (int)((sms + tiles - 1) / tiles);
+      if (split_k > num_kb / 4) split_k = num_kb / 4;
+      if (split_k < 1) split_k = 1;
+    }
+  }
+  UC_REQUIRE(split_k == 1 || ((epi & UC_EPI_ATOMIC) && epi == UC_EPI_ATOMIC), UC_ERR_BAD_SHAPE,
+             "uc_gemm: split_k > 1 requires the pure UC_EPI_ATOMIC epilogue");
+  if (split_k > num_kb) split_k = num_kb;
+  int kb_per = (num_kb + split_k - 1) / split_k;
+  split_k = (num_kb + kb_per - 1) / kb_per;
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2], strides[1];
+    uint32_t box[2];
+    if (!p->a_layout) { dims[0] = p->k; dims[1] = p->m; box[0] = BK; box[1] = BM; }
+    else { dims[0] = p->m; dims[1] = p->k; box[0] = 64; box[1] = BK; }
+    strides[0] = (uint64_t)p->lda * 2;
+    int r = make_tensor_map(&tmA, p->a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r) return r;
+    if (!p->b_layout) { dims[0] = p->k; dims[1] = p->n; box[0] = BK; box[1] = bn; }
+    else { dims[0] = p->n; dims[1] = p->k; box[0] = 64; box[1] = BK; }
+    strides[0] = (uint64_t)p->ldb * 2;
+    r = make_tensor_map(&tmB, p->b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r) return r;
+  }
+
+  GemmArgs g;
+  g.m = p->m; g.n = p->n; g.k = p->k;
+  g.a_mn = p->a_layout ? 1 : 0;
+  g.b_mn = p->b_layout ? 1 : 0;
+  g.num_m = num_m; g.num_n = num_n; g.num_kb = num_kb; g.split_k = split_k; g.kb_per_split = kb_per;
+  g.epilogue = epi; g.c_f32 = p->c_dtype == UC_DTYPE_F32; g.rope_cols = p->rope_cols;
+  g.ldc = p->ldc; g.c = p->c; g.bias = p->bias;
+  g.residual = static_cast<const __nv_bfloat16*>(p->residual);
+  g.aux_out = static_cast<__nv_bfloat16*>(p->aux_out);
+  g.aux_in = static_cast<const __nv_bfloat16*>(p->aux_in);
+  g.positions = p->positions; g.rope_table = p->rope_table;
+
+  const long long total = (long long)num_m * num_n * split_k;
+  const int grid = (int)(total < sms ? total : sms);
+  if (bn == 256) return launch<256>(tmA, tmB, g, grid, stream);
+  if (bn == 128) return launch<128>(tmA, tmB, g, grid, stream);
+  return launch<64>(tmA, tmB, g, grid, stream);
+}

@@ -1,0 +1,225 @@
+"""Raw (non-autograd) operator layer: torch tensors in, one C-ABI call each.
+
+PyTorch is used for device memory and streams only; every function below launches hand-written
+sm_100a kernels from `libuc_b200.so` on `torch.cuda.current_stream()`.  No function here has a
+CPU or library fallback: non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.bfloat16: L.UC_DTYPE_BF16, torch.float32: L.UC_DTYPE_F32, torch.float16: L.UC_DTYPE_F16}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("uniception_b200: tensors must live on a CUDA device (no CPU fallback)")
+
+
+def gemm(a, b, out, *, a_layout=0, b_layout=0, bias=None, residual=None, aux_out=None, aux_in=None,
+         positions=None, rope_table=None, rope_cols=0, gelu=False, gelu_bwd=False, atomic=False, split_k=0):
+    """out[m,n] = epilogue(sum_k A(m,k) B(n,k)); see include/uc_b200.h (uc_gemm).
+    a: [m,k] (a_layout 0) or [k,m] (1); b: [n,k] (0) or [k,n] (1); bf16, inner dim contiguous."""
+    _cuda(a, b, out)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16, "uc_gemm operands are bf16"
+    assert a.dim() == 2 and b.dim() == 2 and out.dim() == 2
+    assert a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1
+    m, k = (a.shape if a_layout == 0 else (a.shape[1], a.shape[0]))
+    n, kb = (b.shape if b_layout == 0 else (b.shape[1], b.shape[0]))
+    assert k == kb, f"contraction mismatch {k} vs {kb}"
+    assert out.shape[0] == m and out.shape[1] == n, f"out {tuple(out.shape)} != ({m},{n})"
+    epi = 0
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == n
+        epi |= L.EPI_BIAS
+    if rope_table is not None:
+        assert positions is not None and positions.dtype == torch.int32
+        epi |= L.EPI_ROPE
+    if gelu:
+        assert aux_out is not None and aux_out.stride(0) == out.stride(0)
+        epi |= L.EPI_GELU
+    if gelu_bwd:
+        assert aux_in is not None and aux_in.stride(0) == out.stride(0)
+        epi |= L.EPI_GELU_BWD
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.stride(0) == out.stride(0)
+        epi |= L.EPI_RESIDUAL
+    if atomic:
+        epi |= L.EPI_ATOMIC
+    p = L.GemmParams(
+        _ptr(a), _ptr(b), _ptr(out), m, n, k, a_layout, b_layout, a.stride(0), b.stride(0), out.stride(0),
+        _DT[out.dtype], epi, split_k, rope_cols,
+        _ptr(bias), _ptr(residual), _ptr(aux_out), _ptr(aux_in), _ptr(positions), _ptr(rope_table),
+    )
+    L.check(L.lib.uc_gemm(C.byref(p), _stream()))
+    return out
+
+
+def rope2d_(tokens_bnhd: torch.Tensor, positions: torch.Tensor, base: float, fwd: float):
+    """In place on a [B,N,H,D] tensor (any strides with D contiguous) == curope.rope_2d (curope.cpp:49-69)."""
+    _cuda(tokens_bnhd, positions)
+    # same checks as the reference's TORCH_CHECKs (curope.cpp:54-59)
+    if tokens_bnhd.dim() != 4:
+        raise RuntimeError("tokens must have 4 dimensions")
+    if positions.dim() != 3:
+        raise RuntimeError("positions must have 3 dimensions")
+    B, N, H, D = tokens_bnhd.shape
+    if positions.shape[0] != B or positions.shape[1] != N:
+        raise RuntimeError("batch size / seq_length differs between tokens & positions")
+    if positions.shape[2] != 2:
+        raise RuntimeError("positions.shape[2] must be equal to 2")
+    if tokens_bnhd.stride(3) != 1:
+        raise RuntimeError("tokens.stride(3) must be equal to 1")
+    if positions.dtype != torch.int64:
+        raise RuntimeError("positions must be int64")
+    positions = positions.contiguous()
+    p = L.Rope2dParams(_ptr(tokens_bnhd), _ptr(positions), B, N, H, D, tokens_bnhd.stride(0), tokens_bnhd.stride(1),
+                       tokens_bnhd.stride(2), _DT[tokens_bnhd.dtype], float(base), float(fwd))
+    L.check(L.lib.uc_rope2d(C.byref(p), _stream()))
+    return tokens_bnhd
+
+
+def rope2d_table(num_pos: int, base: float, f0: float, device, q: int = 16) -> torch.Tensor:
+    t = torch.empty(num_pos, q, 2, dtype=torch.float32, device=device)
+    L.check(L.lib.uc_rope2d_table(_ptr(t), num_pos, q, float(base), float(f0), _stream()))
+    return t
+
+
+def layernorm_fwd(x, gamma, beta, eps, out_dtype=torch.bfloat16, save_stats=True):
+    _cuda(x, gamma, beta)
+    C_ = x.shape[-1]
+    x2 = x.reshape(-1, C_)
+    assert x2.is_contiguous()
+    rows = x2.shape[0]
+    y = torch.empty_like(x2, dtype=out_dtype)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    p = L.LayerNormFwdParams(_ptr(x2), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), rows, C_,
+                             _DT[x2.dtype], _DT[out_dtype], float(eps))
+    L.check(L.lib.uc_layernorm_fwd(C.byref(p), _stream()))
+    return y.view(x.shape), mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dres=None):
+    """dx (bf16) = LN'(dy) [+ dres]; dgamma/dbeta (fp32 [C]) are accumulated in place."""
+    _cuda(dy, x, gamma)
+    C_ = x.shape[-1]
+    x2, dy2 = x.reshape(-1, C_), dy.reshape(-1, C_)
+    assert x2.is_contiguous() and dy2.is_contiguous()
+    if dres is not None:
+        assert dres.dtype == torch.bfloat16 and dres.is_contiguous()
+    dx = torch.empty_like(x2, dtype=torch.bfloat16)
+    p = L.LayerNormBwdParams(_ptr(dy2), _ptr(x2), _ptr(dres), _ptr(dx), _ptr(gamma), _ptr(mean), _ptr(rstd),
+                             _ptr(dgamma), _ptr(dbeta), x2.shape[0], C_, _DT[dy2.dtype], _DT[x2.dtype])
+    L.check(L.lib.uc_layernorm_bwd(C.byref(p), _stream()))
+    return dx.view(x.shape)
+
+
+def attn_fwd(q, k, v, B, H, Nq, Nk, scale, out=None):
+    """q: [B*Nq, >=H*64] bf16 view (row stride = ld), k/v: [B*Nk, ...]; returns (o [B*Nq, H*64], lse [B,H,Nq])."""
+    _cuda(q, k, v)
+    assert q.dtype == k.dtype == v.dtype == torch.bfloat16
+    assert q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1
+    o = torch.empty(B * Nq, H * 64, dtype=torch.bfloat16, device=q.device) if out is None else out
+    lse = torch.empty(B, H, Nq, dtype=torch.float32, device=q.device)
+    p = L.AttnFwdParams(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse), B, H, Nq, Nk,
+                        q.stride(0), k.stride(0), v.stride(0), o.stride(0), float(scale))
+    L.check(L.lib.uc_attn_fwd(C.byref(p), _stream()))
+    return o, lse
+
+
+def attn_bwd(q, k, v, o, d_o, lse, B, H, Nq, Nk, scale, dq, dk, dv, q_positions=None, k_positions=None, rope_table=None):
+    """Writes dq/dk/dv (bf16 views with the same addressing as q/k/v).  With positions + table the
+    gradients are returned w.r.t. the *un-rotated* projections (inverse RoPE fused)."""
+    _cuda(q, k, v, o, d_o, lse, dq, dk, dv)
+    assert d_o.dtype == torch.bfloat16 and d_o.stride(0) == o.stride(0) and d_o.stride(1) == 1
+    delta = torch.empty(B, H, Nq, dtype=torch.float32, device=q.device)
+    dq_acc = torch.empty(B * Nq, H * 64, dtype=torch.float32, device=q.device)
+    p = L.AttnBwdParams(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(d_o), _ptr(lse), _ptr(delta), _ptr(dq_acc),
+                        _ptr(dq), _ptr(dk), _ptr(dv), B, H, Nq, Nk,
+                        q.stride(0), k.stride(0), v.stride(0), o.stride(0), dq.stride(0), dk.stride(0), dv.stride(0),
+                        float(scale), _ptr(q_positions), _ptr(k_positions), _ptr(rope_table))
+    L.check(L.lib.uc_attn_bwd(C.byref(p), _stream()))
+    return dq, dk, dv
+
+
+def patchify(img: torch.Tensor, patch: int) -> torch.Tensor:
+    _cuda(img)
+    assert img.dtype == torch.float32 and img.is_contiguous()
+    B, Cc, H, W = img.shape
+    assert H % patch == 0, f"Input image height ({H}) is not a multiple of patch size ({patch})."
+    assert W % patch == 0, f"Input image width ({W}) is not a multiple of patch size ({patch})."
+    cols = torch.empty(B * (H // patch) * (W // patch), Cc * patch * patch, dtype=torch.bfloat16, device=img.device)
+    L.check(L.lib.uc_patchify(_ptr(img), _ptr(cols), B, Cc, H, W, patch, _stream()))
+    return cols
+
+
+def colsum_(x: torch.Tensor, out: torch.Tensor):
+    """out[cols] (fp32) += column sums of x [rows, cols]."""
+    _cuda(x, out)
+    assert x.dim() == 2 and x.stride(1) == 1 and out.dtype == torch.float32
+    L.check(L.lib.uc_colsum(_ptr(x), _DT[x.dtype], x.stride(0), x.shape[0], x.shape[1], _ptr(out), _stream()))
+    return out
+
+
+def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(src)
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    dst = torch.empty_like(src, dtype=torch.bfloat16) if out is None else out
+    L.check(L.lib.uc_cast_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()))
+    return dst
+
+
+def nlc_to_nchw(x: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """[B, L, C] (bf16/fp32) -> fp32 [B, C, h, w] (encoders/croco.py:177-180)."""
+    _cuda(x)
+    B, Lh, Cc = x.shape
+    assert x.is_contiguous() and Lh == h * w
+    out = torch.empty(B, Cc, h, w, dtype=torch.float32, device=x.device)
+    L.check(L.lib.uc_nlc_to_nchw(_ptr(x), _DT[x.dtype], _ptr(out), B, Lh, Cc, _stream()))
+    return out
+
+
+def nchw_to_nlc(x: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+    """fp32 [B, C, h, w] -> [B, h*w, C] (info_sharing/cross_attention_transformer.py:222-225)."""
+    _cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    B, Cc, h, w = x.shape
+    out = torch.empty(B, h * w, Cc, dtype=dtype, device=x.device)
+    L.check(L.lib.uc_nchw_to_nlc(_ptr(x), _ptr(out), _DT[dtype], B, h * w, Cc, _stream()))
+    return out
+
+
+def head_post_fwd(y: torch.Tensor, B: int, h: int, w: int, patch: int, conf_min=1.0, conf_max=math.inf):
+    _cuda(y)
+    assert y.dtype == torch.float32 and y.is_contiguous() and y.shape == (B * h * w, 4 * patch * patch)
+    pts = torch.empty(B, h * patch, w * patch, 3, dtype=torch.float32, device=y.device)
+    conf = torch.empty(B, h * patch, w * patch, 1, dtype=torch.float32, device=y.device)
+    p = L.HeadPostFwdParams(_ptr(y), _ptr(pts), _ptr(conf), B, h, w, patch, float(conf_min), float(conf_max))
+    L.check(L.lib.uc_head_post_fwd(C.byref(p), _stream()))
+    return pts, conf
+
+
+def head_post_bwd(y, dpts, dconf, B, h, w, patch, conf_min=1.0, conf_max=math.inf, dtype=torch.bfloat16):
+    _cuda(y, dpts, dconf)
+    dpts, dconf = dpts.contiguous(), dconf.contiguous()
+    dy = torch.empty(y.shape, dtype=dtype, device=y.device)
+    p = L.HeadPostBwdParams(_ptr(y), _ptr(dpts), _ptr(dconf), _ptr(dy), _DT[dtype], B, h, w, patch,
+                            float(conf_min), float(conf_max))
+    L.check(L.lib.uc_head_post_bwd(C.byref(p), _stream()))
+    return dy
