@@ -1,0 +1,283 @@
+"""Benchmark of the north-star metric: image-pairs/sec (forward + backward) of DUSt3R ViT-L/16 +
+12-layer two-view decoder + linear pointmap head at 512x512 (BASELINE.json configs[2]/[3]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs-per-gpu 8] [--size 512] [--impl b200|reference]
+
+One process per GPU (the driver launches torchrun for N > 1); weak scaling: 8 pairs per GPU.  A step =
+zero grads -> forward -> loss (sum of the four outputs, the `.sum().backward()` idiom of the
+reference's encoders/utils.py:29-31) -> backward (-> overlapped NCCL all-reduce of the flat gradient
+buffer when N > 1).  Prints ONE JSON line on rank 0.
+
+  value     pairs/s with the image batch already resident in HBM
+  e2e       same metric through the public `DUSt3R.forward(view1, view2)` call with HOST inputs:
+            pinned-host -> device copy of both image batches and a device -> host read of the loss
+            inside the timed region, every step
+  roofline  dominant kernel = the tcgen05 GEMM (82 % of the path's FLOPs): sum of its algorithmic
+            FLOPs / sum of its CUDA-event durations over instrumented steps, vs the measured cuBLAS
+            bf16 peak in MEASURED_PEAKS.json (sustained figure: the kernel is timed inside a long step)
+  cpu_baseline / --impl reference
+            the oracle port of the reference path (oracle/dust3r_oracle.py, fp32, all host threads) on a
+            bounded sample (1 pair at 512x512, forward + backward)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_PAIR = {512: 6.2137e12, 224: 1.0218e12}  # fwd+bwd, SURVEY.md 8d / BASELINE.md section 3
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), float(p["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 1400.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            busy = [s for s in sm if s > 0]
+            out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def _synthetic_pair_batch(B, S, seed):
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(B, 3, S, S, generator=g).clamp_(-1, 1)
+    b = torch.randn(B, 3, S, S, generator=g).clamp_(-1, 1)
+    return a, b
+
+
+def cpu_oracle_pairs_per_sec(S: int, steps: int, warmup: int, budget_s: float):
+    """Reference path on the host CPUs: fp32 oracle port, 1 pair per step, forward + backward."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dust3r_oracle as O
+    import uniception_b200 as U
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(42)
+    m = U.DUSt3R(name="dust3r", img_size=(S, S))  # parameter container only (CPU); arithmetic below is the oracle's
+    sd = {k: v.detach().requires_grad_(True) for k, v in m.state_dict().items()}
+    a, b = _synthetic_pair_batch(1, S, 1234)
+
+    def step():
+        for v in sd.values():
+            v.grad = None
+        r1, r2 = O.dust3r_forward(sd, a, b)
+        O.bench_loss(r1, r2).backward()
+
+    t0 = time.time()
+    step()  # first step doubles as warm-up / calibration
+    t_first = time.time() - t0
+    n = max(1, min(steps, int(max(0.0, budget_s - t_first) / max(t_first, 1e-3))))
+    ts = []
+    for _ in range(n):
+        t0 = time.time()
+        step()
+        ts.append(time.time() - t0)
+    t = statistics.mean(ts)
+    return 1.0 / t, cores, f"1 pair {S}x{S} fwd+bwd per step, {n} timed step(s) after 1 warm-up, fp32, {torch.get_num_threads()} threads", t, n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    v, cores, sample, t, n = cpu_oracle_pairs_per_sec(args.size, args.steps, args.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": "image-pairs/sec (fwd+bwd) DUSt3R ViT-L/16 512^2", "value": v, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"DUSt3R ViT-L/16 + 12-layer 2-view decoder + linear head, {args.size}x{args.size} pairs, fwd+bwd",
+                   "pairs_per_step": 1, "timed_steps_run": n},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import uniception_b200 as U
+    from uniception_b200 import _lib, dp, ops
+
+    rank, local, world = dp.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    S, B = args.size, args.pairs_per_gpu
+    torch.manual_seed(42)
+    model = U.DUSt3R(name="dust3r", img_size=(S, S)).to(dev)
+    pk = model.pack()
+    if world > 1:  # identical weights on every rank, then overlapped gradient all-reduce
+        dist.broadcast(pk.flat, src=0)
+        pk.grad_sync = dp.GradSync(pk.flat_grad, pk.index)
+    a_host, b_host = _synthetic_pair_batch(B, S, 1234 + rank)
+    a_host, b_host = a_host.pin_memory(), b_host.pin_memory()
+    a_dev, b_dev = a_host.to(dev), b_host.to(dev)
+    inst1 = [str(2 * i) for i in range(B)]
+    inst2 = [str(2 * i + 1) for i in range(B)]
+
+    def step(img1, img2):
+        pk.zero_grad()
+        r1, r2 = model({"img": img1, "instance": inst1, "data_norm_type": "dust3r"},
+                       {"img": img2, "instance": inst2, "data_norm_type": "dust3r"})
+        loss = r1["pts3d"].sum() + r1["conf"].sum() + r2["pts3d_in_other_view"].sum() + r2["conf"].sum()
+        loss.backward()
+        if pk.grad_sync is not None:
+            pk.grad_sync.finish()
+        return loss
+
+    def step_resident():
+        return step(a_dev, b_dev)
+
+    def step_e2e():
+        img1 = a_host.to(dev, non_blocking=True)
+        img2 = b_host.to(dev, non_blocking=True)
+        return float(step(img1, img2).item())  # device -> host read of the step's result
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms.item())
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = _lib.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop() if sampler else {}
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM), CUDA events on the launching stream ----
+    ops.PROFILE = []
+    for _ in range(2):
+        step_resident()
+    torch.cuda.synchronize()
+    gemm_ms = sum(s.elapsed_time(e) for (s, e, _f) in ops.PROFILE)
+    gemm_flop = sum(f for (_s, _e, f) in ops.PROFILE)
+    n_gemm = len(ops.PROFILE)
+    ops.PROFILE = None
+    sustained, burst, peak_src = _peaks()
+
+    if rank == 0:
+        pairs_per_s = world * B * args.steps / (ms / 1e3)
+        e2e_pairs = world * B * args.steps / (ms_e2e / 1e3)
+        achieved = gemm_flop / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        flop_pair = FLOP_PER_PAIR.get(S)
+        line = {
+            "metric": "image-pairs/sec (fwd+bwd) DUSt3R ViT-L/16 512^2", "value": pairs_per_s, "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"DUSt3R ViT-L/16 + 12-layer 2-view decoder + linear head, {S}x{S} pairs, fwd+bwd",
+                       "pairs_per_gpu": B, "global_pairs": B * world, "tokens_per_view": (S // 16) ** 2,
+                       "parallelism": f"dp{world}", "l2": "activations per step (>10 GB) far exceed the 126 MB L2; no flush needed",
+                       "grad_allreduce": "flat fp32 buffer, per-block buckets overlapped with backward" if world > 1 else "none"},
+            "e2e": {"value": e2e_pairs, "unit": "pairs/s", "h2d_bytes_per_step": int(a_host.numel() * 4 * 2),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches * world),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
+                         "frac": achieved / sustained if sustained else None, "traffic": None,
+                         "kernel": "uc::gemm_kernel<BN> (tcgen05.mma kind::f16, TMA, TMEM double-buffered epilogue)",
+                         "how": f"sum of 2*m*n*k over {n_gemm} uc_gemm launches of 2 instrumented steps / sum of CUDA-event durations on the launching stream",
+                         "peak_source": peak_src, "frac_of_burst_peak": achieved / burst if burst else None,
+                         "step_tflops": (pairs_per_s / world) * flop_pair / 1e12 if flop_pair else None,
+                         "step_frac_of_peak": (pairs_per_s / world) * flop_pair / 1e12 / sustained if flop_pair else None},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            v, cores, sample, _t, _n = cpu_oracle_pairs_per_sec(S, 1, 0, budget_s=25.0)
+            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--pairs-per-gpu", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,176 @@
+"""Parameter containers with the reference's state-dict keys for the transformer blocks on the path.
+
+`Mlp`, `Attention`, `Block` mirror libs/croco/blocks.py:64-161 (encoder flavour);
+`CrossAttention`, `CrossAttentionBlock` mirror utils/transformer_blocks.py:260-386, :517-647.
+Only the DUSt3R option set is implemented natively (qk_norm=False, LayerScale/DropPath identity,
+no scalable-softmax / entropy scaling, dropout 0, GELU, head_dim 64); other settings raise
+NotImplementedError at construction instead of silently running something else.
+
+The fused whole-module engines (encoders.py / info_sharing.py) never call these modules' forward:
+they read the parameters through a ParamPack.  The `forward` methods here exist so the blocks are
+usable on their own with the reference's call signature; they run the same kernels through
+`autograd_ops`.
+"""
+from __future__ import annotations
+
+from functools import partial
+from typing import Callable, Optional
+
+import torch
+import torch.nn as nn
+
+from . import autograd_ops as A
+from .rope import fusable_rope
+
+
+def _require(cond: bool, what: str):
+    if not cond:
+        raise NotImplementedError(f"uniception_b200: {what} is outside the B200 hot path (SURVEY.md 8f)")
+
+
+class Mlp(nn.Module):
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, bias=True, drop=0.0):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        _require(act_layer is nn.GELU, "a non-GELU activation")
+        _require(drop == 0.0 and bias is True, "dropout / bias-free MLP")
+        self.fc1 = nn.Linear(in_features, hidden_features, bias=True)
+        self.act = nn.GELU()
+        self.drop1 = nn.Identity()
+        self.fc2 = nn.Linear(hidden_features, out_features, bias=True)
+        self.drop2 = nn.Identity()
+
+    def forward(self, x, residual=None):
+        return A.mlp(x, self.fc1, self.fc2, residual)
+
+
+class Attention(nn.Module):
+    """Self-attention with both reference constructor flavours (`rope=` of libs/croco/blocks.py:90 and
+    `custom_positional_encoding=` of utils/transformer_blocks.py:141-156)."""
+
+    def __init__(self, dim, rope=None, num_heads=8, qkv_bias=False, attn_drop=0.0, proj_drop=0.0, qk_norm=False,
+                 custom_positional_encoding: Optional[Callable] = None, use_scalable_softmax=False, use_entropy_scaling=False,
+                 **_ignored):
+        super().__init__()
+        assert dim % num_heads == 0, "dim should be divisible by num_heads"
+        _require(dim // num_heads == 64, f"head_dim {dim // num_heads} (only 64)")
+        _require(not qk_norm and not use_scalable_softmax and not use_entropy_scaling, "qk_norm / softmax scaling options")
+        _require(attn_drop == 0.0 and proj_drop == 0.0, "attention dropout")
+        self.num_heads = num_heads
+        self.head_dim = dim // num_heads
+        self.scale = self.head_dim ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+        self.rope = rope if rope is not None else custom_positional_encoding
+        self.custom_positional_encoding = self.rope
+
+    def forward(self, x, xpos=None, residual=None):
+        B, N, C = x.shape
+        if self.rope is not None:
+            assert xpos is not None, "Positions of tokens (xpos) are a required input when using custom positional encoding"
+        qkv = A.linear(x, self.qkv.weight, self.qkv.bias)
+        o = A.attention(qkv, qkv, B, N, N, self.num_heads, q_off=0, k_off=C, v_off=2 * C, qpos=xpos, kpos=xpos, rope=self.rope)
+        return A.linear(o, self.proj.weight, self.proj.bias, residual=residual)
+
+
+class Block(nn.Module):
+    """libs/croco/blocks.py:133-161."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=4.0, qkv_bias=False, drop=0.0, attn_drop=0.0, drop_path=0.0,
+                 act_layer=nn.GELU, norm_layer=nn.LayerNorm, rope=None):
+        super().__init__()
+        _require(drop_path == 0.0, "stochastic depth")
+        self.norm1 = norm_layer(dim)
+        self.attn = Attention(dim, rope=rope, num_heads=num_heads, qkv_bias=qkv_bias, attn_drop=attn_drop, proj_drop=drop)
+        self.drop_path = nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+
+    def forward(self, x, xpos):
+        x = self.attn(A.layer_norm(x, self.norm1), xpos, residual=x)  # residual add fused into the proj GEMM
+        x = self.mlp(A.layer_norm(x, self.norm2), residual=x)
+        return x
+
+
+class CrossAttention(nn.Module):
+    """utils/transformer_blocks.py:260-386."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, qk_norm=False, attn_drop=0.0, proj_drop=0.0,
+                 norm_layer=nn.LayerNorm, custom_positional_encoding=None, use_scalable_softmax=False,
+                 use_entropy_scaling=False, **_ignored):
+        super().__init__()
+        assert dim % num_heads == 0, "dim should be divisible by num_heads"
+        _require(dim // num_heads == 64, f"head_dim {dim // num_heads} (only 64)")
+        _require(not qk_norm and not use_scalable_softmax and not use_entropy_scaling, "qk_norm / softmax scaling options")
+        _require(attn_drop == 0.0 and proj_drop == 0.0, "attention dropout")
+        self.num_heads = num_heads
+        self.head_dim = dim // num_heads
+        self.scale = self.head_dim ** -0.5
+        self.projq = nn.Linear(dim, dim, bias=qkv_bias)
+        self.projk = nn.Linear(dim, dim, bias=qkv_bias)
+        self.projv = nn.Linear(dim, dim, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+        self.custom_positional_encoding = custom_positional_encoding
+
+    def forward(self, query, key, value, qpos=None, kpos=None, residual=None):
+        B, Nq, C = query.shape
+        Nk = key.shape[1]
+        q = A.linear(query, self.projq.weight, self.projq.bias)
+        k = A.linear(key, self.projk.weight, self.projk.bias)
+        v = A.linear(value, self.projv.weight, self.projv.bias)
+        kv = torch.cat((k, v), dim=-1)
+        o = A.attention(q, kv, B, Nq, Nk, self.num_heads, q_off=0, k_off=0, v_off=C, qpos=qpos, kpos=kpos,
+                        rope=self.custom_positional_encoding)
+        return A.linear(o, self.proj.weight, self.proj.bias, residual=residual)
+
+
+class CrossAttentionBlock(nn.Module):
+    """utils/transformer_blocks.py:517-647 (registration order kept: norm1, attn, norm_y, norm2, cross_attn, norm3, mlp)."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=4.0, qkv_bias=False, qk_norm=False, proj_drop=0.0, attn_drop=0.0,
+                 init_values=None, drop_path=0.0, act_layer=nn.GELU, norm_layer=nn.LayerNorm, mlp_layer=Mlp,
+                 custom_positional_encoding=None, norm_cross_tokens=True, use_scalable_softmax=False,
+                 use_entropy_scaling=False, base_token_count_for_entropy_scaling=444, entropy_scaling_growth_factor=1.4):
+        super().__init__()
+        _require(not init_values, "LayerScale")
+        _require(drop_path == 0.0, "stochastic depth")
+        _require(mlp_layer is Mlp, "a custom mlp_layer")
+        common = dict(num_heads=num_heads, qkv_bias=qkv_bias, qk_norm=qk_norm, attn_drop=attn_drop, proj_drop=proj_drop,
+                      custom_positional_encoding=custom_positional_encoding, use_scalable_softmax=use_scalable_softmax,
+                      use_entropy_scaling=use_entropy_scaling)
+        self.norm1 = norm_layer(dim)
+        self.attn = Attention(dim, **common)
+        self.ls1 = nn.Identity()
+        self.drop_path1 = nn.Identity()
+        self.norm_y = norm_layer(dim) if norm_cross_tokens else nn.Identity()
+        self.custom_positional_encoding = custom_positional_encoding
+        self.norm2 = norm_layer(dim)
+        self.cross_attn = CrossAttention(dim, norm_layer=norm_layer, **common)
+        self.ls2 = nn.Identity()
+        self.drop_path2 = nn.Identity()
+        self.norm3 = norm_layer(dim)
+        self.mlp = mlp_layer(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=proj_drop)
+        self.ls3 = nn.Identity()
+        self.drop_path3 = nn.Identity()
+
+    def forward(self, x, y, xpos=None, ypos=None):
+        if self.custom_positional_encoding is not None:
+            assert xpos is not None, "Positions of tokens (xpos) are a required input when using custom positional encoding"
+            assert ypos is not None, "Positions of cross tokens (ypos) are a required input when using custom positional encoding"
+        x = self.attn(A.layer_norm(x, self.norm1), xpos, residual=x)
+        y_ = A.layer_norm(y, self.norm_y) if isinstance(self.norm_y, nn.LayerNorm) else y
+        x = self.cross_attn(A.layer_norm(x, self.norm2), y_, y_, xpos, ypos, residual=x)
+        x = self.mlp(A.layer_norm(x, self.norm3), residual=x)
+        return x
+
+
+def check_norm_layer(norm_layer) -> None:
+    """The engine implements nn.LayerNorm(dim, eps=1e-6) (encoders/croco.py:32); anything else is refused."""
+    probe = norm_layer(8)
+    _require(isinstance(probe, nn.LayerNorm) and abs(probe.eps - 1e-6) < 1e-12 and probe.elementwise_affine,
+             f"norm_layer {norm_layer}")
+
+
+DEFAULT_NORM = partial(nn.LayerNorm, eps=1e-6)
+__all__ = ["Mlp", "Attention", "Block", "CrossAttention", "CrossAttentionBlock", "fusable_rope"]

@@ -1,0 +1,402 @@
+"""Hand-scheduled forward / backward of the DUSt3R hot path on top of the C-ABI kernels (ops.py).
+
+Everything here works on token-major 2-D bf16 activations `[rows = B*N, C]`; all matrices come from a
+`ParamPack` (bf16 operand copies, fp32 gradient views).  Backward passes are written out explicitly
+(no autograd inside): they consume the tensors the forward saved and ACCUMULATE parameter gradients
+straight into the pack's flat fp32 gradient buffer (wgrad GEMM = split-K + red.add, bias grads =
+column sums, LayerNorm grads = atomics), which is what dp.py all-reduces.
+
+Reference arithmetic being reproduced (file:line under /root/reference/uniception/models):
+  encoder block   libs/croco/blocks.py:105-130, :158-161
+  decoder block   utils/transformer_blocks.py:208-257, :320-386, :617-647
+  encoder         encoders/croco.py:147-182;  decoder  info_sharing/cross_attention_transformer.py:191-275
+  linear head     prediction_heads/linear.py:61-84 + adaptors.py:337-342, :1080-1083
+Autocast dtype map reproduced by hand: bf16 residual stream / GEMM operands, fp32 accumulation,
+fp32 LayerNorm statistics, fp32 softmax, fp32 RoPE angle math, fp32 head output + adaptor.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .params import ParamPack
+
+LN_EPS = 1e-6
+
+# ------------------------------------------------------------------------------------------------
+# positions / rope tables (cached per device; index ops, bit-exact)
+# ------------------------------------------------------------------------------------------------
+_pos_cache: Dict[Tuple, torch.Tensor] = {}
+_table_cache: Dict[Tuple, torch.Tensor] = {}
+
+
+def grid_positions(b: int, h: int, w: int, device, dtype=torch.int32) -> torch.Tensor:
+    """[(b*h*w), 2] (y, x), y outer -- libs/croco/patch_embed.py:25-31, keyed by device too."""
+    key = (b, h, w, str(device), dtype)
+    t = _pos_cache.get(key)
+    if t is None:
+        ys = torch.arange(h, device=device, dtype=dtype).repeat_interleave(w)
+        xs = torch.arange(w, device=device, dtype=dtype).repeat(h)
+        t = torch.stack([ys, xs], dim=-1).repeat(b, 1).contiguous()
+        _pos_cache[key] = t
+    return t
+
+
+def rope_table(num_pos: int, base: float, f0: float, device) -> torch.Tensor:
+    key = (num_pos, float(base), float(f0), str(device))
+    t = _table_cache.get(key)
+    if t is None:
+        t = ops.rope2d_table(num_pos, base, f0, device)
+        _table_cache[key] = t
+    return t
+
+
+class Rope:
+    """Fused-RoPE context for a token grid: int32 positions [rows,2] + (cos,sin) table."""
+
+    def __init__(self, b: int, h: int, w: int, base: float, f0: float, device):
+        self.pos = grid_positions(b, h, w, device)
+        self.table = rope_table(max(h, w), base, f0, device)
+
+
+# ------------------------------------------------------------------------------------------------
+# linear helpers
+# ------------------------------------------------------------------------------------------------
+def _empty(rows, cols, like, dtype=torch.bfloat16):
+    return torch.empty(rows, cols, dtype=dtype, device=like.device)
+
+
+def linear_fwd(pk: ParamPack, name: str, x, *, residual=None, rope: Optional[Rope] = None, rope_cols=0, gelu=False,
+               out_dtype=torch.bfloat16, w16=None, bias=None):
+    w = pk.w16(name + ".weight") if w16 is None else w16
+    b = pk.w32(name + ".bias") if bias is None else bias
+    out = _empty(x.shape[0], w.shape[0], x, out_dtype)
+    if gelu:
+        pre = _empty(x.shape[0], w.shape[0], x)
+        ops.gemm(x, w, out, bias=b, gelu=True, aux_out=pre)
+        return out, pre
+    ops.gemm(x, w, out, bias=b, residual=residual,
+             positions=rope.pos if rope is not None else None, rope_table=rope.table if rope is not None else None,
+             rope_cols=rope_cols)
+    return out
+
+
+def linear_bwd(pk: ParamPack, name: str, dy, x_in, *, need_dx=True, gelu_pre=None, w16=None, wgrad=None, bgrad=None,
+               train_w=None):
+    """dy [rows, out] bf16, x_in [rows, in] bf16.  Accumulates dW, db; returns dx (bf16) or None.
+    gelu_pre: dx is additionally multiplied by gelu'(gelu_pre) (the producer of x_in was GELU)."""
+    w = pk.w16(name + ".weight") if w16 is None else w16
+    if train_w is None:
+        train_w = pk.requires_grad(name + ".weight")
+    if train_w:
+        gw = pk.grad(name + ".weight") if wgrad is None else wgrad
+        ops.gemm(dy, x_in, gw, a_layout=1, b_layout=1, atomic=True)
+        gb = pk.grad(name + ".bias") if bgrad is None else bgrad
+        ops.colsum_(dy, gb)
+    if not need_dx:
+        return None
+    dx = _empty(dy.shape[0], w.shape[1], dy)
+    if gelu_pre is not None:
+        ops.gemm(dy, w, dx, b_layout=1, gelu_bwd=True, aux_in=gelu_pre)
+    else:
+        ops.gemm(dy, w, dx, b_layout=1)
+    return dx
+
+
+def ln_fwd(pk: ParamPack, name: str, x, out_dtype=torch.bfloat16):
+    return ops.layernorm_fwd(x, pk.w32(name + ".weight"), pk.w32(name + ".bias"), LN_EPS, out_dtype)
+
+
+def ln_bwd(pk: ParamPack, name: str, dy, x, mean, rstd, dres=None):
+    train = pk.requires_grad(name + ".weight")
+    return ops.layernorm_bwd(dy, x, pk.w32(name + ".weight"), mean, rstd,
+                             pk.grad(name + ".weight") if train else None, pk.grad(name + ".bias") if train else None, dres=dres)
+
+
+# ------------------------------------------------------------------------------------------------
+# self-attention + MLP sub-blocks (shared by encoder and decoder blocks)
+# ------------------------------------------------------------------------------------------------
+def self_attn_fwd(pk, p, x, B, N, H, rope: Optional[Rope], norm: str, saved: list):
+    """x += proj(attn(rope(qkv(LN(x)))))  -- returns the new residual stream."""
+    C = H * 64
+    h1, mean, rstd = ln_fwd(pk, p + norm, x)
+    qkv = linear_fwd(pk, p + "attn.qkv", h1, rope=rope, rope_cols=2 * C)
+    o, lse = ops.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, H, N, N, 0.125)
+    x2 = linear_fwd(pk, p + "attn.proj", o, residual=x)
+    saved.append((x, mean, rstd, h1, qkv, o, lse))
+    return x2
+
+
+def self_attn_bwd(pk, p, dx2, B, N, H, rope: Optional[Rope], norm: str, saved):
+    """dx2: gradient w.r.t. the sub-block output (bf16).  Returns gradient w.r.t. its input."""
+    x, mean, rstd, h1, qkv, o, lse = saved
+    C = H * 64
+    d_o = linear_bwd(pk, p + "attn.proj", dx2, o)
+    dqkv = torch.empty_like(qkv)
+    ops.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, d_o, lse, B, H, N, N, 0.125,
+                 dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:],
+                 q_positions=rope.pos if rope is not None else None, k_positions=rope.pos if rope is not None else None,
+                 rope_table=rope.table if rope is not None else None)
+    d_h1 = linear_bwd(pk, p + "attn.qkv", dqkv, h1)
+    return ln_bwd(pk, p + norm, d_h1, x, mean, rstd, dres=dx2)
+
+
+def mlp_fwd(pk, p, x, norm: str, saved: list):
+    h, mean, rstd = ln_fwd(pk, p + norm, x)
+    act, pre = linear_fwd(pk, p + "mlp.fc1", h, gelu=True)
+    x2 = linear_fwd(pk, p + "mlp.fc2", act, residual=x)
+    saved.append((x, mean, rstd, h, pre, act))
+    return x2
+
+
+def mlp_bwd(pk, p, dx2, norm: str, saved):
+    x, mean, rstd, h, pre, act = saved
+    d_pre = linear_bwd(pk, p + "mlp.fc2", dx2, act, gelu_pre=pre)
+    d_h = linear_bwd(pk, p + "mlp.fc1", d_pre, h)
+    return ln_bwd(pk, p + norm, d_h, x, mean, rstd, dres=dx2)
+
+
+# ------------------------------------------------------------------------------------------------
+# encoder (encoders/croco.py:147-182)
+# ------------------------------------------------------------------------------------------------
+def encoder_fwd(pk: ParamPack, p: str, img: torch.Tensor, depth: int, heads: int, patch: int, rope_base: Optional[float],
+                rope_f0: float = 1.0, take: Sequence[int] = (), norm_intermediate: bool = True):
+    """img fp32 [B,3,H,W] -> (normalised tokens bf16 [B*N, C], intermediates, saved-for-backward)."""
+    B, _, Hh, Ww = img.shape
+    h, w = Hh // patch, Ww // patch
+    N = h * w
+    rope = Rope(B, h, w, rope_base, rope_f0, img.device) if rope_base is not None else None
+    cols = ops.patchify(img, patch)
+    wpe = pk.w16(p + "patch_embed.proj.weight")
+    x = _empty(cols.shape[0], wpe.shape[0], cols)
+    ops.gemm(cols, wpe, x, bias=pk.w32(p + "patch_embed.proj.bias"))
+    saved = {"cols": cols, "blocks": [], "B": B, "N": N, "rope": rope, "inter": []}
+    inter = []
+    for i in range(depth):
+        bs: list = []
+        bp = f"{p}enc_blocks.{i}."
+        x = self_attn_fwd(pk, bp, x, B, N, heads, rope, "norm1", bs)
+        x = mlp_fwd(pk, bp, x, "norm2", bs)
+        saved["blocks"].append(bs)
+        if i in take:
+            if norm_intermediate:
+                y, m, r = ln_fwd(pk, p + "enc_norm", x)
+                saved["inter"].append((i, x, m, r))
+                inter.append(y)
+            else:
+                saved["inter"].append((i, None, None, None))
+                inter.append(x)
+    y, mean, rstd = ln_fwd(pk, p + "enc_norm", x)
+    saved["final"] = (x, mean, rstd)
+    return y, inter, saved
+
+
+def encoder_bwd(pk: ParamPack, p: str, saved, d_out: Optional[torch.Tensor], depth: int, heads: int,
+                d_inter: Sequence[Optional[torch.Tensor]] = ()):
+    """d_out: gradient w.r.t. the normalised output tokens ([B*N, C] bf16 or fp32), or None."""
+    B, N, rope = saved["B"], saved["N"], saved["rope"]
+    x, mean, rstd = saved["final"]
+    dx = ln_bwd(pk, p + "enc_norm", d_out.contiguous(), x, mean, rstd) if d_out is not None else None
+    inter_at = {i: (k, xi, m, r) for k, (i, xi, m, r) in enumerate(saved["inter"])}
+    for i in reversed(range(depth)):
+        if i in inter_at:
+            k, xi, m, r = inter_at[i]
+            g = d_inter[k] if k < len(d_inter) else None
+            if g is not None:
+                g = g.contiguous()
+                if xi is not None:  # normalised intermediate: through the shared enc_norm
+                    dx = ln_bwd(pk, p + "enc_norm", g, xi, m, r, dres=dx)
+                else:
+                    dx = g.to(torch.bfloat16) if dx is None else (dx + g.to(torch.bfloat16))
+        if dx is None:
+            continue
+        bs = saved["blocks"][i]
+        bp = f"{p}enc_blocks.{i}."
+        dx = mlp_bwd(pk, bp, dx, "norm2", bs[1])
+        dx = self_attn_bwd(pk, bp, dx, B, N, heads, rope, "norm1", bs[0])
+        pk.notify_done(bp)  # this block's gradients are final -> its all-reduce bucket may start
+    if dx is not None and pk.requires_grad(p + "patch_embed.proj.weight"):
+        ops.gemm(dx, saved["cols"], pk.grad(p + "patch_embed.proj.weight"), a_layout=1, b_layout=1, atomic=True)
+        ops.colsum_(dx, pk.grad(p + "patch_embed.proj.bias"))
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+# two-view (N-view) cross-attention decoder (info_sharing/cross_attention_transformer.py:191-275)
+# ------------------------------------------------------------------------------------------------
+def _cross_fwd(pk, p, x, y, B, Nq, Nk, H, rope_q: Optional[Rope], rope_k: Optional[Rope], saved: list, has_norm_y: bool):
+    C = H * 64
+    if has_norm_y:
+        yn, ymean, yrstd = ln_fwd(pk, p + "norm_y", y)
+    else:
+        yn, ymean, yrstd = y, None, None
+    h2, mean, rstd = ln_fwd(pk, p + "norm2", x)
+    q = linear_fwd(pk, p + "cross_attn.projq", h2, rope=rope_q, rope_cols=C)
+    # projk | projv are adjacent in the pack -> one GEMM with N = 2C, RoPE on the k half only
+    wkv = pk.w16_rows(p + "cross_attn.projk.weight", p + "cross_attn.projv.weight")
+    bkv = pk.w32_span(p + "cross_attn.projk.bias", p + "cross_attn.projv.bias")
+    kv = linear_fwd(pk, "", yn, rope=rope_k, rope_cols=C, w16=wkv, bias=bkv)
+    o, lse = ops.attn_fwd(q, kv[:, :C], kv[:, C:], B, H, Nq, Nk, 0.125)
+    x2 = linear_fwd(pk, p + "cross_attn.proj", o, residual=x)
+    saved.append((x, mean, rstd, h2, q, kv, o, lse, y, yn, ymean, yrstd))
+    return x2
+
+
+def _cross_bwd(pk, p, dx2, B, Nq, Nk, H, rope_q, rope_k, saved, has_norm_y: bool):
+    """Returns (dx, d_yn): gradient w.r.t. the block's own stream and w.r.t. norm_y(y) (bf16)."""
+    x, mean, rstd, h2, q, kv, o, lse, y, yn, ymean, yrstd = saved
+    C = H * 64
+    d_o = linear_bwd(pk, p + "cross_attn.proj", dx2, o)
+    dq = torch.empty_like(q)
+    dkv = torch.empty_like(kv)
+    ops.attn_bwd(q, kv[:, :C], kv[:, C:], o, d_o, lse, B, H, Nq, Nk, 0.125, dq, dkv[:, :C], dkv[:, C:],
+                 q_positions=rope_q.pos if rope_q is not None else None,
+                 k_positions=rope_k.pos if rope_k is not None else None,
+                 rope_table=rope_q.table if rope_q is not None else None)
+    d_h2 = linear_bwd(pk, p + "cross_attn.projq", dq, h2)
+    wkv = pk.w16_rows(p + "cross_attn.projk.weight", p + "cross_attn.projv.weight")
+    gkv = pk.grad_span(p + "cross_attn.projk.weight", p + "cross_attn.projv.weight").view(2 * C, -1)
+    gbkv = pk.grad_span(p + "cross_attn.projk.bias", p + "cross_attn.projv.bias")
+    d_yn = linear_bwd(pk, "", dkv, yn, w16=wkv, wgrad=gkv, bgrad=gbkv, train_w=pk.requires_grad(p + "cross_attn.projk.weight"))
+    dx = ln_bwd(pk, p + "norm2", d_h2, x, mean, rstd, dres=dx2)
+    return dx, d_yn
+
+
+def decoder_fwd(pk: ParamPack, p: str, toks: List[torch.Tensor], B: int, h: int, w: int, depth: int, heads: int,
+                rope_base: Optional[float], rope_f0: float = 1.0, take: Sequence[int] = (), norm_intermediate: bool = True,
+                has_proj_embed: bool = True, has_norm_y: bool = True):
+    """toks: per-view bf16 [B*N, C_in].  Returns (per-view normalised bf16 [B*N, dim], intermediates, saved)."""
+    nv = len(toks)
+    N = h * w
+    dev = toks[0].device
+    rope = Rope(B, h, w, rope_base, rope_f0, dev) if rope_base is not None else None
+    rope_o = Rope(B * (nv - 1), h, w, rope_base, rope_f0, dev) if (rope_base is not None and nv > 2) else rope
+    saved = {"in": toks, "blocks": [], "B": B, "N": N, "nv": nv, "rope": rope, "rope_o": rope_o, "inter": [], "final": []}
+    xs = [linear_fwd(pk, p + "proj_embed", t) for t in toks] if has_proj_embed else list(toks)
+    inter = []
+    for k in range(depth):
+        new, lvl = [], []
+        for v in range(nv):
+            bp = f"{p}multi_view_branches.{v}.{k}."
+            bs: list = []
+            if nv == 2:
+                y = xs[1 - v]
+            else:  # other views concatenated along tokens, per batch element
+                y = torch.cat([xs[i].view(B, N, -1) for i in range(nv) if i != v], dim=1).reshape(B * N * (nv - 1), -1)
+            x = self_attn_fwd(pk, bp, xs[v], B, N, heads, rope, "norm1", bs)
+            x = _cross_fwd(pk, bp, x, y, B, N, N * (nv - 1), heads, rope, rope_o, bs, has_norm_y)
+            x = mlp_fwd(pk, bp, x, "norm3", bs)
+            new.append(x)
+            lvl.append(bs)
+        xs = new
+        saved["blocks"].append(lvl)
+        if k in take:
+            if norm_intermediate:
+                outs = []
+                for v in range(nv):
+                    yv, m, r = ln_fwd(pk, p + "norm", xs[v])
+                    outs.append(yv)
+                    saved["inter"].append((k, v, xs[v], m, r))
+                inter.append(outs)
+            else:
+                for v in range(nv):
+                    saved["inter"].append((k, v, None, None, None))
+                inter.append(list(xs))
+    outs = []
+    for v in range(nv):
+        yv, m, r = ln_fwd(pk, p + "norm", xs[v])
+        outs.append(yv)
+        saved["final"].append((xs[v], m, r))
+    return outs, inter, saved
+
+
+def decoder_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[torch.Tensor]], depth: int, heads: int,
+                d_inter: Sequence[Sequence[Optional[torch.Tensor]]] = (), has_proj_embed: bool = True, has_norm_y: bool = True,
+                need_input_grad: bool = True):
+    B, N, nv, rope, rope_o = saved["B"], saved["N"], saved["nv"], saved["rope"], saved["rope_o"]
+    dxs: List[Optional[torch.Tensor]] = [None] * nv
+    for v in range(nv):
+        if d_outs[v] is not None:
+            x, m, r = saved["final"][v]
+            dxs[v] = ln_bwd(pk, p + "norm", d_outs[v].contiguous(), x, m, r)
+    inter_levels = sorted({k for (k, _, _, _, _) in saved["inter"]})
+    for k in reversed(range(depth)):
+        if k in inter_levels:
+            li = inter_levels.index(k)
+            for (kk, v, xi, m, r) in saved["inter"]:
+                if kk != k:
+                    continue
+                g = d_inter[li][v] if li < len(d_inter) and d_inter[li] is not None else None
+                if g is None:
+                    continue
+                g = g.contiguous()
+                if xi is not None:
+                    dxs[v] = ln_bwd(pk, p + "norm", g, xi, m, r, dres=dxs[v])
+                else:
+                    dxs[v] = g.to(torch.bfloat16) if dxs[v] is None else dxs[v] + g.to(torch.bfloat16)
+        lvl = saved["blocks"][k]
+        d_own: List[Optional[torch.Tensor]] = [None] * nv
+        d_yn: List[Optional[torch.Tensor]] = [None] * nv
+        for v in range(nv):
+            if dxs[v] is None:
+                continue
+            bp = f"{p}multi_view_branches.{v}.{k}."
+            bs = lvl[v]
+            dx = mlp_bwd(pk, bp, dxs[v], "norm3", bs[2])
+            dx, d_yn[v] = _cross_bwd(pk, bp, dx, B, N, N * (nv - 1), heads, rope, rope_o, bs[1], has_norm_y)
+            d_own[v] = self_attn_bwd(pk, bp, dx, B, N, heads, rope, "norm1", bs[0])
+            if not has_norm_y:
+                pk.notify_done(bp)
+        # fold the cross-view gradients: d tokens_v(k-1) = d_own[v] + sum_{u != v} norm_y_u'(d_yn[u])|_v
+        new: List[Optional[torch.Tensor]] = list(d_own)
+        for u in range(nv):
+            if d_yn[u] is None:
+                continue
+            bp = f"{p}multi_view_branches.{u}.{k}."
+            y, yn, ymean, yrstd = lvl[u][1][8], lvl[u][1][9], lvl[u][1][10], lvl[u][1][11]
+            if nv == 2:
+                v = 1 - u
+                if has_norm_y:
+                    new[v] = ln_bwd(pk, bp + "norm_y", d_yn[u], y, ymean, yrstd, dres=new[v])
+                    pk.notify_done(bp)
+                else:
+                    new[v] = d_yn[u] if new[v] is None else new[v] + d_yn[u]
+            else:
+                dy = ln_bwd(pk, bp + "norm_y", d_yn[u], y, ymean, yrstd) if has_norm_y else d_yn[u]
+                parts = dy.view(B, nv - 1, N, -1)
+                others = [i for i in range(nv) if i != u]
+                for j, v in enumerate(others):
+                    g = parts[:, j].reshape(B * N, -1)
+                    new[v] = g.contiguous() if new[v] is None else new[v] + g
+        dxs = new
+    d_in: List[Optional[torch.Tensor]] = [None] * nv
+    for v in range(nv):
+        if dxs[v] is None:
+            continue
+        if has_proj_embed:
+            d_in[v] = linear_bwd(pk, p + "proj_embed", dxs[v], saved["in"][v], need_dx=need_input_grad)
+        else:
+            d_in[v] = dxs[v]
+    return d_in
+
+
+# ------------------------------------------------------------------------------------------------
+# linear head + pixel-shuffle + pointmap/confidence adaptor
+# ------------------------------------------------------------------------------------------------
+def linear_head_fwd(pk: ParamPack, p: str, tok: torch.Tensor, B: int, h: int, w: int, patch: int, conf_min: float, conf_max: float):
+    """tok bf16 [B*h*w, C] -> (pts [B,H,W,3], conf [B,H,W,1]) fp32."""
+    wt = pk.w16(p + "linear.weight")
+    y = _empty(tok.shape[0], wt.shape[0], tok, torch.float32)
+    ops.gemm(tok, wt, y, bias=pk.w32(p + "linear.bias"))
+    pts, conf = ops.head_post_fwd(y, B, h, w, patch, conf_min, conf_max)
+    return pts, conf, (tok, y)
+
+
+def linear_head_bwd(pk: ParamPack, p: str, saved, dpts, dconf, B, h, w, patch, conf_min, conf_max, need_dx=True):
+    tok, y = saved
+    dy = ops.head_post_bwd(y, dpts, dconf, B, h, w, patch, conf_min, conf_max)
+    dx = linear_bwd(pk, p + "linear", dy, tok, need_dx=need_dx)
+    pk.notify_done(p)
+    return dx

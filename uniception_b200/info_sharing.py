@@ -1,0 +1,239 @@
+"""Drop-in multi-view cross-attention transformer (reference:
+uniception/models/info_sharing/cross_attention_transformer.py, base.py).
+
+Same constructor signatures, dataclass I/O, assertions and state-dict keys as
+`MultiViewCrossAttentionTransformer` / `MultiViewCrossAttentionTransformerIFR`; per-view branches
+hold separate weights (deep copies re-initialised, :148-160).  Forward = B200 engine (engine.decoder_fwd).
+"""
+from __future__ import annotations
+
+from copy import deepcopy
+from dataclasses import dataclass
+from functools import partial
+from typing import Callable, List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from . import fused
+from .blocks import CrossAttentionBlock, Mlp, _require, check_norm_layer
+from .encoders import IntermediateFeatureReturner, PositionGetter, feature_take_indices
+from .params import ParamPack, get_pack
+from .rope import fusable_rope
+
+
+# ---- dataclasses: info_sharing/base.py:14-97 ----
+@dataclass
+class InfoSharingInput:
+    pass
+
+
+@dataclass
+class InfoSharingOutput:
+    pass
+
+
+@dataclass
+class MultiViewTransformerInput(InfoSharingInput):
+    features: List[torch.Tensor]  # per view [B, C_in, h, w]
+    additional_input_tokens: Optional[torch.Tensor] = None
+    additional_input_tokens_per_view: Optional[List[torch.Tensor]] = None
+
+
+@dataclass
+class MultiViewTransformerOutput(InfoSharingOutput):
+    features: List[torch.Tensor]  # per view [B, dim, h, w]
+    additional_token_features: Optional[torch.Tensor] = None
+    additional_token_features_per_view: Optional[List[torch.Tensor]] = None
+
+
+class UniCeptionInfoSharingBase(nn.Module):
+    def __init__(self, name: str, size: Optional[str] = None, *args, **kwargs):
+        super().__init__()
+        self.name = name
+        self.size = size
+
+
+class MultiViewCrossAttentionTransformer(UniCeptionInfoSharingBase):
+    "UniCeption Multi-View Cross-Attention Transformer on the B200 engine"
+
+    def __init__(
+        self,
+        name: str,
+        input_embed_dim: int,
+        num_views: int,
+        size: Optional[str] = None,
+        depth: int = 12,
+        dim: int = 768,
+        num_heads: int = 12,
+        mlp_ratio: float = 4.0,
+        qkv_bias: bool = True,
+        qk_norm: bool = False,
+        proj_drop: float = 0.0,
+        attn_drop: float = 0.0,
+        init_values: Optional[float] = None,
+        drop_path: float = 0.0,
+        act_layer: nn.Module = nn.GELU,
+        norm_layer: nn.Module = partial(nn.LayerNorm, eps=1e-6),
+        mlp_layer: nn.Module = Mlp,
+        custom_positional_encoding: Callable = None,
+        norm_cross_tokens: bool = True,
+        use_scalable_softmax: bool = False,
+        use_entropy_scaling: bool = False,
+        base_token_count_for_entropy_scaling: int = 444,
+        entropy_scaling_growth_factor: float = 1.4,
+        pretrained_checkpoint_path: str = None,
+        gradient_checkpointing: bool = False,
+        *args,
+        **kwargs,
+    ):
+        super().__init__(name=name, size=size, *args, **kwargs)
+        self.input_embed_dim = input_embed_dim
+        self.num_views = num_views
+        self.depth = depth
+        self.dim = dim
+        self.num_heads = num_heads
+        self.mlp_ratio = mlp_ratio
+        self.qkv_bias = qkv_bias
+        self.qk_norm = qk_norm
+        self.proj_drop = proj_drop
+        self.attn_drop = attn_drop
+        self.init_values = init_values
+        self.drop_path = drop_path
+        self.act_layer = act_layer
+        self.norm_layer = norm_layer
+        self.mlp_layer = mlp_layer
+        self.custom_positional_encoding = custom_positional_encoding
+        self.norm_cross_tokens = norm_cross_tokens
+        self.use_scalable_softmax = use_scalable_softmax
+        self.use_entropy_scaling = use_entropy_scaling
+        self.base_token_count_for_entropy_scaling = base_token_count_for_entropy_scaling
+        self.entropy_scaling_growth_factor = entropy_scaling_growth_factor
+        self.pretrained_checkpoint_path = pretrained_checkpoint_path
+        self.gradient_checkpointing = gradient_checkpointing
+        check_norm_layer(norm_layer)
+        _require(qkv_bias, "qkv_bias=False")
+        _require(not gradient_checkpointing,
+                 "gradient_checkpointing (raises AttributeError in the reference too, cross_attention_transformer.py:163-165)")
+        _require(custom_positional_encoding is None or fusable_rope(custom_positional_encoding) is not None,
+                 "a positional encoding that is not RoPE2D-compatible (needs .base/.F0) in the fused decoder")
+
+        if self.input_embed_dim != self.dim:
+            self.proj_embed = nn.Linear(self.input_embed_dim, self.dim, bias=True)
+        else:
+            self.proj_embed = nn.Identity()
+
+        blocks = nn.ModuleList(
+            [CrossAttentionBlock(dim=dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_norm=qk_norm,
+                                 proj_drop=proj_drop, attn_drop=attn_drop, init_values=init_values, drop_path=drop_path,
+                                 act_layer=act_layer, norm_layer=norm_layer, mlp_layer=mlp_layer,
+                                 custom_positional_encoding=custom_positional_encoding, norm_cross_tokens=norm_cross_tokens,
+                                 use_scalable_softmax=use_scalable_softmax, use_entropy_scaling=use_entropy_scaling)
+             for _ in range(depth)]
+        )
+        self.multi_view_branches = nn.ModuleList([blocks])
+        for _ in range(1, self.num_views):
+            self.multi_view_branches.append(deepcopy(blocks))
+        self.norm = self.norm_layer(self.dim)
+        if self.custom_positional_encoding is not None:
+            self.position_getter = PositionGetter()
+        self.initialize_weights()
+
+        if self.pretrained_checkpoint_path is not None:
+            print(f"Loading pretrained multi-view cross-attention transformer weights from {self.pretrained_checkpoint_path} ...")
+            ckpt = torch.load(self.pretrained_checkpoint_path, weights_only=False)
+            print(self.load_state_dict(ckpt["model"]))
+
+    def initialize_weights(self):
+        self.apply(self._init_weights)
+
+    def _init_weights(self, m):
+        if isinstance(m, nn.Linear):
+            torch.nn.init.xavier_uniform_(m.weight)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    # ---- engine entry ----
+    def _cfg(self, B, h, w, take=(), norm_intermediate=True):
+        fr = fusable_rope(self.custom_positional_encoding)
+        return dict(B=B, h=h, w=w, depth=self.depth, heads=self.num_heads, rope_base=fr[0] if fr else None,
+                    rope_f0=fr[1] if fr else 1.0, take=tuple(take), norm_intermediate=norm_intermediate,
+                    has_proj_embed=isinstance(self.proj_embed, nn.Linear), has_norm_y=self.norm_cross_tokens)
+
+    def forward_tokens(self, toks: List[torch.Tensor], B: int, h: int, w: int, pk: ParamPack, prefix: str, take=(),
+                       norm_intermediate=True):
+        """per-view tokens [B*h*w, C_in] -> (per-view normalised tokens bf16, [[per-view intermediate] per level])."""
+        nv = len(toks)
+        outs = fused.DecoderFn.apply(pk, prefix, self._cfg(B, h, w, take, norm_intermediate), nv, *toks, *pk.params.values())
+        finals = list(outs[:nv])
+        rest = outs[nv:]
+        inter = [list(rest[l * nv:(l + 1) * nv]) for l in range(len(rest) // nv)]
+        return finals, inter
+
+    def _pack(self) -> ParamPack:
+        pk = get_pack(self)
+        pk.refresh_bf16()
+        return pk
+
+    def _check_input(self, model_input):
+        assert len(model_input.features) == self.num_views, f"Expected {self.num_views} views, got {len(model_input.features)}"
+        assert all(
+            f.shape[1] == self.input_embed_dim for f in model_input.features
+        ), f"All views must have input dimension {self.input_embed_dim}"
+        assert all(f.ndim == 4 for f in model_input.features), "All views must have 4 dimensions (N, C, H, W)"
+        if not model_input.features[0].is_cuda:
+            raise RuntimeError("uniception_b200.MultiViewCrossAttentionTransformer runs on CUDA only (no CPU fallback)")
+
+    def forward(self, model_input: MultiViewTransformerInput) -> MultiViewTransformerOutput:
+        self._check_input(model_input)
+        B, _, h, w = model_input.features[0].shape
+        toks = [fused.NchwToNlcFn.apply(f) for f in model_input.features]
+        finals, _ = self.forward_tokens(toks, B, h, w, self._pack(), "")
+        return MultiViewTransformerOutput(features=[fused.NlcToNchwFn.apply(t, B, h, w) for t in finals])
+
+
+class MultiViewCrossAttentionTransformerIFR(MultiViewCrossAttentionTransformer, IntermediateFeatureReturner):
+    "Intermediate Feature Returner variant (cross_attention_transformer.py:278-505)"
+
+    def __init__(self, name: str, input_embed_dim: int, num_views: int, size: Optional[str] = None, depth: int = 12,
+                 dim: int = 768, num_heads: int = 12, mlp_ratio: float = 4.0, qkv_bias: bool = True, qk_norm: bool = False,
+                 proj_drop: float = 0.0, attn_drop: float = 0.0, init_values: Optional[float] = None, drop_path: float = 0.0,
+                 act_layer: nn.Module = nn.GELU, norm_layer: nn.Module = partial(nn.LayerNorm, eps=1e-6),
+                 mlp_layer: nn.Module = Mlp, custom_positional_encoding: Callable = None, norm_cross_tokens: bool = True,
+                 use_scalable_softmax: bool = False, use_entropy_scaling: bool = False,
+                 base_token_count_for_entropy_scaling: int = 444, entropy_scaling_growth_factor: float = 1.4,
+                 pretrained_checkpoint_path: str = None, indices: Optional[Union[int, List[int]]] = None,
+                 norm_intermediate: bool = True, intermediates_only: bool = False, gradient_checkpointing: bool = False,
+                 *args, **kwargs):
+        MultiViewCrossAttentionTransformer.__init__(
+            self, name=name, input_embed_dim=input_embed_dim, num_views=num_views, size=size, depth=depth, dim=dim,
+            num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_norm=qk_norm, proj_drop=proj_drop,
+            attn_drop=attn_drop, init_values=init_values, drop_path=drop_path, act_layer=act_layer, norm_layer=norm_layer,
+            mlp_layer=mlp_layer, custom_positional_encoding=custom_positional_encoding, norm_cross_tokens=norm_cross_tokens,
+            use_scalable_softmax=use_scalable_softmax, use_entropy_scaling=use_entropy_scaling,
+            base_token_count_for_entropy_scaling=base_token_count_for_entropy_scaling,
+            entropy_scaling_growth_factor=entropy_scaling_growth_factor,
+            pretrained_checkpoint_path=pretrained_checkpoint_path, gradient_checkpointing=gradient_checkpointing,
+            *args, **kwargs)
+        IntermediateFeatureReturner.__init__(self, indices=indices, norm_intermediate=norm_intermediate,
+                                             intermediates_only=intermediates_only)
+
+    def forward(self, model_input: MultiViewTransformerInput):
+        self._check_input(model_input)
+        B, _, h, w = model_input.features[0].shape
+        take, _ = feature_take_indices(self.depth, self.indices)
+        toks = [fused.NchwToNlcFn.apply(f) for f in model_input.features]
+        finals, inter = self.forward_tokens(toks, B, h, w, self._pack(), "", take, self.norm_intermediate)
+        inter_out = [MultiViewTransformerOutput(features=[fused.NlcToNchwFn.apply(t, B, h, w) for t in lvl]) for lvl in inter]
+        if self.intermediates_only:
+            return inter_out
+        return MultiViewTransformerOutput(features=[fused.NlcToNchwFn.apply(t, B, h, w) for t in finals]), inter_out
+
+
+# registry surface: info_sharing/__init__.py:23-37 (in-scope entries)
+INFO_SHARING_CLASSES = {
+    "cross_attention": (MultiViewCrossAttentionTransformer, MultiViewCrossAttentionTransformerIFR),
+}

@@ -14,6 +14,8 @@ import torch
 
 from . import _lib as L
 
+PROFILE = None  # bench.py: set to a list to record (start_event, end_event, flops) per uc_gemm launch
+
 _DT = {torch.bfloat16: L.UC_DTYPE_BF16, torch.float32: L.UC_DTYPE_F32, torch.float16: L.UC_DTYPE_F16}
 
 
@@ -66,6 +68,13 @@ def gemm(a, b, out, *, a_layout=0, b_layout=0, bias=None, residual=None, aux_out
         _DT[out.dtype], epi, split_k, rope_cols,
         _ptr(bias), _ptr(residual), _ptr(aux_out), _ptr(aux_in), _ptr(positions), _ptr(rope_table),
     )
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L.lib.uc_gemm(C.byref(p), _stream()))
+        e1.record()
+        PROFILE.append((e0, e1, 2.0 * m * n * k))
+        return out
     L.check(L.lib.uc_gemm(C.byref(p), _stream()))
     return out
 
