@@ -50,4 +50,4 @@ def test_rope2d_matches_reference_native_api_and_golden():
     ma, rel = O.parity(tok.grad, a["grad_in"])
     assert rel <= 1e-6, (ma, rel)
     with pytest.raises(RuntimeError):  # TORCH_CHECK-style argument errors (curope.cpp:54-59)
-        rope(torch.zeros(1, 2, 3, 64, device="cuda"), torch.zeros(1, 3, 3, device="cuda", dtype=torch.int64))
+        rope(torch.zeros(1, 2, 3, 64, device="cuda"), torch.zeros(2, 3, 2, device="cuda", dtype=torch.int64))

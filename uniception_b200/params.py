@@ -24,6 +24,18 @@ class ParamPack:
         named = [(n, p) for n, p in module.named_parameters()]  # de-duplicated by torch
         if not named:
             raise RuntimeError("ParamPack: module has no parameters")
+        # Layout order: registration order, except that inside one parent module (e.g. `cross_attn`) all
+        # matrices come before all vectors, so projq|projk|projv|proj weights (and their biases) are adjacent.
+        ordered, i = [], 0
+        while i < len(named):
+            key = named[i][0].rsplit(".", 2)[0] if named[i][0].count(".") >= 2 else ""
+            j = i
+            while j < len(named) and (named[j][0].rsplit(".", 2)[0] if named[j][0].count(".") >= 2 else "") == key:
+                j += 1
+            grp = named[i:j]
+            ordered += [x for x in grp if x[1].dim() >= 2] + [x for x in grp if x[1].dim() < 2]
+            i = j
+        named = ordered
         dev = named[0][1].device
         if dev.type != "cuda":
             raise RuntimeError("uniception_b200 modules run on CUDA only (no CPU fallback); call .cuda() first")
