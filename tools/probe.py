@@ -313,6 +313,23 @@ def check_perf():
     return True
 
 
+def check_attn_once():
+    """one fwd + bwd launch at the encoder's C3 shape (for ncu)"""
+    import torch
+    from uniception_b200 import ops
+    B, H, N = 16, 16, 1024
+    Cc = H * 64
+    qkv = torch.randn(B * N, 3 * Cc, device="cuda").bfloat16()
+    q, k, v = qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:]
+    for _ in range(2):
+        o, lse = ops.attn_fwd(q, k, v, B, H, N, N, 0.125)
+        do = torch.randn_like(o)
+        dqkv = torch.empty_like(qkv)
+        ops.attn_bwd(q, k, v, o, do, lse, B, H, N, N, 0.125, dqkv[:, :Cc], dqkv[:, Cc:2 * Cc], dqkv[:, 2 * Cc:])
+    torch.cuda.synchronize()
+    return True
+
+
 CHECKS = ["gemm_tn", "gemm_dgrad", "gemm_wgrad", "gemm_epilogues", "elementwise", "attn_fwd", "attn_bwd", "perf"]
 
 if __name__ == "__main__":

@@ -7,11 +7,12 @@
 //        P^T  = exp2(S^T c - lse_i),   dS^T = P^T o (dP^T - delta_i)            (registers)
 //        dV  += P^T  dO_i    (TS: P^T  from TMEM, dO_i MN-major from the same smem tile)
 //        dK  += dS^T Q_i     (TS: dS^T from TMEM, Q_i  MN-major)
-//        dQ_i = dS   K       (SS: dS written to smem as an MN-major A tile, K MN-major) -> fp32 red.add
+//        dQ_i = dS   K       (SS: dS written to smem as an MN-major A tile, K MN-major) -> TMEM -> smem ->
+//                            cp.reduce.async.bulk.tensor (TMA add-reduction into the fp32 dq accumulator)
 //   3. attn_bwd_finish : dq = bf16(scale * dq_acc) with optional inverse 2-D RoPE  (memory-bound)
 // dK gets `scale` and the optional inverse RoPE in the main kernel's epilogue.
-//   warp 0: TMA producer | warp 1: MMA issuer | warps 2..5: softmax/dS (thread == key) |
-//   warps 6..9: dQ drain (TMEM -> red.global.add.v4.f32)
+//   warp 0: TMA producer | warp 1: MMA issuer | warps 2..9: softmax/dS (two threads per key row, 64 query
+//   columns each) | warps 10..13: dQ drain (TMEM -> swizzled smem -> TMA reduce-add)
 // TMEM columns: S^T/P^T [0,128) | dP^T/dS^T [128,256) | dV [256,320) | dK [320,384) | dQ [384,448).
 #include "common.cuh"
 
@@ -21,11 +22,12 @@ int make_head_map(CUtensorMap* m, const void* base, int H, int N, int B, long lo
 
 namespace {
 
-constexpr int BW_THREADS = 320;
+constexpr int BW_THREADS = 448;  // TMA, MMA, 8 softmax/dS warps (two threads per key row), 4 dQ-drain warps
 constexpr uint32_t BW_TILE = 128 * 64 * 2;  // 16 KB
 // smem: K, V, 2 x (Q, dO), dS (32 KB), 2 x (lse2, delta) floats, barriers
 constexpr uint32_t BW_OFF_K = 0, BW_OFF_V = BW_TILE, BW_OFF_QDO = 2 * BW_TILE, BW_OFF_DS = 6 * BW_TILE,
-                   BW_OFF_STATS = 8 * BW_TILE, BW_OFF_BAR = 8 * BW_TILE + 2048;
+                   BW_OFF_DQ = 8 * BW_TILE /* fp32 [2 boxes][128 q][32 d], 128B-swizzled, TMA-reduce source */,
+                   BW_OFF_STATS = 10 * BW_TILE, BW_OFF_BAR = 10 * BW_TILE + 2048;
 constexpr uint32_t BW_SMEM = BW_OFF_BAR + 256 + 1024;
 constexpr uint32_t BT_SP = 0, BT_DP = 128, BT_DV = 256, BT_DK = 320, BT_DQ = 384, BT_COLS = 512;
 
@@ -114,7 +116,8 @@ __global__ void attn_bwd_finish_kernel(const float* __restrict__ acc, __nv_bfloa
 
 __global__ void __launch_bounds__(BW_THREADS, 1)
 attn_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const AttnBwdArgs a) {
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                     const __grid_constant__ CUtensorMap tmDQ, const AttnBwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -136,11 +139,11 @@ attn_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int num_q_tiles = (a.Nq + 127) / 128;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmDQ);
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(qdo_full(s), 1); mbar_init(qdo_empty(s), 1); }
     mbar_init(sdp_full, 1);
-    mbar_init(ds_ready, 4);
+    mbar_init(ds_ready, 8);
     mbar_init(dq_full, 1);
     mbar_init(dq_free, 4);
     mbar_init(fin_full, 1);
@@ -193,10 +196,10 @@ attn_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint64_t ds_mn = umma_desc_mnmajor(sDS, 16384), k_mn = umma_desc_mnmajor(sK, 8192);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_ts(tmem_base + BT_DV, tmem_base + BT_SP + k * 8, do_mn + uint64_t(k * 128), id_ts, (i > 0 || k > 0) ? 1u : 0u);
+          umma_ts(tmem_base + BT_DV, tmem_base + BT_SP + (k >> 2) * 64 + (k & 3) * 8, do_mn + uint64_t(k * 128), id_ts, (i > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_ts(tmem_base + BT_DK, tmem_base + BT_DP + k * 8, q_mn + uint64_t(k * 128), id_ts, (i > 0 || k > 0) ? 1u : 0u);
+          umma_ts(tmem_base + BT_DK, tmem_base + BT_DP + (k >> 2) * 64 + (k & 3) * 8, q_mn + uint64_t(k * 128), id_ts, (i > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 8; ++k) umma_ss(tmem_base + BT_DQ, ds_mn + uint64_t(k * 128), k_mn + uint64_t(k * 128), id_dq, k > 0);
         umma_commit(dq_full);
@@ -204,29 +207,31 @@ attn_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       umma_commit(fin_full);
     }
-  } else if (warp < 6) {
-    // ===================== softmax / dS: thread <-> key row =====================
+  } else if (warp < 10) {
+    // ===================== softmax / dS: two threads per key row =====================
     const int lane_group = warp & 3;
+    const int half = (warp - 2) >> 2;  // query columns [64*half, 64*half+64) of each tile; head columns [32*half, +32) in the epilogue
     const uint32_t lane_addr = uint32_t(lane_group * 32) << 16;
     const int r = lane_group * 32 + lane;   // key row inside the tile
-    const int ct = threadIdx.x - 64;        // 0..127
+    const int ct = threadIdx.x - 64;        // 0..255
     const uint32_t ds_row = sDS + r * 128;
+    auto load_stat = [&](int tile) -> float {  // threads 0..127: lse*log2e, 128..255: delta, of query (tile, ct&127)
+      const int q = tile * 128 + (ct & 127);
+      if (q >= a.Nq) return ct < 128 ? INFINITY : 0.f;
+      const long long off = ((long long)b * a.H + h) * a.Nq + q;
+      return ct < 128 ? a.lse[off] * 1.4426950408889634f : a.delta[off];
+    };
+    stats[ct] = load_stat(0);
     for (int i = 0; i < num_q_tiles; ++i) {
       const int st = i & 1;
       float* lse2 = stats + st * 256;
       float* dl = lse2 + 128;
-      {
-        const int q = i * 128 + ct;
-        const bool ok = q < a.Nq;
-        const long long off = ((long long)b * a.H + h) * a.Nq + q;
-        lse2[ct] = ok ? a.lse[off] * 1.4426950408889634f : INFINITY;
-        dl[ct] = ok ? a.delta[off] : 0.f;
-      }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);  // stats(i) visible; everyone is done with iteration i-1
+      const float next_stat = (i + 1 < num_q_tiles) ? load_stat(i + 1) : 0.f;  // latency hidden behind this tile's work
       mbar_wait(sdp_full, i & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 2 * half; c < 2 * half + 2; ++c) {
         uint32_t s[32], dp[32];
         tmem_ld32(tmem_base + lane_addr + BT_SP + c * 32, s);
         tmem_ld32(tmem_base + lane_addr + BT_DP + c * 32, dp);
@@ -242,8 +247,10 @@ attn_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           pk[j] = pack_bf16(p0, p1);
           dk[j] = pack_bf16(d0, d1);
         }
-        tmem_st16(tmem_base + lane_addr + BT_SP + c * 16, pk);
-        tmem_st16(tmem_base + lane_addr + BT_DP + c * 16, dk);
+        // packed P^T / dS^T overwrite the already-consumed fp32 columns of THIS thread's half only:
+        // queries [0,64) -> columns [0,32), queries [64,128) -> columns [64,96) of the region
+        tmem_st16(tmem_base + lane_addr + BT_SP + (c >> 1) * 64 + (c & 1) * 16, pk);
+        tmem_st16(tmem_base + lane_addr + BT_DP + (c >> 1) * 64 + (c & 1) * 16, dk);
         // dS -> smem as MN-major A tile: [q-block of 64][key row r][64 q] with the 128B swizzle
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -259,6 +266,7 @@ attn_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(ds_ready);
+      stats[(st ^ 1) * 256 + ct] = next_stat;
     }
     // ---- epilogue: dV, dK (x scale, inverse RoPE) ----
     mbar_wait(fin_full, 0);
@@ -266,8 +274,8 @@ attn_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int kv = kv0 + r;
     const bool ok = kv < a.Nk;
     const long long tok = (long long)b * a.Nk + kv;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    {
+      const int c = half;
       uint32_t v[32];
       tmem_ld32(tmem_base + lane_addr + BT_DV + c * 32, v);
       tmem_ld_wait();
@@ -285,8 +293,8 @@ attn_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       __syncwarp();
     }
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    {
+      const int c = half;
       uint32_t raw[32];
       tmem_ld32(tmem_base + lane_addr + BT_DK + c * 32, raw);
       tmem_ld_wait();
@@ -316,32 +324,41 @@ attn_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       __syncwarp();
     }
   } else {
-    // ===================== dQ drain: TMEM -> fp32 red.add =====================
+    // ===================== dQ drain: TMEM -> swizzled smem -> TMA reduce-add =====================
     const int lane_group = warp & 3;
     const uint32_t lane_addr = uint32_t(lane_group * 32) << 16;
+    const int r = lane_group * 32 + lane;
+    const uint32_t sDQ = smem_base + BW_OFF_DQ;
+    const bool issuer = (warp == 10 && lane == 0);
     for (int i = 0; i < num_q_tiles; ++i) {
       mbar_wait(dq_full, i & 1);
       tc_fence_after();
-      const int q = i * 128 + lane_group * 32 + lane;
-      float* dst = a.dq_acc + ((long long)b * a.Nq + q) * (a.H * 64) + h * 64;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + lane_addr + BT_DQ + c * 32, v);
-        tmem_ld_wait();
-        if (q < a.Nq) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c * 32 + 4 * g), "f"(__uint_as_float(v[4 * g])),
-                         "f"(__uint_as_float(v[4 * g + 1])), "f"(__uint_as_float(v[4 * g + 2])), "f"(__uint_as_float(v[4 * g + 3]))
-                         : "memory");
-        }
-        __syncwarp();
-      }
+      uint32_t v0[32], v1[32];
+      tmem_ld32(tmem_base + lane_addr + BT_DQ, v0);
+      tmem_ld32(tmem_base + lane_addr + BT_DQ + 32, v1);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(dq_free);
+      if (lane == 0) mbar_arrive(dq_free);          // TMEM dQ region may be overwritten by the next tile
+      if (issuer) tma_store_wait_read0();            // previous reduction has finished reading the staging tile
+      named_bar_sync(2, 128);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t off = r * 128 + ((j ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDQ + off), "r"(v0[4 * j]), "r"(v0[4 * j + 1]),
+                     "r"(v0[4 * j + 2]), "r"(v0[4 * j + 3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDQ + 16384 + off), "r"(v1[4 * j]), "r"(v1[4 * j + 1]),
+                     "r"(v1[4 * j + 2]), "r"(v1[4 * j + 3]) : "memory");
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(2, 128);
+      if (issuer) {
+        tma_reduce_add_3d(&tmDQ, sDQ, h * 64, i * 128, b);
+        tma_reduce_add_3d(&tmDQ, sDQ + 16384, h * 64 + 32, i * 128, b);
+        tma_store_commit();
+      }
     }
+    if (issuer) tma_store_wait0();
   }
 
   tc_fence_before();
@@ -381,12 +398,18 @@ extern "C" int uc_attn_bwd(const uc_attn_bwd_params* p, uc_stream_t stream_) {
   cudaError_t e = cudaMemsetAsync(p->dq_acc, 0, sizeof(float) * rows_q * p->H * 64, stream);
   UC_REQUIRE(e == cudaSuccess, UC_ERR_CUDA, "uc_attn_bwd: memset failed: %s", cudaGetErrorString(e));
 
-  CUtensorMap tmQ, tmK, tmV, tmdO;
+  CUtensorMap tmQ, tmK, tmV, tmdO, tmDQ;
   int r;
   if ((r = make_head_map(&tmQ, p->q, p->H, p->Nq, p->B, p->ldq, 128))) return r;
   if ((r = make_head_map(&tmK, p->k, p->H, p->Nk, p->B, p->ldk, 128))) return r;
   if ((r = make_head_map(&tmV, p->v, p->H, p->Nk, p->B, p->ldv, 128))) return r;
   if ((r = make_head_map(&tmdO, p->d_o, p->H, p->Nq, p->B, p->ldo, 128))) return r;
+  {  // fp32 dq accumulator [B][Nq][H*64]: box (32 floats = 128 B, 128 rows), 128B swizzle; rows >= Nq are clipped by TMA
+    uint64_t dims[3] = {(uint64_t)p->H * 64, (uint64_t)p->Nq, (uint64_t)p->B};
+    uint64_t strides[2] = {(uint64_t)p->H * 64 * 4, (uint64_t)p->Nq * p->H * 64 * 4};
+    uint32_t box[3] = {32, 128, 1};
+    if ((r = make_tensor_map(&tmDQ, p->dq_acc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return r;
+  }
   static bool configured = false;
   if (!configured) {
     e = cudaFuncSetAttribute(attn_bwd_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM);
@@ -404,7 +427,7 @@ extern "C" int uc_attn_bwd(const uc_attn_bwd_params* p, uc_stream_t stream_) {
   a.k_positions = p->k_positions;
   a.rope_table = p->rope_table;
   dim3 grid((p->Nk + 127) / 128, p->B * p->H);
-  attn_bwd_main_kernel<<<grid, BW_THREADS, BW_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, a);
+  attn_bwd_main_kernel<<<grid, BW_THREADS, BW_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, a);
   if ((r = check_launch("uc_attn_bwd(main)"))) return r;
   {
     const long long total = rows_q * p->H * 2;

@@ -4,8 +4,9 @@
 //
 //   warp 0     : TMA producer  (Q once; K/V tiles of 128 keys, 2-stage ring; 3-D maps so rows >= N zero-fill)
 //   warp 1     : MMA issuer    (S = Q K^T  SS-mode 128x128x64;  O += P V  TS-mode: P read from TMEM, V MN-major)
-//   warps 2..5 : softmax       (thread == query row: no cross-thread reductions; online max/sum in fp32,
-//                               P -> TMEM as packed bf16, O rescaled in TMEM, epilogue O/l -> global, LSE)
+//   warps 2..9 : softmax       (two threads per query row, 64 key columns each: online max/sum in fp32,
+//                               one smem exchange of the row max per tile, P -> TMEM as packed bf16,
+//                               O rescaled in TMEM, epilogue O/l -> global, LSE)
 // TMEM columns: S [0,128) fp32 | P [128,192) packed bf16 | O [192,256) fp32.
 #include "common.cuh"
 
@@ -15,9 +16,9 @@ namespace {
 constexpr int AT_BM = 128;      // queries per CTA
 constexpr int AT_BN = 128;      // keys per tile
 constexpr int AT_D = 64;        // head dim
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 320;  // TMA warp, MMA warp, 8 softmax warps (two threads per query row)
 constexpr uint32_t AT_TILE_BYTES = 128 * 64 * 2;  // 16 KB
-constexpr uint32_t AT_SMEM = 5 * AT_TILE_BYTES + 1024 + 128;
+constexpr uint32_t AT_SMEM = 5 * AT_TILE_BYTES + 1024 + 128 + 3 * 1024;  // + row-max / row-sum exchange
 constexpr uint32_t TM_S = 0, TM_P = 128, TM_O = 192, TM_COLS = 256;
 
 struct AttnFwdArgs {
@@ -29,6 +30,9 @@ struct AttnFwdArgs {
   float scale;
 };
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -65,7 +69,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     mbar_init(s_full, 1);
-    mbar_init(p_ready, 4);
+    mbar_init(p_ready, 8);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -115,97 +119,94 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       umma_commit(o_full);
     }
   } else {
-    // ===================== softmax: thread <-> query row =====================
+    // ===================== softmax: two threads per query row =====================
     const int lane_group = warp & 3;
+    const int half = (warp - 2) >> 2;                    // key columns [64*half, 64*half+64)
     const uint32_t lane_addr = uint32_t(lane_group * 32) << 16;
-    const int row = q0 + lane_group * 32 + lane;
-    float m_run = -INFINITY;  // running max of raw scores
-    float l_run = 0.f;
+    const int r = lane_group * 32 + lane;                // row inside the tile
+    const int row = q0 + r;
+    float* xch = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 128);  // [3][2][128]
+    float m_run = -INFINITY;  // running max of raw scores (shared by both halves)
+    float l_run = 0.f;        // this thread's partial row sum
     for (int j = 0; j < num_tiles; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const int kv_valid = a.Nk - j * AT_BN;  // columns >= kv_valid are padding
-      // pass 1: row max
+      const int kv_valid = a.Nk - j * AT_BN - 64 * half;  // columns >= kv_valid (of this half) are padding
+      uint32_t s[64];
+      tmem_ld32(tmem_base + lane_addr + TM_S + 64 * half, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+      tmem_ld32(tmem_base + lane_addr + TM_S + 64 * half + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+      tmem_ld_wait();
       float m_tile = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + lane_addr + TM_S + c * 32, r);
-        tmem_ld_wait();
+      if (kv_valid >= 64) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = (c * 32 + i < kv_valid) ? __uint_as_float(r[i]) : -INFINITY;
-          m_tile = fmaxf(m_tile, s);
+        for (int i = 0; i < 64; ++i) m_tile = fmaxf(m_tile, __uint_as_float(s[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
+          m_tile = fmaxf(m_tile, __uint_as_float(s[i]));
         }
       }
-      const float m_new = fmaxf(m_run, m_tile);
+      float* mx = xch + (j & 1) * 256;
+      mx[half * 128 + r] = m_tile;
+      named_bar_sync(1, 256);
+      const float m_new = fmaxf(m_run, fmaxf(m_tile, mx[(half ^ 1) * 128 + r]));
       const float alpha = fast_exp2((m_run - m_new) * a.scale_log2);  // 0 on the first tile (m_run = -inf)
       const float m_scaled = m_new * a.scale_log2;
-      // pass 2: p = exp2(s*c - m*c) -> packed bf16 -> TMEM P
       float l_tile = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + lane_addr + TM_S + c * 32, r);
-        tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int col = c * 32 + 2 * i;
-          float p0 = fast_exp2(__uint_as_float(r[2 * i]) * a.scale_log2 - m_scaled);
-          float p1 = fast_exp2(__uint_as_float(r[2 * i + 1]) * a.scale_log2 - m_scaled);
-          if (col >= kv_valid) p0 = 0.f;
-          if (col + 1 >= kv_valid) p1 = 0.f;
+          const float p0 = fast_exp2(__uint_as_float(s[32 * c + 2 * i]) * a.scale_log2 - m_scaled);
+          const float p1 = fast_exp2(__uint_as_float(s[32 * c + 2 * i + 1]) * a.scale_log2 - m_scaled);
           l_tile += p0 + p1;
           pk[i] = pack_bf16(p0, p1);
         }
-        tmem_st16(tmem_base + lane_addr + TM_P + c * 16, pk);
+        tmem_st16(tmem_base + lane_addr + TM_P + 32 * half + 16 * c, pk);
       }
       l_run = l_run * alpha + l_tile;
       m_run = m_new;
-      // rescale the running O (PV(j-1) has retired: s_full(j) was committed after it)
+      // rescale this thread's half of the running O (PV(j-1) has retired: s_full(j) was committed after it)
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + lane_addr + TM_O + c * 32, r);
-          tmem_ld_wait();
+        uint32_t o[32];
+        tmem_ld32(tmem_base + lane_addr + TM_O + 32 * half, o);
+        tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-          tmem_st32(tmem_base + lane_addr + TM_O + c * 32, r);
-        }
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st32(tmem_base + lane_addr + TM_O + 32 * half, o);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
     }
-    // ---- epilogue: O / l -> global, LSE ----
+    // ---- epilogue: O / l -> global (32 of the 64 head columns per thread), LSE ----
+    float* lx = xch + 512;
+    lx[half * 128 + r] = l_run;
+    named_bar_sync(1, 256);
+    const float l_tot = l_run + lx[(half ^ 1) * 128 + r];
     mbar_wait(o_full, 0);
     tc_fence_after();
-    const float inv_l = 1.0f / l_run;
+    const float inv_l = 1.0f / l_tot;
     const bool row_ok = row < a.Nq;
-    __nv_bfloat16* optr = a.o + ((long long)b * a.Nq + row) * a.ldo + h * AT_D;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + lane_addr + TM_O + c * 32, r);
-      tmem_ld_wait();
-      if (row_ok) {
-        uint4* dst = reinterpret_cast<uint4*>(optr + c * 32);
+    uint32_t o[32];
+    tmem_ld32(tmem_base + lane_addr + TM_O + 32 * half, o);
+    tmem_ld_wait();
+    if (row_ok) {
+      uint4* dst = reinterpret_cast<uint4*>(a.o + ((long long)b * a.Nq + row) * a.ldo + h * AT_D + 32 * half);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 t;
-          t.x = pack_bf16(__uint_as_float(r[8 * i + 0]) * inv_l, __uint_as_float(r[8 * i + 1]) * inv_l);
-          t.y = pack_bf16(__uint_as_float(r[8 * i + 2]) * inv_l, __uint_as_float(r[8 * i + 3]) * inv_l);
-          t.z = pack_bf16(__uint_as_float(r[8 * i + 4]) * inv_l, __uint_as_float(r[8 * i + 5]) * inv_l);
-          t.w = pack_bf16(__uint_as_float(r[8 * i + 6]) * inv_l, __uint_as_float(r[8 * i + 7]) * inv_l);
-          dst[i] = t;
-        }
+      for (int i = 0; i < 4; ++i) {
+        uint4 t;
+        t.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
+        t.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
+        t.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
+        t.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
+        dst[i] = t;
       }
-      __syncwarp();
+      if (half == 0 && a.lse) a.lse[((long long)b * a.H + h) * a.Nq + row] = m_run * a.scale + logf(l_tot);
     }
-    if (row_ok && a.lse) a.lse[((long long)b * a.H + h) * a.Nq + row] = m_run * a.scale + logf(l_run);
   }
 
   tc_fence_before();

@@ -140,39 +140,43 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(uc_layernorm_fwd_par
 }
 
 // dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)) [+ dres];  dgamma += sum dy*xhat;  dbeta += sum dy
+// One warp per row.  Pass 1 streams x / dy once (row statistics + per-lane dgamma/dbeta partials), pass 2
+// re-reads the same 2-4 KB row (L1-resident) to form dx, so only the 2*CH*8 partial sums live in registers
+// across rows (2 blocks / SM).  Block partials are combined warp-by-warp in smem (no smem atomics) and leave
+// the block as one global atomicAdd per column.
 template <int CH>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(uc_layernorm_bwd_params p) {
-  extern __shared__ float red[];  // [2][C] block-level dgamma/dbeta accumulators
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(uc_layernorm_bwd_params p) {
+  extern __shared__ float red[];  // [2][C]
   const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
   const float inv_c = 1.0f / (float)p.C;
   for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
   float dg[CH][8], db[CH][8];
 #pragma unroll
   for (int c = 0; c < CH; ++c)
 #pragma unroll
     for (int j = 0; j < 8; ++j) { dg[c][j] = 0.f; db[c][j] = 0.f; }
 
-  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < p.rows; row += gridDim.x * warps_per_block) {
+  for (int row = blockIdx.x * warps_per_block + warp; row < p.rows; row += gridDim.x * warps_per_block) {
     const float mean = p.mean[row], rstd = p.rstd[row];
-    float xh[CH][8], gy[CH][8];
+    const int64_t base = (int64_t)row * p.C;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < p.C) {
         float x[8], dy[8], g[8];
-        load8(p.x, p.x_dtype, (int64_t)row * p.C + col, x);
-        load8(p.dy, p.dy_dtype, (int64_t)row * p.C + col, dy);
+        load8(p.x, p.x_dtype, base + col, x);
+        load8(p.dy, p.dy_dtype, base + col, dy);
         load8(p.gamma, UC_DTYPE_F32, col, g);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[c][j] = (x[j] - mean) * rstd;
-          gy[c][j] = g[j] * dy[j];
-          s1 += gy[c][j];
-          s2 += gy[c][j] * xh[c][j];
-          dg[c][j] += dy[j] * xh[c][j];
+          const float xh = (x[j] - mean) * rstd;
+          const float gy = g[j] * dy[j];
+          s1 += gy;
+          s2 += gy * xh;
+          dg[c][j] += dy[j] * xh;
           db[c][j] += dy[j];
         }
       }
@@ -183,28 +187,36 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(uc_layernorm_bwd_par
     for (int c = 0; c < CH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < p.C) {
-        float dx[8];
+        float x[8], dy[8], g[8], dx[8];
+        load8(p.x, p.x_dtype, base + col, x);
+        load8(p.dy, p.dy_dtype, base + col, dy);
+        load8(p.gamma, UC_DTYPE_F32, col, g);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dx[j] = rstd * (gy[c][j] - s1 - xh[c][j] * s2);
+        for (int j = 0; j < 8; ++j) dx[j] = rstd * (g[j] * dy[j] - s1 - (x[j] - mean) * rstd * s2);
         if (p.dres) {
           float r[8];
-          load8(p.dres, UC_DTYPE_BF16, (int64_t)row * p.C + col, r);
+          load8(p.dres, UC_DTYPE_BF16, base + col, r);
 #pragma unroll
           for (int j = 0; j < 8; ++j) dx[j] += r[j];
         }
-        store8(p.dx, UC_DTYPE_BF16, (int64_t)row * p.C + col, dx);
+        store8(p.dx, UC_DTYPE_BF16, base + col, dx);
       }
     }
   }
   if (p.dgamma) {
+    for (int w = 0; w < warps_per_block; ++w) {
+      __syncthreads();
+      if (warp == w) {
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int col = c * 256 + lane * 8;
-      if (col < p.C) {
+        for (int c = 0; c < CH; ++c) {
+          const int col = c * 256 + lane * 8;
+          if (col < p.C) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          atomicAdd(&red[col + j], dg[c][j]);
-          atomicAdd(&red[p.C + col + j], db[c][j]);
+            for (int j = 0; j < 8; ++j) {
+              red[col + j] += dg[c][j];
+              red[p.C + col + j] += db[c][j];
+            }
+          }
         }
       }
     }

@@ -23,7 +23,7 @@ struct GemmArgs {
   int m, n, k;
   int a_mn, b_mn;
   int num_m, num_n, num_kb, split_k, kb_per_split;
-  int epilogue, c_f32, rope_cols;
+  int epilogue, c_f32, rope_cols, n_fastest;
   long long ldc;
   void* c;
   const float* bias;
@@ -118,8 +118,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int item = blockIdx.x; item < total; item += gridDim.x) {
         const int split = item % g.split_k;
         const int tile = item / g.split_k;
-        const int m0 = (tile % g.num_m) * BM;
-        const int n0 = (tile / g.num_m) * BN;
+        const int m0 = g.n_fastest ? (tile / g.num_n) * BM : (tile % g.num_m) * BM;
+        const int n0 = g.n_fastest ? (tile % g.num_n) * BN : (tile / g.num_m) * BN;
         const int kb0 = split * g.kb_per_split;
         const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -191,8 +191,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int item = blockIdx.x; item < total; item += gridDim.x) {
       const int split = item % g.split_k;
       const int tile = item / g.split_k;
-      const int m0 = (tile % g.num_m) * BM;
-      const int n0 = (tile / g.num_m) * BN;
+      const int m0 = g.n_fastest ? (tile / g.num_n) * BM : (tile % g.num_m) * BM;
+      const int n0 = g.n_fastest ? (tile % g.num_n) * BN : (tile / g.num_m) * BN;
       const int kb0 = split * g.kb_per_split;
       const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
       if (kb0 >= kb1) continue;
@@ -389,6 +389,9 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
   g.a_mn = p->a_layout ? 1 : 0;
   g.b_mn = p->b_layout ? 1 : 0;
   g.num_m = num_m; g.num_n = num_n; g.num_kb = num_kb; g.split_k = split_k; g.kb_per_split = kb_per;
+  // rasterisation: tiles that run concurrently share the LARGER operand's blocks (read once from HBM);
+  // the smaller operand is re-read from L2.  wgrad (atomic) keeps m-fastest: consecutive tiles share the B block.
+  g.n_fastest = (!atomic && (long long)p->m >= (long long)p->n) ? 1 : 0;
   g.epilogue = epi; g.c_f32 = p->c_dtype == UC_DTYPE_F32; g.rope_cols = p->rope_cols;
   g.ldc = p->ldc; g.c = p->c; g.bias = p->bias;
   g.residual = static_cast<const __nv_bfloat16*>(p->residual);
