@@ -160,53 +160,63 @@ attn_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    if (lane == 0) {
+    // whole warp loops (uniform control flow); one elected lane issues the TMA copies
+    if (elect_one()) {
       mbar_arrive_expect_tx(kv_full, 2 * BW_TILE);
       tma_load_3d(sK, &tmK, kv_full, h * 64, kv0, b);
       tma_load_3d(sV, &tmV, kv_full, h * 64, kv0, b);
-      for (int i = 0; i < num_q_tiles; ++i) {
-        const int st = i & 1;
-        mbar_wait(qdo_empty(st), ((i >> 1) & 1) ^ 1u);
+    }
+    __syncwarp();
+    for (int i = 0; i < num_q_tiles; ++i) {
+      const int st = i & 1;
+      mbar_wait(qdo_empty(st), ((i >> 1) & 1) ^ 1u);
+      if (elect_one()) {
         mbar_arrive_expect_tx(qdo_full(st), 2 * BW_TILE);
         tma_load_3d(sQ(st), &tmQ, qdo_full(st), h * 64, i * 128, b);
         tma_load_3d(sdO(st), &tmdO, qdo_full(st), h * 64, i * 128, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);   // K-major x K-major
-      const uint32_t id_ts = umma_idesc_bf16(128, 64, 0, 1);   // A in TMEM, B MN-major
-      const uint32_t id_dq = umma_idesc_bf16(128, 64, 1, 1);   // A MN-major (dS in smem), B MN-major
-      mbar_wait(kv_full, 0);
-      for (int i = 0; i < num_q_tiles; ++i) {
-        const int st = i & 1;
-        mbar_wait(qdo_full(st), (i >> 1) & 1);
-        tc_fence_after();
-        const uint64_t kd = umma_desc_kmajor(sK), vd = umma_desc_kmajor(sV);
-        const uint64_t qd = umma_desc_kmajor(sQ(st)), dod = umma_desc_kmajor(sdO(st));
+    // whole warp loops; operands stay in uniform registers; one elected lane issues tcgen05.mma / commit
+    const uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);   // K-major x K-major
+    const uint32_t id_ts = umma_idesc_bf16(128, 64, 0, 1);   // A in TMEM, B MN-major
+    const uint32_t id_dq = umma_idesc_bf16(128, 64, 1, 1);   // A MN-major (dS in smem), B MN-major
+    mbar_wait(kv_full, 0);
+    const uint64_t kd = umma_desc_kmajor(sK), vd = umma_desc_kmajor(sV);
+    const uint64_t ds_mn = umma_desc_mnmajor(sDS, 16384), k_mn = umma_desc_mnmajor(sK, 8192);
+    for (int i = 0; i < num_q_tiles; ++i) {
+      const int st = i & 1;
+      mbar_wait(qdo_full(st), (i >> 1) & 1);
+      tc_fence_after();
+      const uint64_t qd = umma_desc_kmajor(sQ(st)), dod = umma_desc_kmajor(sdO(st));
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tmem_base + BT_SP, kd + uint64_t(k * 2), qd + uint64_t(k * 2), id_s, k > 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tmem_base + BT_DP, vd + uint64_t(k * 2), dod + uint64_t(k * 2), id_s, k > 0);
+        for (int k = 0; k < 4; ++k) {
+          umma_ss(tmem_base + BT_SP, kd + uint64_t(k * 2), qd + uint64_t(k * 2), id_s, k > 0);
+          umma_ss(tmem_base + BT_DP, vd + uint64_t(k * 2), dod + uint64_t(k * 2), id_s, k > 0);
+        }
         umma_commit(sdp_full);
-        mbar_wait(ds_ready, i & 1);
-        if (i > 0) mbar_wait(dq_free, (i - 1) & 1);
-        tc_fence_after();
-        const uint64_t do_mn = umma_desc_mnmajor(sdO(st), 8192), q_mn = umma_desc_mnmajor(sQ(st), 8192);
-        const uint64_t ds_mn = umma_desc_mnmajor(sDS, 16384), k_mn = umma_desc_mnmajor(sK, 8192);
+      }
+      __syncwarp();
+      mbar_wait(ds_ready, i & 1);
+      if (i > 0) mbar_wait(dq_free, (i - 1) & 1);
+      tc_fence_after();
+      const uint64_t do_mn = umma_desc_mnmajor(sdO(st), 8192), q_mn = umma_desc_mnmajor(sQ(st), 8192);
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
+        for (int k = 0; k < 8; ++k) {
           umma_ts(tmem_base + BT_DV, tmem_base + BT_SP + (k >> 2) * 64 + (k & 3) * 8, do_mn + uint64_t(k * 128), id_ts, (i > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
           umma_ts(tmem_base + BT_DK, tmem_base + BT_DP + (k >> 2) * 64 + (k & 3) * 8, q_mn + uint64_t(k * 128), id_ts, (i > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) umma_ss(tmem_base + BT_DQ, ds_mn + uint64_t(k * 128), k_mn + uint64_t(k * 128), id_dq, k > 0);
+          umma_ss(tmem_base + BT_DQ, ds_mn + uint64_t(k * 128), k_mn + uint64_t(k * 128), id_dq, k > 0);
+        }
         umma_commit(dq_full);
         umma_commit(qdo_empty(st));
       }
-      umma_commit(fin_full);
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(fin_full);
+    __syncwarp();
   } else if (warp < 10) {
     // ===================== softmax / dS: two threads per key row =====================
     const int lane_group = warp & 3;

@@ -1,25 +1,31 @@
 // Fused attention forward (uc_attn_fwd): softmax(q k^T * scale) v, head_dim 64, bf16 in / fp32 softmax.
-// One CTA per (128-query tile, batch*head); two CTAs co-reside per SM (80 KB smem, 256 TMEM columns
-// each) so one CTA's softmax overlaps the other's tensor-core work.
+// One CTA per (128-query tile, batch*head); two CTAs co-reside per SM (80 KB smem, 256 TMEM columns each).
 //
-//   warp 0     : TMA producer  (Q once; K/V tiles of 128 keys, 2-stage ring; 3-D maps so rows >= N zero-fill)
-//   warp 1     : MMA issuer    (S = Q K^T  SS-mode 128x128x64;  O += P V  TS-mode: P read from TMEM, V MN-major)
-//   warps 2..9 : softmax       (two threads per query row, 64 key columns each: online max/sum in fp32,
-//                               one smem exchange of the row max per tile, P -> TMEM as packed bf16,
-//                               O rescaled in TMEM, epilogue O/l -> global, LSE)
-// TMEM columns: S [0,128) fp32 | P [128,192) packed bf16 | O [192,256) fp32.
+//   warp 0     : TMA producer  (Q once; K/V tiles of 64 keys, 4-stage ring; 3-D maps so rows >= N zero-fill)
+//   warp 1     : MMA issuer    (S = Q K^T  SS-mode 128x64x64 into a DOUBLE-BUFFERED S, issued one tile ahead of
+//                               the softmax;  O += P V  TS-mode: P read from TMEM, V MN-major)
+//   warps 2..5 : softmax       (thread == query row: no cross-thread reductions; online max/sum in fp32 with
+//                               lazy rescaling -- O is only rescaled when the row max grows by > 2^8 --,
+//                               P -> TMEM as packed bf16, epilogue O/l -> global, LSE)
+// Because QK^T(j+1) is already in TMEM when softmax(j) ends, the exp pipe (MUFU, the true bound of d=64
+// attention on this chip: 16 exp/clk/SM vs 256 MMA-FLOPs per score) never waits on the tensor pipe.
+// TMEM columns: S0 [0,64) S1 [64,128) fp32 | P0 [128,160) P1 [160,192) packed bf16 | O [192,256) fp32.
 #include "common.cuh"
 
 namespace uc {
 namespace {
 
 constexpr int AT_BM = 128;      // queries per CTA
-constexpr int AT_BN = 128;      // keys per tile
+constexpr int AT_BN = 64;       // keys per tile
 constexpr int AT_D = 64;        // head dim
-constexpr int AT_THREADS = 320;  // TMA warp, MMA warp, 8 softmax warps (two threads per query row)
-constexpr uint32_t AT_TILE_BYTES = 128 * 64 * 2;  // 16 KB
-constexpr uint32_t AT_SMEM = 5 * AT_TILE_BYTES + 1024 + 128 + 3 * 1024;  // + row-max / row-sum exchange
+constexpr int AT_STAGES = 4;
+constexpr int AT_THREADS = 192;
+constexpr uint32_t AT_QBYTES = 128 * 64 * 2;  // 16 KB
+constexpr uint32_t AT_KBYTES = 64 * 64 * 2;   //  8 KB
+constexpr uint32_t AT_OFF_BAR = AT_QBYTES + AT_STAGES * 2 * AT_KBYTES;
+constexpr uint32_t AT_SMEM = AT_OFF_BAR + 256 + 1024;
 constexpr uint32_t TM_S = 0, TM_P = 128, TM_O = 192, TM_COLS = 256;
+constexpr float kLazyThreshold = 8.0f;  // log2 units
 
 struct AttnFwdArgs {
   __nv_bfloat16* o;
@@ -30,9 +36,6 @@ struct AttnFwdArgs {
   float scale;
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -45,16 +48,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base;
-  auto sK = [&](int st) { return smem_base + AT_TILE_BYTES * (1 + 2 * st); };
-  auto sV = [&](int st) { return smem_base + AT_TILE_BYTES * (2 + 2 * st); };
-  const uint32_t bar_base = smem_base + 5 * AT_TILE_BYTES;
-  const uint32_t q_full = bar_base;
-  auto kv_full = [&](int st) { return bar_base + 8u * (1 + st); };
-  auto kv_empty = [&](int st) { return bar_base + 8u * (3 + st); };
-  const uint32_t s_full = bar_base + 8u * 5;
-  const uint32_t p_ready = bar_base + 8u * 6;
-  const uint32_t o_full = bar_base + 8u * 7;
-  const uint32_t tmem_slot = bar_base + 8u * 8;
+  auto sK = [&](int st) { return smem_base + AT_QBYTES + st * 2 * AT_KBYTES; };
+  auto sV = [&](int st) { return smem_base + AT_QBYTES + st * 2 * AT_KBYTES + AT_KBYTES; };
+  const uint32_t bar = smem_base + AT_OFF_BAR;
+  const uint32_t q_full = bar;
+  auto kv_full = [&](int st) { return bar + 8u * (1 + st); };
+  auto kv_empty = [&](int st) { return bar + 8u * (1 + AT_STAGES + st); };
+  auto s_full = [&](int buf) { return bar + 8u * (1 + 2 * AT_STAGES + buf); };
+  const uint32_t p_ready = bar + 8u * (3 + 2 * AT_STAGES);
+  const uint32_t o_done = p_ready + 8, o_full = p_ready + 16, tmem_slot = p_ready + 24;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BM;
@@ -67,9 +69,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-    mbar_init(s_full, 1);
-    mbar_init(p_ready, 8);
+    for (int s = 0; s < AT_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    mbar_init(s_full(0), 1);
+    mbar_init(s_full(1), 1);
+    mbar_init(p_ready, 4);
+    mbar_init(o_done, 1);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -84,60 +88,79 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, AT_TILE_BYTES);
+    // whole warp loops (uniform control flow); one elected lane issues the TMA copies
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, AT_QBYTES);
       tma_load_3d(sQ, &tmQ, q_full, h * AT_D, q0, b);
-      for (int j = 0; j < num_tiles; ++j) {
-        const int st = j & 1;
-        mbar_wait(kv_empty(st), ((j >> 1) & 1) ^ 1u);
-        mbar_arrive_expect_tx(kv_full(st), 2 * AT_TILE_BYTES);
+    }
+    __syncwarp();
+    int st = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < num_tiles; ++j) {
+      mbar_wait(kv_empty(st), ph ^ 1u);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(kv_full(st), 2 * AT_KBYTES);
         tma_load_3d(sK(st), &tmK, kv_full(st), h * AT_D, j * AT_BN, b);
         tma_load_3d(sV(st), &tmV, kv_full(st), h * AT_D, j * AT_BN, b);
       }
+      __syncwarp();
+      if (++st == AT_STAGES) { st = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_qk = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);
-      const uint32_t idesc_pv = umma_idesc_bf16(AT_BM, AT_D, 0, 1);
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < num_tiles; ++j) {
-        const int st = j & 1;
-        mbar_wait(kv_full(st), (j >> 1) & 1);
-        tc_fence_after();
-        const uint64_t qd = umma_desc_kmajor(sQ), kd = umma_desc_kmajor(sK(st));
+    // whole warp loops; operands stay in uniform registers; one elected lane issues tcgen05.mma / commit
+    const uint32_t idesc_qk = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);
+    const uint32_t idesc_pv = umma_idesc_bf16(AT_BM, AT_D, 0, 1);
+    const uint64_t qd = umma_desc_kmajor(sQ);
+    auto issue_qk = [&](int j) {  // S[j&1] = Q K_j^T
+      const int st = j % AT_STAGES;
+      mbar_wait(kv_full(st), (j / AT_STAGES) & 1);
+      tc_fence_after();
+      const uint64_t kd = umma_desc_kmajor(sK(st));
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k) umma_ss(tmem_base + TM_S, qd + uint64_t(k * 2), kd + uint64_t(k * 2), idesc_qk, k > 0);
-        umma_commit(s_full);
-        mbar_wait(p_ready, j & 1);
-        tc_fence_after();
-        const uint64_t vd = umma_desc_mnmajor(sV(st), 8192);
+        for (int k = 0; k < AT_D / 16; ++k)
+          umma_ss(tmem_base + TM_S + (j & 1) * 64, qd + uint64_t(k * 2), kd + uint64_t(k * 2), idesc_qk, k > 0);
+        umma_commit(s_full(j & 1));
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int j = 0; j < num_tiles; ++j) {
+      // look-ahead: S[(j+1)&1] was last read by softmax(j-1), which finished before p_ready(j-1) fired
+      if (j + 1 < num_tiles) issue_qk(j + 1);
+      mbar_wait(p_ready, j & 1);
+      tc_fence_after();
+      const int st = j % AT_STAGES;
+      const uint64_t vd = umma_desc_mnmajor(sV(st), 8192);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < AT_BN / 16; ++k)
-          umma_ts(tmem_base + TM_O, tmem_base + TM_P + k * 8, vd + uint64_t(k * (2048 >> 4)), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          umma_ts(tmem_base + TM_O, tmem_base + TM_P + (j & 1) * 32 + k * 8, vd + uint64_t(k * 128), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(kv_empty(st));
+        umma_commit(o_done);
       }
-      umma_commit(o_full);
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(o_full);
+    __syncwarp();
   } else {
-    // ===================== softmax: two threads per query row =====================
+    // ===================== softmax: thread <-> query row =====================
     const int lane_group = warp & 3;
-    const int half = (warp - 2) >> 2;                    // key columns [64*half, 64*half+64)
     const uint32_t lane_addr = uint32_t(lane_group * 32) << 16;
-    const int r = lane_group * 32 + lane;                // row inside the tile
-    const int row = q0 + r;
-    float* xch = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 128);  // [3][2][128]
-    float m_run = -INFINITY;  // running max of raw scores (shared by both halves)
-    float l_run = 0.f;        // this thread's partial row sum
+    const int row = q0 + lane_group * 32 + lane;
+    float m_run = -INFINITY;  // reference max (raw score units); lags the true max by at most kLazyThreshold
+    float l_run = 0.f;
     for (int j = 0; j < num_tiles; ++j) {
-      mbar_wait(s_full, j & 1);
+      mbar_wait(s_full(j & 1), (j >> 1) & 1);
       tc_fence_after();
-      const int kv_valid = a.Nk - j * AT_BN - 64 * half;  // columns >= kv_valid (of this half) are padding
+      const int kv_valid = a.Nk - j * AT_BN;  // columns >= kv_valid are padding
       uint32_t s[64];
-      tmem_ld32(tmem_base + lane_addr + TM_S + 64 * half, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-      tmem_ld32(tmem_base + lane_addr + TM_S + 64 * half + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+      tmem_ld32(tmem_base + lane_addr + TM_S + (j & 1) * 64, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+      tmem_ld32(tmem_base + lane_addr + TM_S + (j & 1) * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
       tmem_ld_wait();
       float m_tile = -INFINITY;
-      if (kv_valid >= 64) {
+      if (kv_valid >= AT_BN) {
 #pragma unroll
         for (int i = 0; i < 64; ++i) m_tile = fmaxf(m_tile, __uint_as_float(s[i]));
       } else {
@@ -147,11 +170,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           m_tile = fmaxf(m_tile, __uint_as_float(s[i]));
         }
       }
-      float* mx = xch + (j & 1) * 256;
-      mx[half * 128 + r] = m_tile;
-      named_bar_sync(1, 256);
-      const float m_new = fmaxf(m_run, fmaxf(m_tile, mx[(half ^ 1) * 128 + r]));
-      const float alpha = fast_exp2((m_run - m_new) * a.scale_log2);  // 0 on the first tile (m_run = -inf)
+      // lazy rescaling: keep the old reference unless the max grew by more than 2^kLazyThreshold
+      const bool grow = (m_tile - m_run) * a.scale_log2 > kLazyThreshold;  // true on the first tile (m_run = -inf)
+      const float m_new = grow ? m_tile : m_run;
+      const float alpha = grow ? fast_exp2((m_run - m_new) * a.scale_log2) : 1.0f;
       const float m_scaled = m_new * a.scale_log2;
       float l_tile = 0.f;
 #pragma unroll
@@ -164,49 +186,55 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           l_tile += p0 + p1;
           pk[i] = pack_bf16(p0, p1);
         }
-        tmem_st16(tmem_base + lane_addr + TM_P + 32 * half + 16 * c, pk);
+        tmem_st16(tmem_base + lane_addr + TM_P + (j & 1) * 32 + 16 * c, pk);
       }
       l_run = l_run * alpha + l_tile;
       m_run = m_new;
-      // rescale this thread's half of the running O (PV(j-1) has retired: s_full(j) was committed after it)
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-        uint32_t o[32];
-        tmem_ld32(tmem_base + lane_addr + TM_O + 32 * half, o);
-        tmem_ld_wait();
+      if (j > 0 && __any_sync(0xffffffffu, grow)) {
+        // rescale the running O: PV(j-1) must have retired, PV(j) cannot start before p_ready(j)
+        mbar_wait(o_done, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tmem_base + lane_addr + TM_O + 32 * c, o);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-        tmem_st32(tmem_base + lane_addr + TM_O + 32 * half, o);
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(tmem_base + lane_addr + TM_O + 32 * c, o);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
     }
-    // ---- epilogue: O / l -> global (32 of the 64 head columns per thread), LSE ----
-    float* lx = xch + 512;
-    lx[half * 128 + r] = l_run;
-    named_bar_sync(1, 256);
-    const float l_tot = l_run + lx[(half ^ 1) * 128 + r];
+    // ---- epilogue: O / l -> global, LSE ----
     mbar_wait(o_full, 0);
     tc_fence_after();
-    const float inv_l = 1.0f / l_tot;
+    const float inv_l = 1.0f / l_run;
     const bool row_ok = row < a.Nq;
-    uint32_t o[32];
-    tmem_ld32(tmem_base + lane_addr + TM_O + 32 * half, o);
-    tmem_ld_wait();
-    if (row_ok) {
-      uint4* dst = reinterpret_cast<uint4*>(a.o + ((long long)b * a.Nq + row) * a.ldo + h * AT_D + 32 * half);
+    __nv_bfloat16* optr = a.o + ((long long)b * a.Nq + row) * a.ldo + h * AT_D;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + lane_addr + TM_O + c * 32, r);
+      tmem_ld_wait();
+      if (row_ok) {
+        uint4* dst = reinterpret_cast<uint4*>(optr + c * 32);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 t;
-        t.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
-        t.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
-        t.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
-        t.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
-        dst[i] = t;
+        for (int i = 0; i < 4; ++i) {
+          uint4 t;
+          t.x = pack_bf16(__uint_as_float(r[8 * i + 0]) * inv_l, __uint_as_float(r[8 * i + 1]) * inv_l);
+          t.y = pack_bf16(__uint_as_float(r[8 * i + 2]) * inv_l, __uint_as_float(r[8 * i + 3]) * inv_l);
+          t.z = pack_bf16(__uint_as_float(r[8 * i + 4]) * inv_l, __uint_as_float(r[8 * i + 5]) * inv_l);
+          t.w = pack_bf16(__uint_as_float(r[8 * i + 6]) * inv_l, __uint_as_float(r[8 * i + 7]) * inv_l);
+          dst[i] = t;
+        }
       }
-      if (half == 0 && a.lse) a.lse[((long long)b * a.H + h) * a.Nq + row] = m_run * a.scale + logf(l_tot);
+      __syncwarp();
     }
+    if (row_ok && a.lse) a.lse[((long long)b * a.H + h) * a.Nq + row] = m_run * a.scale + logf(l_run);
   }
 
   tc_fence_before();
@@ -219,7 +247,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 }  // namespace
 
-// 3-D map over a token-major bf16 matrix: dims (H*64 columns, N tokens, B), box (64, 128, 1).
+// 3-D map over a token-major bf16 matrix: dims (H*64 columns, N tokens, B), box (64, box_rows, 1).
 int make_head_map(CUtensorMap* m, const void* base, int H, int N, int B, long long ld, int box_rows) {
   uint64_t dims[3] = {(uint64_t)H * 64, (uint64_t)N, (uint64_t)B};
   uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)N * (uint64_t)ld * 2};
@@ -242,8 +270,8 @@ extern "C" int uc_attn_fwd(const uc_attn_fwd_params* p, uc_stream_t stream_) {
   CUtensorMap tmQ, tmK, tmV;
   int r;
   if ((r = make_head_map(&tmQ, p->q, p->H, p->Nq, p->B, p->ldq, 128))) return r;
-  if ((r = make_head_map(&tmK, p->k, p->H, p->Nk, p->B, p->ldk, 128))) return r;
-  if ((r = make_head_map(&tmV, p->v, p->H, p->Nk, p->B, p->ldv, 128))) return r;
+  if ((r = make_head_map(&tmK, p->k, p->H, p->Nk, p->B, p->ldk, AT_BN))) return r;
+  if ((r = make_head_map(&tmV, p->v, p->H, p->Nk, p->B, p->ldv, AT_BN))) return r;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);

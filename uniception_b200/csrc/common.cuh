@@ -44,6 +44,19 @@ __device__ __forceinline__ uint32_t lane_id() {
   return l;
 }
 
+// One lane of a fully converged warp.  ptxas understands elect.sync: code under this predicate keeps its
+// operands in uniform registers, so tcgen05.mma / TMA issue compiles to straight-line UTCHMMA / UTMALDG
+// instead of a per-lane R2UR + ELECT uniformisation loop (what `if (lane == 0)` produces).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -111,21 +111,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int total = g.num_m * g.num_n * g.split_k;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = blockIdx.x; item < total; item += gridDim.x) {
-        const int split = item % g.split_k;
-        const int tile = item / g.split_k;
-        const int m0 = g.n_fastest ? (tile / g.num_n) * BM : (tile % g.num_m) * BM;
-        const int n0 = g.n_fastest ? (tile % g.num_n) * BN : (tile / g.num_m) * BN;
-        const int kb0 = split * g.kb_per_split;
-        const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t sb = sa + C::A_BYTES;
+    // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+      const int split = item % g.split_k;
+      const int tile = item / g.split_k;
+      const int m0 = g.n_fastest ? (tile / g.num_n) * BM : (tile % g.num_m) * BM;
+      const int n0 = g.n_fastest ? (tile % g.num_n) * BN : (tile / g.num_m) * BN;
+      const int kb0 = split * g.kb_per_split;
+      const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+        const uint32_t sb = sa + C::A_BYTES;
+        if (elect_one()) {
           mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
           if (!g.a_mn) {
             tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
@@ -139,45 +139,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, full_bar(stage), n0 + j * 64, kb * BK);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BM, BN, g.a_mn, g.b_mn);
-      const uint32_t a_step = g.a_mn ? (2048u >> 4) : (32u >> 4);  // descriptor start-address step per UMMA_K
-      const uint32_t b_step = g.b_mn ? (2048u >> 4) : (32u >> 4);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < total; item += gridDim.x) {
-        const int split = item % g.split_k;
-        const int kb0 = split * g.kb_per_split;
-        const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
-        if (kb0 >= kb1) continue;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+    // ===================== MMA issuer (whole warp loops, operands uniform, one elected lane issues) =====================
+    const uint32_t idesc = umma_idesc_bf16(BM, BN, g.a_mn, g.b_mn);
+    const uint32_t a_step = g.a_mn ? (2048u >> 4) : (32u >> 4);  // descriptor start-address step per UMMA_K
+    const uint32_t b_step = g.b_mn ? (2048u >> 4) : (32u >> 4);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+      const int split = item % g.split_k;
+      const int kb0 = split * g.kb_per_split;
+      const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
+      if (kb0 >= kb1) continue;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t sb = sa + C::A_BYTES;
-          const uint64_t adesc = g.a_mn ? umma_desc_mnmajor(sa, 8192) : umma_desc_kmajor(sa);
-          const uint64_t bdesc = g.b_mn ? umma_desc_mnmajor(sb, 8192) : umma_desc_kmajor(sb);
+        const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+        const uint32_t sb = sa + C::A_BYTES;
+        const uint64_t adesc = g.a_mn ? umma_desc_mnmajor(sa, 8192) : umma_desc_kmajor(sa);
+        const uint64_t bdesc = g.b_mn ? umma_desc_mnmajor(sb, 8192) : umma_desc_kmajor(sb);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_ss(d_tmem, adesc + uint64_t(k * a_step), bdesc + uint64_t(k * b_step), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (elect_one()) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
     }
   } else {
     // ===================== epilogue =====================
