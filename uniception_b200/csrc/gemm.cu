@@ -8,6 +8,8 @@
 // main loop of tile i+1.  Both operands may be K-major or MN-major (UMMA descriptor major bits), so
 // forward (x W^T), dgrad (dy W) and wgrad (dy^T x, split-K + fp32 red.add) share this one kernel without
 // any transposition pass.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace uc {
@@ -65,6 +67,73 @@ __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* p, const float (
     t.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
     t.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
     q[i] = t;
+  }
+}
+
+// Fused epilogue on one 32-column chunk of one accumulator row (fp32 bits in r[]): bias -> 2-D RoPE -> GELU
+// (+ pre-activation) / GELU' -> residual -> store bf16 / fp32 / red.add.
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int row, int n, int pos_y, int pos_x, const uint32_t (&r)[32]) {
+  const int epi = g.epilogue;
+        float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (epi & UC_EPI_BIAS) {
+    const float4* b4 = reinterpret_cast<const float4*>(g.bias + n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 b = __ldg(b4 + j);
+      v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
+  }
+  if ((epi & UC_EPI_ROPE) && n < g.rope_cols) {
+    const int p = ((n >> 5) & 1) ? pos_x : pos_y;
+    const float4* t4 = reinterpret_cast<const float4*>(g.rope_table + (size_t)p * 32);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 cs = __ldg(t4 + j);  // (cos_{2j}, sin_{2j}, cos_{2j+1}, sin_{2j+1})
+      float u0 = v[2 * j], w0 = v[2 * j + 16];
+      v[2 * j] = u0 * cs.x - w0 * cs.y;
+      v[2 * j + 16] = w0 * cs.x + u0 * cs.y;
+      float u1 = v[2 * j + 1], w1 = v[2 * j + 17];
+      v[2 * j + 1] = u1 * cs.z - w1 * cs.w;
+      v[2 * j + 17] = w1 * cs.z + u1 * cs.w;
+    }
+  }
+  const size_t off = (size_t)row * g.ldc + n;
+  if (epi & UC_EPI_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = round_bf16(v[j]);
+    store_row32_bf16(g.aux_out + off, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  }
+  if (epi & UC_EPI_GELU_BWD) {
+    float h[32];
+    load_row32_bf16(g.aux_in + off, h);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(h[j]);
+  }
+  if (epi & UC_EPI_RESIDUAL) {
+    float h[32];
+    load_row32_bf16(g.residual + off, h);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += h[j];
+  }
+  if (g.c_f32) {
+    float* cp = reinterpret_cast<float*>(g.c) + off;
+    if (epi & UC_EPI_ATOMIC) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + 4 * j), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                     "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                     : "memory");
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        reinterpret_cast<float4*>(cp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  } else {
+    store_row32_bf16(reinterpret_cast<__nv_bfloat16*>(g.c) + off, v);
   }
 }
 
@@ -217,67 +286,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tmem_ld32(tmem_base + (uint32_t(lane_group * 32) << 16) + uint32_t(acc * BN + col), r);
         tmem_ld_wait();
         if (n >= g.n || !row_ok) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (epi & UC_EPI_BIAS) {
-          const float4* b4 = reinterpret_cast<const float4*>(g.bias + n);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 b = __ldg(b4 + j);
-            v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-          }
-        }
-        if ((epi & UC_EPI_ROPE) && n < g.rope_cols) {
-          const int p = ((n >> 5) & 1) ? pos_x : pos_y;
-          const float4* t4 = reinterpret_cast<const float4*>(g.rope_table + (size_t)p * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 cs = __ldg(t4 + j);  // (cos_{2j}, sin_{2j}, cos_{2j+1}, sin_{2j+1})
-            float u0 = v[2 * j], w0 = v[2 * j + 16];
-            v[2 * j] = u0 * cs.x - w0 * cs.y;
-            v[2 * j + 16] = w0 * cs.x + u0 * cs.y;
-            float u1 = v[2 * j + 1], w1 = v[2 * j + 17];
-            v[2 * j + 1] = u1 * cs.z - w1 * cs.w;
-            v[2 * j + 17] = w1 * cs.z + u1 * cs.w;
-          }
-        }
-        const size_t off = (size_t)row * g.ldc + n;
-        if (epi & UC_EPI_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = round_bf16(v[j]);
-          store_row32_bf16(g.aux_out + off, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        }
-        if (epi & UC_EPI_GELU_BWD) {
-          float h[32];
-          load_row32_bf16(g.aux_in + off, h);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(h[j]);
-        }
-        if (epi & UC_EPI_RESIDUAL) {
-          float h[32];
-          load_row32_bf16(g.residual + off, h);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += h[j];
-        }
-        if (g.c_f32) {
-          float* cp = reinterpret_cast<float*>(g.c) + off;
-          if (epi & UC_EPI_ATOMIC) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + 4 * j), "f"(v[4 * j]), "f"(v[4 * j + 1]),
-                           "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
-                           : "memory");
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              reinterpret_cast<float4*>(cp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-        } else {
-          store_row32_bf16(reinterpret_cast<__nv_bfloat16*>(g.c) + off, v);
-        }
+        epilogue_chunk(g, row, n, pos_y, pos_x, r);
       }
       tc_fence_before();
       __syncwarp();
@@ -293,6 +302,205 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair GEMM: cluster (2,1,1), tcgen05.mma.cta_group::2, 256 x 256 output tile per pair.
+// CTA rank r stages A rows [m0+128r, +128) and B columns [n0+128r, +128) (32 KB / stage instead of 48 KB, so the
+// L2->SM operand stream per FLOP drops by a third: 128 FLOP/B instead of 85); the leader CTA's elected lane issues
+// the 256x256x16 MMAs for both SMs; each CTA's TMEM holds its own 128 x 256 fp32 accumulator (double-buffered) and
+// each CTA runs the same fused epilogue on its rows.  Barriers: TMA of both CTAs credit the leader's `full`;
+// `empty` / `tmem_full` are released in both CTAs by a multicast tcgen05.commit; the peer's epilogue warps arrive
+// remotely on the leader's `tmem_empty`.
+// ------------------------------------------------------------------------------------------------
+constexpr int G2_BN = 256;
+constexpr int G2_STAGES = 6;
+constexpr uint32_t G2_A_BYTES = 128 * BK * 2, G2_B_BYTES = 128 * BK * 2, G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+constexpr uint32_t G2_SMEM = G2_STAGES * G2_STAGE_BYTES + 1024 + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  constexpr int STAGES = G2_STAGES;
+  constexpr int BN = G2_BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * G2_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);   // leader: its own producer's arrive.expect_tx (bytes of BOTH CTAs)
+      mbar_init(empty_bar(s), 1);  // one multicast commit from the leader's MMA lane
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 2 * NUM_EPI_WARPS);  // leader: epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();  // barrier inits visible to the peer before any remote arrive / TMA credit
+  if (warp == 1) {
+    tmem_alloc2(tmem_slot, 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int total = g.num_m * g.num_n * g.split_k;  // num_m counts 256-row blocks here
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = cluster_id; item < total; item += num_clusters) {
+      const int split = item % g.split_k;
+      const int tile = item / g.split_k;
+      const int m0 = (g.n_fastest ? (tile / g.num_n) : (tile % g.num_m)) * 256 + 128 * (int)rank;
+      const int n0 = (g.n_fastest ? (tile % g.num_n) : (tile / g.num_m)) * BN + 128 * (int)rank;
+      const int kb0 = split * g.kb_per_split;
+      const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sa = smem_base + stage * G2_STAGE_BYTES;
+        const uint32_t sb = sa + G2_A_BYTES;
+        if (elect_one()) {
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * G2_STAGE_BYTES);
+          if (!g.a_mn) {
+            tma2_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
+          } else {
+            tma2_load_2d(sa, &tmA, full_bar(stage), m0, kb * BK);
+            tma2_load_2d(sa + 8192, &tmA, full_bar(stage), m0 + 64, kb * BK);
+          }
+          if (!g.b_mn) {
+            tma2_load_2d(sb, &tmB, full_bar(stage), kb * BK, n0);
+          } else {
+            tma2_load_2d(sb, &tmB, full_bar(stage), n0, kb * BK);
+            tma2_load_2d(sb + 8192, &tmB, full_bar(stage), n0 + 64, kb * BK);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(256, BN, g.a_mn, g.b_mn);
+      const uint32_t a_step = g.a_mn ? (2048u >> 4) : (32u >> 4);
+      const uint32_t b_step = g.b_mn ? (2048u >> 4) : (32u >> 4);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = cluster_id; item < total; item += num_clusters) {
+        const int split = item % g.split_k;
+        const int kb0 = split * g.kb_per_split;
+        const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
+        if (kb0 >= kb1) continue;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * G2_STAGE_BYTES;
+          const uint32_t sb = sa + G2_A_BYTES;
+          const uint64_t adesc = g.a_mn ? umma_desc_mnmajor(sa, 8192) : umma_desc_kmajor(sa);
+          const uint64_t bdesc = g.b_mn ? umma_desc_mnmajor(sb, 8192) : umma_desc_kmajor(sb);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma2_ss(d_tmem, adesc + uint64_t(k * a_step), bdesc + uint64_t(k * b_step), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma2_commit_mc(empty_bar(stage));
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (elect_one()) umma2_commit_mc(tfull_bar(acc));
+        __syncwarp();
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int e = warp - 2;
+    const int lane_group = warp & 3;
+    const int col_half = e >> 2;
+    constexpr int CHUNKS = BN / 2 / 32;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = cluster_id; item < total; item += num_clusters) {
+      const int split = item % g.split_k;
+      const int tile = item / g.split_k;
+      const int m0 = (g.n_fastest ? (tile / g.num_n) : (tile % g.num_m)) * 256 + 128 * (int)rank;
+      const int n0 = (g.n_fastest ? (tile % g.num_n) : (tile / g.num_m)) * BN;
+      const int kb0 = split * g.kb_per_split;
+      const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
+      if (kb0 >= kb1) continue;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m0 + lane_group * 32 + lane;
+      const bool row_ok = row < g.m;
+      int pos_y = 0, pos_x = 0;
+      if ((g.epilogue & UC_EPI_ROPE) && row_ok) {
+        pos_y = g.positions[2 * row];
+        pos_x = g.positions[2 * row + 1];
+      }
+#pragma unroll 1
+      for (int ch = 0; ch < CHUNKS; ++ch) {
+        const int col = col_half * (BN / 2) + ch * 32;
+        const int n = n0 + col;
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + (uint32_t(lane_group * 32) << 16) + uint32_t(acc * BN + col), r);
+        tmem_ld_wait();
+        if (n >= g.n || !row_ok) continue;
+        epilogue_chunk(g, row, n, pos_y, pos_x, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_cluster(tempty_bar(acc), 0);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody exits (or frees TMEM) while the peer can still touch this CTA's smem / barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, int grid, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
+    UC_REQUIRE(e == cudaSuccess, UC_ERR_CUDA, "uc_gemm: cudaFuncSetAttribute(gemm2) failed: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  gemm2_kernel<<<grid, GEMM_THREADS, G2_SMEM, stream>>>(tmA, tmB, g);
+  return check_launch("uc_gemm(cta_pair)");
 }
 
 template <int BN>
@@ -333,34 +541,46 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
              "uc_gemm: UC_EPI_ROPE needs positions, rope_table and rope_cols %% 64 == 0");
   UC_REQUIRE(!(epi & UC_EPI_ATOMIC) || p->c_dtype == UC_DTYPE_F32, UC_ERR_BAD_DTYPE, "uc_gemm: atomic epilogue needs fp32 C");
 
-  const int num_m = (p->m + BM - 1) / BM;
   const int num_kb = (p->k + BK - 1) / BK;
   const int sms = sm_count();
-  // tile width: maximise (wave efficiency) x (per-tile MMA efficiency; narrow tiles are smem-bandwidth bound)
+  // tile shape: maximise (wave efficiency) x (per-tile efficiency).  "pair" = 256x256 per CTA pair (cta_group::2):
+  // a third less L2->SM operand traffic per FLOP; narrow single-CTA tiles are smem-bandwidth bound.
   const bool atomic = (epi & UC_EPI_ATOMIC) != 0;
-  int bn = 64;
+  static const int pair_env = [] { const char* e = getenv("UC_GEMM_PAIR"); return e ? atoi(e) : -1; }();
+  int bn = 0;
+  bool pair = false;
   {
     double best = -1.0;
-    const int cand[3] = {256, 128, 64};
-    const double rate[3] = {1.0, 0.9, 0.6};
-    for (int i = 0; i < 3; ++i) {
+    // measured on B200 (profiles/): the pair kernel reaches 1.35 PFLOP/s at K=4096 but needs a long K loop to
+    // amortise its 256x256 tile prologue / epilogue; at K=768 it only ties the single-CTA kernel
+    const double kf = num_kb <= 8 ? 0.0 : (num_kb >= 40 ? 1.0 : double(num_kb - 8) / 32.0);
+    const int cand[4] = {256, 128, 64, 256};
+    const double rate[4] = {1.0, 0.9, 0.6, 0.95 + 0.4 * kf};
+    for (int i = 0; i < 4; ++i) {
+      const bool is_pair = (i == 3);
+      if (is_pair && pair_env == 0) continue;
       if (p->n % cand[i] != 0) continue;
-      const long long tiles = (long long)num_m * (p->n / cand[i]);
-      const long long waves = (tiles + sms - 1) / sms;
-      // split-K (wgrad) fills the machine by itself, so only the MMA efficiency matters there
-      const double eff = (atomic ? 1.0 : double(tiles) / double(waves * sms)) * rate[i];
-      if (eff > best) { best = eff; bn = cand[i]; }
+      const int bm = is_pair ? 256 : BM;
+      const int slots = is_pair ? sms / 2 : sms;
+      const long long tiles = (long long)((p->m + bm - 1) / bm) * (p->n / cand[i]);
+      const long long waves = (tiles + slots - 1) / slots;
+      // split-K (wgrad) fills the machine by itself, so only the per-tile efficiency matters there
+      double eff = (atomic ? 1.0 : double(tiles) / double(waves * slots)) * rate[i];
+      if (is_pair && pair_env == 1) eff = 10.0;
+      if (eff > best) { best = eff; bn = cand[i]; pair = is_pair; }
     }
-    if (best < 0) bn = 32;
   }
-  UC_REQUIRE(bn != 32, UC_ERR_BAD_SHAPE, "uc_gemm: n=%d must be a multiple of 64", p->n);
+  UC_REQUIRE(bn != 0, UC_ERR_BAD_SHAPE, "uc_gemm: n=%d must be a multiple of 64", p->n);
+  const int bm_eff = pair ? 256 : BM;
+  const int slots = pair ? sms / 2 : sms;
+  const int num_m = (p->m + bm_eff - 1) / bm_eff;
   const int num_n = p->n / bn;
   int split_k = p->split_k;
   if (split_k <= 0) {
     split_k = 1;
     if (atomic) {
       const long long tiles = (long long)num_m * num_n;
-      split_k = (int)((sms + tiles - 1) / tiles);
+      split_k = (int)((slots + tiles - 1) / tiles);
       if (split_k > num_kb / 4) split_k = num_kb / 4;
       if (split_k < 1) split_k = 1;
     }
@@ -380,7 +600,7 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
     strides[0] = (uint64_t)p->lda * 2;
     int r = make_tensor_map(&tmA, p->a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (r) return r;
-    if (!p->b_layout) { dims[0] = p->k; dims[1] = p->n; box[0] = BK; box[1] = bn; }
+    if (!p->b_layout) { dims[0] = p->k; dims[1] = p->n; box[0] = BK; box[1] = pair ? 128 : bn; }
     else { dims[0] = p->n; dims[1] = p->k; box[0] = 64; box[1] = BK; }
     strides[0] = (uint64_t)p->ldb * 2;
     r = make_tensor_map(&tmB, p->b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -403,6 +623,10 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
   g.positions = p->positions; g.rope_table = p->rope_table;
 
   const long long total = (long long)num_m * num_n * split_k;
+  if (pair) {
+    const int clusters = (int)(total < slots ? total : slots);
+    return launch2(tmA, tmB, g, 2 * clusters, stream);
+  }
   const int grid = (int)(total < sms ? total : sms);
   if (bn == 256) return launch<256>(tmA, tmB, g, grid, stream);
   if (bn == 128) return launch<128>(tmA, tmB, g, grid, stream);
