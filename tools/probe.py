@@ -310,6 +310,17 @@ def check_perf():
     g = torch.ones(1024, device="cuda")
     ms = _time(lambda: ops.layernorm_fwd(x, g, g, 1e-6))
     print(f"[perf] layernorm fwd 16384x1024: {ms*1e3:.1f} us = {2*x.numel()*2/ms/1e6:.0f} GB/s", flush=True)
+    y, mean, rstd = ops.layernorm_fwd(x, g, g, 1e-6)
+    dy, dres = torch.randn_like(x), torch.randn_like(x)
+    dg, db = torch.zeros(1024, device="cuda"), torch.zeros(1024, device="cuda")
+    ms = _time(lambda: ops.layernorm_bwd(dy, x, g, mean, rstd, dg, db, dres=dres))
+    print(f"[perf] layernorm bwd 16384x1024 (+dres): {ms*1e3:.1f} us = {4*x.numel()*2/ms/1e6:.0f} GB/s", flush=True)
+    big = torch.randn(16384, 4096, device="cuda").bfloat16()
+    out = torch.zeros(4096, device="cuda")
+    ms = _time(lambda: ops.colsum_(big, out))
+    print(f"[perf] colsum 16384x4096: {ms*1e3:.1f} us = {big.numel()*2/ms/1e6:.0f} GB/s", flush=True)
+    ms = _time(lambda: ops.colsum_(x, out[:1024]))
+    print(f"[perf] colsum 16384x1024: {ms*1e3:.1f} us = {x.numel()*2/ms/1e6:.0f} GB/s", flush=True)
     return True
 
 

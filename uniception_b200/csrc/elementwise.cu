@@ -91,66 +91,108 @@ __device__ __forceinline__ void store8(void* base, int dtype, int64_t elem_off, 
 
 template <int CH>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(uc_layernorm_fwd_params p) {
+  // one warp per row, TWO rows in flight per warp (the kernel is latency-bound, not issue-bound)
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const float inv_c = 1.0f / (float)p.C;
-  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < p.rows; row += gridDim.x * warps_per_block) {
-    float x[CH][8];
-    float sum = 0.f;
+  const int stride = gridDim.x * warps_per_block;
+  for (int row0 = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row0 < p.rows; row0 += 2 * stride) {
+    const int row1 = row0 + stride;
+    const bool has1 = row1 < p.rows;
+    float x[2][CH][8];
+    float sum[2] = {0.f, 0.f};
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int col = c * 256 + lane * 8;
-      if (col < p.C) {
-        load8(p.x, p.x_dtype, (int64_t)row * p.C + col, x[c]);
+    for (int r = 0; r < 2; ++r) {
+      const int row = r ? row1 : row0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sum += x[c][j];
-      } else {
+      for (int c = 0; c < CH; ++c) {
+        const int col = c * 256 + lane * 8;
+        if (col < p.C && (r == 0 || has1)) {
+          load8(p.x, p.x_dtype, (int64_t)row * p.C + col, x[r][c]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[c][j] = 0.f;
+          for (int j = 0; j < 8; ++j) x[r][c][j] = 0.f;
+        }
       }
     }
-    const float mean = warp_sum(sum) * inv_c;
-    float sq = 0.f;
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int col = c * 256 + lane * 8;
-      if (col < p.C) {
+    for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { const float d = x[c][j] - mean; sq += d * d; }
+      for (int c = 0; c < CH; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum[r] += x[r][c][j];
+    const float mean[2] = {warp_sum(sum[0]) * inv_c, warp_sum(sum[1]) * inv_c};
+    float sq[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int col = c * 256 + lane * 8;
+        if (col < p.C) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float d = x[r][c][j] - mean[r]; sq[r] += d * d; }
+        }
       }
-    }
-    const float rstd = rsqrtf(warp_sum(sq) * inv_c + p.eps);
-    if (lane == 0) {
-      if (p.mean) p.mean[row] = mean;
-      if (p.rstd) p.rstd[row] = rstd;
-    }
+    const float rstd[2] = {rsqrtf(warp_sum(sq[0]) * inv_c + p.eps), rsqrtf(warp_sum(sq[1]) * inv_c + p.eps)};
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int col = c * 256 + lane * 8;
-      if (col < p.C) {
-        float g[8], b[8], y[8];
-        load8(p.gamma, UC_DTYPE_F32, col, g);
-        load8(p.beta, UC_DTYPE_F32, col, b);
+    for (int r = 0; r < 2; ++r) {
+      const int row = r ? row1 : row0;
+      if (r == 1 && !has1) break;
+      if (lane == 0) {
+        if (p.mean) p.mean[row] = mean[r];
+        if (p.rstd) p.rstd[row] = rstd[r];
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = (x[c][j] - mean) * rstd * g[j] + b[j];
-        store8(p.y, p.y_dtype, (int64_t)row * p.C + col, y);
+      for (int c = 0; c < CH; ++c) {
+        const int col = c * 256 + lane * 8;
+        if (col < p.C) {
+          float g[8], b[8], y[8];
+          load8(p.gamma, UC_DTYPE_F32, col, g);
+          load8(p.beta, UC_DTYPE_F32, col, b);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[j] = (x[r][c][j] - mean[r]) * rstd[r] * g[j] + b[j];
+          store8(p.y, p.y_dtype, (int64_t)row * p.C + col, y);
+        }
       }
     }
   }
 }
 
 // dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)) [+ dres];  dgamma += sum dy*xhat;  dbeta += sum dy
-// One warp per row.  Pass 1 streams x / dy once (row statistics + per-lane dgamma/dbeta partials), pass 2
-// re-reads the same 2-4 KB row (L1-resident) to form dx, so only the 2*CH*8 partial sums live in registers
-// across rows (2 blocks / SM).  Block partials are combined warp-by-warp in smem (no smem atomics) and leave
-// the block as one global atomicAdd per column.
-template <int CH>
+// One warp per row, latency-bound: x, dy and dres of a row are requested TOGETHER (one exposed memory latency per
+// row) and kept in registers in their packed 16-byte form; only the 2*CH*8 dgamma/dbeta partial sums persist across
+// rows.  Block partials are combined warp-by-warp in smem (no smem atomics), one global atomicAdd per column.
+struct Raw8 { uint4 a; uint4 b; };  // 8 elements: bf16 -> a only, fp32 -> a,b
+__device__ __forceinline__ Raw8 load_raw8(const void* base, int dtype, int64_t off) {
+  Raw8 r;
+  if (dtype == UC_DTYPE_BF16) {
+    r.a = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(base) + off));
+    r.b = make_uint4(0, 0, 0, 0);
+  } else {
+    const uint4* q = reinterpret_cast<const uint4*>(static_cast<const float*>(base) + off);
+    r.a = __ldg(q);
+    r.b = __ldg(q + 1);
+  }
+  return r;
+}
+__device__ __forceinline__ void unpack8(const Raw8& r, int dtype, float (&v)[8]) {
+  if (dtype == UC_DTYPE_BF16) {
+    v[0] = bf16_lo(r.a.x); v[1] = bf16_hi(r.a.x); v[2] = bf16_lo(r.a.y); v[3] = bf16_hi(r.a.y);
+    v[4] = bf16_lo(r.a.z); v[5] = bf16_hi(r.a.z); v[6] = bf16_lo(r.a.w); v[7] = bf16_hi(r.a.w);
+  } else {
+    v[0] = __uint_as_float(r.a.x); v[1] = __uint_as_float(r.a.y); v[2] = __uint_as_float(r.a.z); v[3] = __uint_as_float(r.a.w);
+    v[4] = __uint_as_float(r.b.x); v[5] = __uint_as_float(r.b.y); v[6] = __uint_as_float(r.b.z); v[7] = __uint_as_float(r.b.w);
+  }
+}
+
+template <int CH, bool BF16_IN>
 __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(uc_layernorm_bwd_params p) {
   extern __shared__ float red[];  // [2][C]
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
   const float inv_c = 1.0f / (float)p.C;
+  const int xdt = BF16_IN ? UC_DTYPE_BF16 : p.x_dtype, ydt = BF16_IN ? UC_DTYPE_BF16 : p.dy_dtype;
   for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) red[i] = 0.f;
   float dg[CH][8], db[CH][8];
 #pragma unroll
@@ -159,16 +201,27 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(uc_layernorm_bwd_
     for (int j = 0; j < 8; ++j) { dg[c][j] = 0.f; db[c][j] = 0.f; }
 
   for (int row = blockIdx.x * warps_per_block + warp; row < p.rows; row += gridDim.x * warps_per_block) {
-    const float mean = p.mean[row], rstd = p.rstd[row];
     const int64_t base = (int64_t)row * p.C;
+    Raw8 rx[CH], rdy[CH];
+    uint4 rres[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < p.C) {
+        rx[c] = load_raw8(p.x, xdt, base + col);
+        rdy[c] = load_raw8(p.dy, ydt, base + col);
+        if (p.dres) rres[c] = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.dres) + base + col));
+      }
+    }
+    const float mean = p.mean[row], rstd = p.rstd[row];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < p.C) {
         float x[8], dy[8], g[8];
-        load8(p.x, p.x_dtype, base + col, x);
-        load8(p.dy, p.dy_dtype, base + col, dy);
+        unpack8(rx[c], xdt, x);
+        unpack8(rdy[c], ydt, dy);
         load8(p.gamma, UC_DTYPE_F32, col, g);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -188,14 +241,16 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(uc_layernorm_bwd_
       const int col = c * 256 + lane * 8;
       if (col < p.C) {
         float x[8], dy[8], g[8], dx[8];
-        load8(p.x, p.x_dtype, base + col, x);
-        load8(p.dy, p.dy_dtype, base + col, dy);
+        unpack8(rx[c], xdt, x);
+        unpack8(rdy[c], ydt, dy);
         load8(p.gamma, UC_DTYPE_F32, col, g);
 #pragma unroll
         for (int j = 0; j < 8; ++j) dx[j] = rstd * (g[j] * dy[j] - s1 - (x[j] - mean) * rstd * s2);
         if (p.dres) {
+          Raw8 rr;
+          rr.a = rres[c];
           float r[8];
-          load8(p.dres, UC_DTYPE_BF16, base + col, r);
+          unpack8(rr, UC_DTYPE_BF16, r);
 #pragma unroll
           for (int j = 0; j < 8; ++j) dx[j] += r[j];
         }
@@ -260,7 +315,18 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x,
   const int col = blockIdx.x * 256 + lane * 8;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (col < cols) {
-    for (int row = blockIdx.y * 8 + warp; row < rows; row += gridDim.y * 8) {
+    const int stride = gridDim.y * 8;
+    int row = blockIdx.y * 8 + warp;
+    for (; row + 3 * stride < rows; row += 4 * stride) {  // 4 independent 16-byte loads in flight per lane
+      float v0[8], v1[8], v2[8], v3[8];
+      load8(x, dtype, (int64_t)row * ld + col, v0);
+      load8(x, dtype, (int64_t)(row + stride) * ld + col, v1);
+      load8(x, dtype, (int64_t)(row + 2 * stride) * ld + col, v2);
+      load8(x, dtype, (int64_t)(row + 3 * stride) * ld + col, v3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += (v0[j] + v1[j]) + (v2[j] + v3[j]);
+    }
+    for (; row < rows; row += stride) {
       float v[8];
       load8(x, dtype, (int64_t)row * ld + col, v);
 #pragma unroll
@@ -441,11 +507,18 @@ extern "C" int uc_layernorm_bwd(const uc_layernorm_bwd_params* p, uc_stream_t st
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const size_t sm = 2 * p->C * sizeof(float);
   const int ch = (p->C + 255) / 256;
-  if (ch <= 1) layernorm_bwd_kernel<1><<<grid, 256, sm, stream>>>(*p);
-  else if (ch <= 2) layernorm_bwd_kernel<2><<<grid, 256, sm, stream>>>(*p);
-  else if (ch <= 3) layernorm_bwd_kernel<3><<<grid, 256, sm, stream>>>(*p);
-  else if (ch <= 4) layernorm_bwd_kernel<4><<<grid, 256, sm, stream>>>(*p);
-  else layernorm_bwd_kernel<8><<<grid, 256, sm, stream>>>(*p);
+  const bool bf = p->x_dtype == UC_DTYPE_BF16 && p->dy_dtype == UC_DTYPE_BF16;
+#define UC_LN_BWD(CHV)                                                                  \
+  do {                                                                                  \
+    if (bf) layernorm_bwd_kernel<CHV, true><<<grid, 256, sm, stream>>>(*p);             \
+    else layernorm_bwd_kernel<CHV, false><<<grid, 256, sm, stream>>>(*p);               \
+  } while (0)
+  if (ch <= 1) UC_LN_BWD(1);
+  else if (ch <= 2) UC_LN_BWD(2);
+  else if (ch <= 3) UC_LN_BWD(3);
+  else if (ch <= 4) UC_LN_BWD(4);
+  else UC_LN_BWD(8);
+#undef UC_LN_BWD
   return check_launch("uc_layernorm_bwd");
 }
 
