@@ -223,9 +223,18 @@ def run_b200(args):
     for _ in range(2):
         step_resident()
     torch.cuda.synchronize()
-    gemm_ms = sum(s.elapsed_time(e) for (s, e, _f) in ops.PROFILE)
-    gemm_flop = sum(f for (_s, _e, f) in ops.PROFILE)
+    gemm_ms = sum(rec[0].elapsed_time(rec[1]) for rec in ops.PROFILE)
+    gemm_flop = sum(rec[2] for rec in ops.PROFILE)
     n_gemm = len(ops.PROFILE)
+    if args.gemm_breakdown and rank == 0:
+        by = {}
+        for rec in ops.PROFILE:
+            t = by.setdefault(rec[3], [0, 0.0, 0.0])
+            t[0] += 1
+            t[1] += rec[0].elapsed_time(rec[1])
+            t[2] += rec[2]
+        for key, (cnt, t_ms, fl) in sorted(by.items(), key=lambda kv: -kv[1][1]):
+            print(f"[gemm] m,n,k,aL,bL,epi={key}: n={cnt} total {t_ms:.2f} ms  avg {t_ms/cnt*1e3:.1f} us  {fl/t_ms/1e9:.0f} TFLOP/s", file=sys.stderr)
     ops.PROFILE = None
     sustained, burst, peak_src = _peaks()
 
@@ -272,6 +281,7 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--pairs-per-gpu", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm-breakdown", action="store_true", help="print per-shape GEMM timings of the instrumented steps to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

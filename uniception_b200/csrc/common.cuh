@@ -131,6 +131,12 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t
                "r"(src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -295,9 +301,31 @@ __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v 
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7) on the fast MUFU paths: one rcp + one ex2 + 7 FMA.
+// The same exp(-x^2/2) serves the Gaussian term of GELU', so GELU' costs no second transcendental.
+// (CUDA's erff() is ~3x the instructions; the GELU epilogues of fc1 / fc2-dgrad were math-bound with it.)
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& gauss) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170f));  // exp(-x^2/2)
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);          // erf(|x|/sqrt2)
+  cdf = fmaf(copysignf(0.5f, x), erf_abs, 0.5f);            // Phi(x) = 0.5 (1 + erf(x/sqrt2))
+  gauss = e * 0.3989422804014327f;                          // phi(x)
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float cdf, g;
+  gelu_parts(x, cdf, g);
+  return x * cdf;
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+  float cdf, g;
+  gelu_parts(x, cdf, g);
+  return fmaf(x, g, cdf);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

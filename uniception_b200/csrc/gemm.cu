@@ -70,11 +70,12 @@ __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* p, const float (
   }
 }
 
-// Fused epilogue on one 32-column chunk of one accumulator row (fp32 bits in r[]): bias -> 2-D RoPE -> GELU
-// (+ pre-activation) / GELU' -> residual -> store bf16 / fp32 / red.add.
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int row, int n, int pos_y, int pos_x, const uint32_t (&r)[32]) {
+// Fused epilogue math on one 32-column chunk of one accumulator row (fp32 bits in r[]):
+// bias -> 2-D RoPE -> GELU (pre-activation returned in pre[]) / GELU' -> residual.  No stores.
+__device__ __forceinline__ void epilogue_math(const GemmArgs& g, int row, int n, int pos_y, int pos_x, bool row_ok,
+                                              const uint32_t (&r)[32], float (&v)[32], float (&pre)[32],
+                                              const float* hin = nullptr /* staged aux_in / residual values, or load */) {
   const int epi = g.epilogue;
-        float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
   if (epi & UC_EPI_BIAS) {
@@ -102,26 +103,44 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int row, int n
   const size_t off = (size_t)row * g.ldc + n;
   if (epi & UC_EPI_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = round_bf16(v[j]);
-    store_row32_bf16(g.aux_out + off, v);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    for (int j = 0; j < 32; ++j) {
+      pre[j] = round_bf16(v[j]);
+      v[j] = gelu_erf(pre[j]);
+    }
   }
-  if (epi & UC_EPI_GELU_BWD) {
+  if ((epi & UC_EPI_GELU_BWD) && row_ok) {
     float h[32];
-    load_row32_bf16(g.aux_in + off, h);
+    if (hin) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) h[j] = hin[j];
+    } else {
+      load_row32_bf16(g.aux_in + off, h);
+    }
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(h[j]);
   }
-  if (epi & UC_EPI_RESIDUAL) {
+  if ((epi & UC_EPI_RESIDUAL) && row_ok) {
     float h[32];
-    load_row32_bf16(g.residual + off, h);
+    if (hin) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) h[j] = hin[j];
+    } else {
+      load_row32_bf16(g.residual + off, h);
+    }
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += h[j];
   }
+}
+
+// epilogue math + direct row-per-thread global stores (single-CTA kernels)
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int row, int n, int pos_y, int pos_x, const uint32_t (&r)[32]) {
+  float v[32], pre[32];
+  epilogue_math(g, row, n, pos_y, pos_x, true, r, v, pre);
+  const size_t off = (size_t)row * g.ldc + n;
+  if (g.epilogue & UC_EPI_GELU) store_row32_bf16(g.aux_out + off, pre);
   if (g.c_f32) {
     float* cp = reinterpret_cast<float*>(g.c) + off;
-    if (epi & UC_EPI_ATOMIC) {
+    if (g.epilogue & UC_EPI_ATOMIC) {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + 4 * j), "f"(v[4 * j]), "f"(v[4 * j + 1]),
@@ -314,22 +333,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // remotely on the leader's `tmem_empty`.
 // ------------------------------------------------------------------------------------------------
 constexpr int G2_BN = 256;
-constexpr int G2_STAGES = 6;
+constexpr int G2_STAGES = 5;
 constexpr uint32_t G2_A_BYTES = 128 * BK * 2, G2_B_BYTES = 128 * BK * 2, G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
-constexpr uint32_t G2_SMEM = G2_STAGES * G2_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t G2_STG_BYTES = NUM_EPI_WARPS * 2 * 4096;  // per epilogue warp: two 32-row x 128-byte staging tiles
+constexpr uint32_t G2_SMEM = G2_STAGES * G2_STAGE_BYTES + G2_STG_BYTES + 1024 + 256;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, const GemmArgs g) {
   constexpr int STAGES = G2_STAGES;
   constexpr int BN = G2_BN;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * G2_STAGE_BYTES;
+  const uint32_t stg_base = smem_base + STAGES * G2_STAGE_BYTES;
+  const uint32_t bar_base = stg_base + G2_STG_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto ld_bar = [&](int e) { return bar_base + 8u * (2 * STAGES + 6 + e); };  // per epilogue warp: staged input tile landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -348,6 +371,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 2 * NUM_EPI_WARPS);  // leader: epilogue warps of both CTAs
     }
+    for (int e = 0; e < NUM_EPI_WARPS; ++e) mbar_init(ld_bar(e), 1);
     fence_barrier_init();
   }
   cluster_sync_all();  // barrier inits visible to the peer before any remote arrive / TMA credit
@@ -439,12 +463,36 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else {
     // ===================== epilogue (both CTAs, own 128 rows) =====================
+    // TMEM -> registers -> fused math -> 128B-swizzled smem staging tile (32 rows x 128 B) -> TMA store / TMA
+    // reduce-add.  A row-per-thread direct store would cost 32 partial-line transactions per instruction;
+    // the staged path writes full 128-byte lines and runs asynchronously behind the next chunk's math.
     const int e = warp - 2;
     const int lane_group = warp & 3;
     const int col_half = e >> 2;
-    constexpr int CHUNKS = BN / 2 / 32;
+    const uint32_t stg = stg_base + e * 8192;  // [0]: C tile, [1]: GELU pre-activation tile
+    const bool f32 = g.c_f32 != 0;
+    const bool atomic = (g.epilogue & UC_EPI_ATOMIC) != 0;
+    const bool has_aux = (g.epilogue & UC_EPI_GELU) != 0;
+    const bool has_in = (g.epilogue & (UC_EPI_GELU_BWD | UC_EPI_RESIDUAL)) != 0;  // aux_in / residual tile, via TMA
+    uint32_t ld_phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    auto stage_and_store = [&](const CUtensorMap* tm, uint32_t buf, const uint32_t (&w)[32], int col, int row0, bool reduce) {
+      if (lane == 0) tma_store_wait_read0();  // the previous store issued by this lane no longer reads the staging tiles
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + lane * 128 + ((j ^ (lane & 7)) << 4)), "r"(w[4 * j]),
+                     "r"(w[4 * j + 1]), "r"(w[4 * j + 2]), "r"(w[4 * j + 3])
+                     : "memory");
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (reduce) tma_reduce_add_2d(tm, buf, col, row0);
+        else tma_store_2d(tm, buf, col, row0);
+        tma_store_commit();
+      }
+    };
     for (int item = cluster_id; item < total; item += num_clusters) {
       const int split = item % g.split_k;
       const int tile = item / g.split_k;
@@ -455,23 +503,76 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (kb0 >= kb1) continue;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = m0 + lane_group * 32 + lane;
+      const int row0 = m0 + lane_group * 32;
+      const int row = row0 + lane;
       const bool row_ok = row < g.m;
       int pos_y = 0, pos_x = 0;
       if ((g.epilogue & UC_EPI_ROPE) && row_ok) {
         pos_y = g.positions[2 * row];
         pos_x = g.positions[2 * row + 1];
       }
+      const uint32_t tbase = tmem_base + (uint32_t(lane_group * 32) << 16) + uint32_t(acc * BN + col_half * (BN / 2));
+      if (f32) {
+        // 4 units of 32 fp32 columns (128 B rows)
 #pragma unroll 1
-      for (int ch = 0; ch < CHUNKS; ++ch) {
-        const int col = col_half * (BN / 2) + ch * 32;
-        const int n = n0 + col;
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld32(tmem_base + (uint32_t(lane_group * 32) << 16) + uint32_t(acc * BN + col), r);
-        tmem_ld_wait();
-        if (n >= g.n || !row_ok) continue;
-        epilogue_chunk(g, row, n, pos_y, pos_x, r);
+        for (int u = 0; u < 4; ++u) {
+          uint32_t r[32];
+          __syncwarp();
+          tmem_ld32(tbase + u * 32, r);
+          tmem_ld_wait();
+          const int n = n0 + col_half * (BN / 2) + u * 32;
+          float v[32], pre[32];
+          epilogue_math(g, row, n, pos_y, pos_x, row_ok, r, v, pre);
+          uint32_t w[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j]);
+          stage_and_store(&tmC, stg, w, n, row0, atomic);
+        }
+      } else {
+        // 2 units of 64 bf16 columns (128 B rows)
+#pragma unroll 1
+        for (int u = 0; u < 2; ++u) {
+          uint32_t r0[32], r1[32];
+          const int n = n0 + col_half * (BN / 2) + u * 64;
+          __syncwarp();
+          if (has_in && lane == 0) {  // [32 rows x 64 cols] bf16 input tile -> staging tile 1 (free: no aux_out in these modes)
+            tma_store_wait_read0();
+            mbar_arrive_expect_tx(ld_bar(e), 4096);
+            tma_load_2d(stg + 4096, &tmAux, ld_bar(e), n, row0);
+          }
+          tmem_ld32(tbase + u * 64, r0);
+          tmem_ld32(tbase + u * 64 + 32, r1);
+          tmem_ld_wait();
+          float v0[32], v1[32], p0[32], p1[32];
+          if (has_in) {
+            mbar_wait(ld_bar(e), ld_phase);
+            ld_phase ^= 1u;
+            float h0[32], h1[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint32_t a0, a1, a2, a3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                           : "r"(stg + 4096 + lane * 128 + ((j ^ (lane & 7)) << 4)));
+              float* h = (j < 4) ? &h0[8 * j] : &h1[8 * (j - 4)];
+              h[0] = bf16_lo(a0); h[1] = bf16_hi(a0); h[2] = bf16_lo(a1); h[3] = bf16_hi(a1);
+              h[4] = bf16_lo(a2); h[5] = bf16_hi(a2); h[6] = bf16_lo(a3); h[7] = bf16_hi(a3);
+            }
+            epilogue_math(g, row, n, pos_y, pos_x, row_ok, r0, v0, p0, h0);
+            epilogue_math(g, row, n + 32, pos_y, pos_x, row_ok, r1, v1, p1, h1);
+          } else {
+            epilogue_math(g, row, n, pos_y, pos_x, row_ok, r0, v0, p0);
+            epilogue_math(g, row, n + 32, pos_y, pos_x, row_ok, r1, v1, p1);
+          }
+          uint32_t w[32];
+          if (has_aux) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { w[j] = pack_bf16(p0[2 * j], p0[2 * j + 1]); w[16 + j] = pack_bf16(p1[2 * j], p1[2 * j + 1]); }
+            stage_and_store(&tmAux, stg + 4096, w, n, row0, false);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { w[j] = pack_bf16(v0[2 * j], v0[2 * j + 1]); w[16 + j] = pack_bf16(v1[2 * j], v1[2 * j + 1]); }
+          stage_and_store(&tmC, stg, w, n, row0, false);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -482,6 +583,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (lane == 0) tma_store_wait0();  // all bulk stores of this lane have completed before the CTA may exit
   }
 
   tc_fence_before();
@@ -492,14 +594,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
-int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, int grid, cudaStream_t stream) {
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux, const GemmArgs& g,
+            int grid, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
     UC_REQUIRE(e == cudaSuccess, UC_ERR_CUDA, "uc_gemm: cudaFuncSetAttribute(gemm2) failed: %s", cudaGetErrorString(e));
     configured = true;
   }
-  gemm2_kernel<<<grid, GEMM_THREADS, G2_SMEM, stream>>>(tmA, tmB, g);
+  gemm2_kernel<<<grid, GEMM_THREADS, G2_SMEM, stream>>>(tmA, tmB, tmC, tmAux, g);
   return check_launch("uc_gemm(cta_pair)");
 }
 
@@ -624,8 +727,25 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
 
   const long long total = (long long)num_m * num_n * split_k;
   if (pair) {
+    // output tiles leave through TMA: [32 rows x 128 B] boxes, 128B swizzle (bf16: 64 columns, fp32: 32 columns)
+    CUtensorMap tmC, tmAux;
+    const bool f32 = p->c_dtype == UC_DTYPE_F32;
+    uint64_t dims[2] = {(uint64_t)p->n, (uint64_t)p->m};
+    uint64_t strides[1] = {(uint64_t)p->ldc * (f32 ? 4 : 2)};
+    uint32_t box[2] = {f32 ? 32u : 64u, 32u};
+    int r = make_tensor_map(&tmC, p->c, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r) return r;
+    tmAux = tmC;
+    const void* aux_ptr = (epi & UC_EPI_GELU) ? p->aux_out : (epi & UC_EPI_GELU_BWD) ? p->aux_in : (epi & UC_EPI_RESIDUAL) ? p->residual : nullptr;
+    UC_REQUIRE(!((epi & UC_EPI_GELU_BWD) && (epi & UC_EPI_RESIDUAL)) && !((epi & UC_EPI_GELU) && (epi & (UC_EPI_GELU_BWD | UC_EPI_RESIDUAL))),
+               UC_ERR_UNSUPPORTED, "uc_gemm: GELU / GELU_BWD / RESIDUAL epilogues are mutually exclusive");
+    if (aux_ptr && !f32) {
+      r = make_tensor_map(&tmAux, aux_ptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (r) return r;
+    }
     const int clusters = (int)(total < slots ? total : slots);
-    return launch2(tmA, tmB, g, 2 * clusters, stream);
+    return launch2(tmA, tmB, tmC, tmAux, g, 2 * clusters, stream);
   }
   const int grid = (int)(total < sms ? total : sms);
   if (bn == 256) return launch<256>(tmA, tmB, g, grid, stream);

@@ -73,7 +73,7 @@ def gemm(a, b, out, *, a_layout=0, b_layout=0, bias=None, residual=None, aux_out
         e0.record()
         L.check(L.lib.uc_gemm(C.byref(p), _stream()))
         e1.record()
-        PROFILE.append((e0, e1, 2.0 * m * n * k))
+        PROFILE.append((e0, e1, 2.0 * m * n * k, (m, n, k, a_layout, b_layout, epi)))
         return out
     L.check(L.lib.uc_gemm(C.byref(p), _stream()))
     return out
