@@ -70,6 +70,7 @@ UC_API uint64_t uc_launch_count(void);
  *                     rope_table[pos[m][half]][i] = (cos, sin)   (curope/kernels.cu:39-80)
  *   UC_EPI_GELU       aux_out[m,n] = bf16(v);  v = gelu_erf(bf16(v))     (blocks.py:80-86)
  *   UC_EPI_GELU_BWD   v *= gelu_erf'(aux_in[m,n])
+ *   UC_EPI_RELU / UC_EPI_RELU_BWD   v = max(v,0) / v *= (aux_in[m,n] > 0)
  *   UC_EPI_RESIDUAL   v += residual[m,n]                    (bf16, pitch ldc)
  *   UC_EPI_ATOMIC     C += v with red.global.add (fp32 C only; implied when split_k > 1)
  * ------------------------------------------------------------------------------------------ */
@@ -79,6 +80,8 @@ UC_API uint64_t uc_launch_count(void);
 #define UC_EPI_GELU_BWD 8
 #define UC_EPI_RESIDUAL 16
 #define UC_EPI_ATOMIC 32
+#define UC_EPI_RELU 64      /* v = max(v, 0)                      (DPT convs, dpt_block.py:114-177) */
+#define UC_EPI_RELU_BWD 128 /* v *= (aux_in[m,n] > 0)             (aux_in = the ReLU output) */
 
 typedef struct {
   const void* a;
@@ -226,6 +229,7 @@ typedef struct {
   float* conf;
   int32_t B, h, w, patch;
   float conf_min, conf_max; /* confidence = conf_min + min(exp(x), conf_max - conf_min) */
+  int64_t ldy;              /* row pitch of y in elements; 0 = 4*patch*patch (dense).  patch = 1 + ldy = 64 serves the DPT head */
 } uc_head_post_fwd_params;
 UC_API int uc_head_post_fwd(const uc_head_post_fwd_params* p, uc_stream_t stream);
 
@@ -237,8 +241,27 @@ typedef struct {
   int32_t dy_dtype;
   int32_t B, h, w, patch;
   float conf_min, conf_max;
+  int64_t ldy; /* row pitch of y AND dy; 0 = dense */
 } uc_head_post_bwd_params;
 UC_API int uc_head_post_bwd(const uc_head_post_bwd_params* p, uc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * DPT head support (prediction_heads/dpt.py:94-311, libs/croco/dpt_block.py:114-255).  Feature maps are NHWC
+ * bf16 (== token-major [B*H*W, C], C % 8 == 0), so every convolution is uc_gemm:
+ *   3x3 conv, pad 1, stride 1|2 : uc_im2col3x3 -> uc_gemm;  dgrad: uc_gemm -> uc_col2im3x3;  wgrad: uc_gemm on the columns
+ *   ConvTranspose2d k == s      : uc_gemm to [(i,j,co)] columns -> uc_depth_space(to_space=1); bwd: to_space=0 -> uc_gemm
+ *   F.interpolate(bilinear, align_corners=True) : uc_bilinear_fwd / uc_bilinear_bwd
+ *   uc_elementwise op 0: a+b  1: relu(a)  2: a*(b>0)  3: a+b+c
+ * ------------------------------------------------------------------------------------------ */
+UC_API int uc_im2col3x3(const void* x, void* cols, int32_t B, int32_t H, int32_t W, int32_t C, int32_t stride, uc_stream_t stream);
+UC_API int uc_col2im3x3(const void* dcols, void* dx, int32_t B, int32_t H, int32_t W, int32_t C, int32_t stride, uc_stream_t stream);
+UC_API int uc_depth_space(const void* src, void* dst, int32_t B, int32_t h, int32_t w, int32_t C, int32_t s, int32_t to_space,
+                          uc_stream_t stream);
+UC_API int uc_bilinear_fwd(const void* in, void* out, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, int32_t C,
+                           uc_stream_t stream);
+UC_API int uc_bilinear_bwd(const void* dout, void* din, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, int32_t C,
+                           uc_stream_t stream);
+UC_API int uc_elementwise(int32_t op, const void* a, const void* b, const void* c, void* out, int64_t n, uc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -210,3 +210,56 @@ def test_full_size_property_checks():
     # symmetrized dedup (encode each image once) must agree with the plain path
     assert O.parity(s1["pts3d"], r1["pts3d"])[1] <= 1e-2
     assert O.parity(s2["conf"], r2["conf"])[1] <= 1e-2
+
+
+def _oracle_dpt(sd, img1, img2, cfg):
+    """dust3r_forward(head='dpt') with the fixture's IFR indices (see oracle/make_golden.py::_oracle_dpt_forward)."""
+    B, _, H, W = img1.shape
+    feat = O.croco_encoder(sd, "encoder.", torch.cat((img1, img2), 0), cfg["enc_depth"], cfg["enc_heads"])
+    f1, f2 = feat.chunk(2, dim=0)
+    (d1, d2), inter = O.info_sharing(sd, "info_sharing.", [f1, f2], cfg["dec_depth"], cfg["dec_heads"],
+                                     indices=cfg["ifr_indices"], norm_intermediate=False)
+    o1 = O.dpt_regressor(sd, "dpt_regressor_head1.", O.dpt_feature(sd, "dpt_feature_head1.", [f1, inter[0][0], inter[1][0], d1]), (H, W))
+    o2 = O.dpt_regressor(sd, "dpt_regressor_head2.", O.dpt_feature(sd, "dpt_feature_head2.", [f2, inter[0][1], inter[1][1], d2]), (H, W))
+    return o1, o2
+
+
+def test_dust3r_dpt_vs_reference_golden_fwd_bwd():
+    """DUSt3R with DPT heads: forward vs the reference's golden, backward vs oracle autograd.
+    The raw head outputs are compared before the exp adaptor too (the adaptor amplifies errors by e^d)."""
+    cfg, a = load("dust3r_tiny_dpt")
+    m = U.DUSt3R(name="t", img_size=tuple(cfg["hw"]), pred_head_type="dpt", pred_head_feature_dim=32,
+                 encoder_kwargs=dict(enc_embed_dim=cfg["C_enc"], enc_depth=cfg["enc_depth"], enc_num_heads=cfg["enc_heads"]),
+                 info_sharing_kwargs=dict(depth=cfg["dec_depth"], dim=cfg["C_dec"], num_heads=cfg["dec_heads"]),
+                 dpt_kwargs=dict(layer_dims=[12, 24, 48, 96]), dpt_indices=tuple(cfg["ifr_indices"]))
+    m.load_state_dict(weights(cfg))
+    m = m.to(DEV)
+    img1, img2 = a["img1"].to(DEV), a["img2"].to(DEV)
+    r1, r2 = m({"img": img1, "instance": cfg["inst1"], "data_norm_type": "dust3r"},
+               {"img": img2, "instance": cfg["inst2"], "data_norm_type": "dust3r"})
+    sd = {k: v.to(DEV).requires_grad_(True) for k, v in weights(cfg).items()}
+    o1, o2 = _oracle_dpt(sd, img1, img2, cfg)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        l1, _ = _oracle_dpt({k: v.detach() for k, v in sd.items()}, img1, img2, cfg)
+    ref_err = O.parity(l1.float(), o1)[1]
+    # conf = 1 + exp(raw channel 3): log(conf - 1) recovers the raw head output of the confidence channel
+    raw_conf = torch.log((r1["conf"] - 1.0).clamp_min(1e-30))[..., 0]
+    ma, rel = O.parity(raw_conf, o1[:, 3])
+    print(f"dpt raw conf channel: ours vs oracle fp32 rel {rel:.3e} (autocast-bf16 oracle, all channels: {ref_err:.3e})")
+    assert rel <= 2.0 * ref_err + 5e-3, (rel, ref_err)
+    p1, c1 = O.pointmap_conf_adaptor(o1)
+    gold_conf = a["conf_1"].to(DEV)
+    assert O.parity(c1.permute(0, 2, 3, 1), gold_conf)[1] <= 1e-4  # oracle == reference golden
+    # backward: a bounded loss on the raw outputs (log conf) so that the exp adaptor does not dominate the gradient
+    m.pack().zero_grad()
+    torch.log(r1["conf"] - 1.0 + 1e-30).sum().backward()
+    o1[:, 3].sum().backward()
+    dot = na = nb = 0.0
+    for k, p in m.named_parameters():
+        if p.grad is None or sd[k].grad is None:
+            continue
+        g, r = p.grad.double().flatten(), sd[k].grad.double().flatten()
+        dot += float(g @ r); na += float(g @ g); nb += float(r @ r)
+    cos = dot / math.sqrt(na * nb)
+    print(f"dpt whole-model gradient cosine {cos:.5f}")
+    assert cos >= 0.995

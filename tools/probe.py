@@ -324,6 +324,70 @@ def check_perf():
     return True
 
 
+def check_dpt_ops():
+    """DPT building blocks (conv3x3 s1/s2, ConvTranspose k=s, bilinear align_corners) fwd + bwd vs torch fp32."""
+    import torch
+    import torch.nn.functional as F
+    import torch.nn as nn
+    from uniception_b200 import dpt_engine as D, ops
+    ok = True
+    torch.manual_seed(7)
+    B, H, W, Ci, Co = 2, 12, 10, 64, 128
+    x = torch.randn(B, Ci, H, W, device="cuda").bfloat16().float()
+    xt = x.permute(0, 2, 3, 1).reshape(B * H * W, Ci).bfloat16().contiguous()
+    for stride in (1, 2):
+        conv = nn.Conv2d(Ci, Co, 3, stride=stride, padding=1).cuda()
+        conv.weight.data = conv.weight.data.bfloat16().float()
+        cw = D.ConvW("conv3", conv.weight, conv.bias, cin_pad=Ci, stride=stride)
+        tape = D.Tape()
+        y = D.conv3x3(tape, xt, B, H, W, cw)
+        xr = x.clone().requires_grad_(True)
+        ref = conv(xr)
+        Ho, Wo = ref.shape[2], ref.shape[3]
+        ok &= _report(f"dpt conv3x3 s{stride} fwd", y.float().view(B, Ho, Wo, Co).permute(0, 3, 1, 2), ref, 5e-3)
+        g = torch.randn_like(ref).bfloat16().float()
+        ref.backward(g)
+        tape.add_grad(y, g.permute(0, 2, 3, 1).reshape(-1, Co).bfloat16().contiguous())
+        tape.backward()
+        cw.flush_grads()
+        ok &= _report(f"dpt conv3x3 s{stride} dx", tape.pop_grad(xt).float().view(B, H, W, Ci).permute(0, 3, 1, 2), xr.grad, 6e-3)
+        ok &= _report(f"dpt conv3x3 s{stride} dW", conv.weight.grad, torch.autograd.grad(conv(x), conv.weight, g)[0], 6e-3)
+        conv.weight.grad = None
+    # ConvTranspose k = s = 4 with 96 -> 96 channels (padded to 128 internally)
+    C2 = 96
+    x2 = torch.randn(B, C2, 5, 6, device="cuda").bfloat16().float()
+    ct = nn.ConvTranspose2d(C2, C2, 4, stride=4).cuda()
+    ct.weight.data = ct.weight.data.bfloat16().float()
+    xpad = torch.zeros(B * 30, 128, device="cuda", dtype=torch.bfloat16)
+    xpad[:, :C2] = x2.permute(0, 2, 3, 1).reshape(B * 30, C2).bfloat16()
+    cw = D.ConvW("convT", ct.weight, ct.bias, cin_pad=128)
+    tape = D.Tape()
+    y = D.conv_transpose(tape, xpad, B, 5, 6, cw)
+    x2r = x2.clone().requires_grad_(True)
+    ref = ct(x2r)
+    ok &= _report("dpt convT k4s4 fwd", y.float().view(B, 20, 24, 128)[..., :C2].permute(0, 3, 1, 2), ref, 5e-3)
+    g = torch.randn_like(ref).bfloat16().float()
+    ref.backward(g)
+    gp = torch.zeros(B * 20 * 24, 128, device="cuda", dtype=torch.bfloat16)
+    gp[:, :C2] = g.permute(0, 2, 3, 1).reshape(-1, C2).bfloat16()
+    tape.add_grad(y, gp)
+    tape.backward()
+    cw.flush_grads()
+    ok &= _report("dpt convT dx", tape.pop_grad(xpad).float()[:, :C2].view(B, 5, 6, C2).permute(0, 3, 1, 2), x2r.grad, 6e-3)
+    ok &= _report("dpt convT dW", ct.weight.grad, torch.autograd.grad(ct(x2), ct.weight, g)[0], 6e-3)
+    # bilinear align_corners, x2 and arbitrary size
+    for (Ho, Wo) in ((2 * H, 2 * W), (31, 29)):
+        xr = x.clone().requires_grad_(True)
+        ref = F.interpolate(xr, size=(Ho, Wo), mode="bilinear", align_corners=True)
+        out = ops.bilinear_fwd(xt, B, H, W, Ho, Wo)
+        ok &= _report(f"dpt bilinear fwd {Ho}x{Wo}", out.float().view(B, Ho, Wo, Ci).permute(0, 3, 1, 2), ref, 4e-3)
+        g = torch.randn_like(ref).bfloat16().float()
+        ref.backward(g)
+        din = ops.bilinear_bwd(g.permute(0, 2, 3, 1).reshape(-1, Ci).bfloat16().contiguous(), B, H, W, Ho, Wo)
+        ok &= _report(f"dpt bilinear bwd {Ho}x{Wo}", din.float().view(B, H, W, Ci).permute(0, 3, 1, 2), xr.grad, 4e-3)
+    return ok
+
+
 def check_attn_once():
     """one fwd + bwd launch at the encoder's C3 shape (for ncu)"""
     import torch
@@ -341,7 +405,7 @@ def check_attn_once():
     return True
 
 
-CHECKS = ["gemm_tn", "gemm_dgrad", "gemm_wgrad", "gemm_epilogues", "elementwise", "attn_fwd", "attn_bwd", "perf"]
+CHECKS = ["gemm_tn", "gemm_dgrad", "gemm_wgrad", "gemm_epilogues", "elementwise", "attn_fwd", "attn_bwd", "dpt_ops", "perf"]
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] != "all":

@@ -23,7 +23,7 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 UC_DTYPE_BF16, UC_DTYPE_F32, UC_DTYPE_F16 = 0, 1, 2
-EPI_BIAS, EPI_ROPE, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ATOMIC = 1, 2, 4, 8, 16, 32
+EPI_BIAS, EPI_ROPE, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ATOMIC, EPI_RELU, EPI_RELU_BWD = 1, 2, 4, 8, 16, 32, 64, 128
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -87,7 +87,7 @@ class HeadPostFwdParams(C.Structure):
     _fields_ = [
         ("y", vp), ("pts", vp), ("conf", vp),
         ("B", i32), ("h", i32), ("w", i32), ("patch", i32),
-        ("conf_min", f32), ("conf_max", f32),
+        ("conf_min", f32), ("conf_max", f32), ("ldy", i64),
     ]
 
 
@@ -95,7 +95,7 @@ class HeadPostBwdParams(C.Structure):
     _fields_ = [
         ("y", vp), ("dpts", vp), ("dconf", vp), ("dy", vp), ("dy_dtype", i32),
         ("B", i32), ("h", i32), ("w", i32), ("patch", i32),
-        ("conf_min", f32), ("conf_max", f32),
+        ("conf_min", f32), ("conf_max", f32), ("ldy", i64),
     ]
 
 
@@ -118,6 +118,12 @@ EXPORTS = {
     "uc_nchw_to_nlc": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
     "uc_head_post_fwd": (C.c_int, [C.POINTER(HeadPostFwdParams), vp]),
     "uc_head_post_bwd": (C.c_int, [C.POINTER(HeadPostBwdParams), vp]),
+    "uc_im2col3x3": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp]),
+    "uc_col2im3x3": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp]),
+    "uc_depth_space": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "uc_bilinear_fwd": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "uc_bilinear_bwd": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "uc_elementwise": (C.c_int, [i32, vp, vp, vp, vp, i64, vp]),
 }
 
 for _name, (_res, _args) in EXPORTS.items():

@@ -395,7 +395,8 @@ __global__ void head_post_fwd_kernel(uc_head_post_fwd_params p) {
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int X = idx % Ww, Y = (idx / Ww) % Hh, b = idx / ((int64_t)Ww * Hh);
     const int64_t tok = ((int64_t)b * p.h + Y / p.patch) * p.w + X / p.patch;
-    const float* y = p.y + tok * 4 * pp + (Y % p.patch) * p.patch + (X % p.patch);
+    const int64_t ld = p.ldy ? p.ldy : 4 * pp;
+    const float* y = p.y + tok * ld + (Y % p.patch) * p.patch + (X % p.patch);
     const float x0 = y[0], x1 = y[pp], x2 = y[2 * pp], c = y[3 * pp];
     const float d = sqrtf(x0 * x0 + x1 * x1 + x2 * x2);
     const float s = expm1f(d) / fmaxf(d, 1e-8f);
@@ -411,7 +412,7 @@ __global__ void head_post_bwd_kernel(uc_head_post_bwd_params p) {
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int X = idx % Ww, Y = (idx / Ww) % Hh, b = idx / ((int64_t)Ww * Hh);
     const int64_t tok = ((int64_t)b * p.h + Y / p.patch) * p.w + X / p.patch;
-    const int64_t off = tok * 4 * pp + (Y % p.patch) * p.patch + (X % p.patch);
+    const int64_t off = tok * (p.ldy ? p.ldy : 4 * pp) + (Y % p.patch) * p.patch + (X % p.patch);
     const float* y = p.y + off;
     const float x0 = y[0], x1 = y[pp], x2 = y[2 * pp], c = y[3 * pp];
     const float g0 = p.dpts[idx * 3], g1 = p.dpts[idx * 3 + 1], g2 = p.dpts[idx * 3 + 2];

@@ -101,12 +101,27 @@ __device__ __forceinline__ void epilogue_math(const GemmArgs& g, int row, int n,
     }
   }
   const size_t off = (size_t)row * g.ldc + n;
+  if (epi & UC_EPI_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
   if (epi & UC_EPI_GELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       pre[j] = round_bf16(v[j]);
       v[j] = gelu_erf(pre[j]);
     }
+  }
+  if ((epi & UC_EPI_RELU_BWD) && row_ok) {
+    float h[32];
+    if (hin) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) h[j] = hin[j];
+    } else {
+      load_row32_bf16(g.aux_in + off, h);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = h[j] > 0.f ? v[j] : 0.f;
   }
   if ((epi & UC_EPI_GELU_BWD) && row_ok) {
     float h[32];
@@ -473,7 +488,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const bool f32 = g.c_f32 != 0;
     const bool atomic = (g.epilogue & UC_EPI_ATOMIC) != 0;
     const bool has_aux = (g.epilogue & UC_EPI_GELU) != 0;
-    const bool has_in = (g.epilogue & (UC_EPI_GELU_BWD | UC_EPI_RESIDUAL)) != 0;  // aux_in / residual tile, via TMA
+    const bool has_in = (g.epilogue & (UC_EPI_GELU_BWD | UC_EPI_RELU_BWD | UC_EPI_RESIDUAL)) != 0;  // aux_in / residual tile, via TMA
     uint32_t ld_phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -639,7 +654,12 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
   UC_REQUIRE(!(epi & UC_EPI_RESIDUAL) || p->residual, UC_ERR_BAD_SHAPE, "uc_gemm: UC_EPI_RESIDUAL without residual");
   UC_REQUIRE(!(epi & UC_EPI_GELU) || (p->aux_out && p->c_dtype == UC_DTYPE_BF16), UC_ERR_BAD_SHAPE,
              "uc_gemm: UC_EPI_GELU needs aux_out and bf16 C");
-  UC_REQUIRE(!(epi & UC_EPI_GELU_BWD) || p->aux_in, UC_ERR_BAD_SHAPE, "uc_gemm: UC_EPI_GELU_BWD without aux_in");
+  UC_REQUIRE(!(epi & (UC_EPI_GELU_BWD | UC_EPI_RELU_BWD)) || p->aux_in, UC_ERR_BAD_SHAPE, "uc_gemm: GELU_BWD / RELU_BWD without aux_in");
+  {
+    const int users = ((epi & UC_EPI_GELU) ? 1 : 0) + ((epi & UC_EPI_GELU_BWD) ? 1 : 0) + ((epi & UC_EPI_RELU_BWD) ? 1 : 0) +
+                      ((epi & UC_EPI_RESIDUAL) ? 1 : 0);
+    UC_REQUIRE(users <= 1, UC_ERR_UNSUPPORTED, "uc_gemm: GELU / GELU_BWD / RELU_BWD / RESIDUAL epilogues are mutually exclusive");
+  }
   UC_REQUIRE(!(epi & UC_EPI_ROPE) || (p->positions && p->rope_table && p->rope_cols % 64 == 0), UC_ERR_BAD_SHAPE,
              "uc_gemm: UC_EPI_ROPE needs positions, rope_table and rope_cols %% 64 == 0");
   UC_REQUIRE(!(epi & UC_EPI_ATOMIC) || p->c_dtype == UC_DTYPE_F32, UC_ERR_BAD_DTYPE, "uc_gemm: atomic epilogue needs fp32 C");
@@ -737,9 +757,8 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
                             CU_TENSOR_MAP_SWIZZLE_128B);
     if (r) return r;
     tmAux = tmC;
-    const void* aux_ptr = (epi & UC_EPI_GELU) ? p->aux_out : (epi & UC_EPI_GELU_BWD) ? p->aux_in : (epi & UC_EPI_RESIDUAL) ? p->residual : nullptr;
-    UC_REQUIRE(!((epi & UC_EPI_GELU_BWD) && (epi & UC_EPI_RESIDUAL)) && !((epi & UC_EPI_GELU) && (epi & (UC_EPI_GELU_BWD | UC_EPI_RESIDUAL))),
-               UC_ERR_UNSUPPORTED, "uc_gemm: GELU / GELU_BWD / RESIDUAL epilogues are mutually exclusive");
+    const void* aux_ptr = (epi & UC_EPI_GELU) ? p->aux_out : (epi & (UC_EPI_GELU_BWD | UC_EPI_RELU_BWD)) ? p->aux_in
+                          : (epi & UC_EPI_RESIDUAL) ? p->residual : nullptr;
     if (aux_ptr && !f32) {
       r = make_tensor_map(&tmAux, aux_ptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
       if (r) return r;

@@ -1,0 +1,340 @@
+"""DPT head (DPTFeature + DPTRegressionProcessor) on the B200 kernels, forward and backward.
+
+Reference arithmetic: prediction_heads/dpt.py:94-232 (feature head), :271-311 (regression processor),
+libs/croco/dpt_block.py:114-177 (ResidualConvUnit_custom), :180-255 (FeatureFusionBlock_custom).
+Feature maps are NHWC bf16 (token-major [B*H*W, C]); every conv is `uc_gemm` (see csrc/dpt.cu).  The graph
+is irregular (4 scales, skips, crops), so instead of a hand-written backward schedule this file keeps a tiny
+tape: every forward helper records a closure that consumes the gradient of its output and adds the gradients
+of its inputs; `Tape.backward()` replays the closures in reverse.  No torch autograd inside.
+
+Channel counts that are not multiples of 64 (layer_dims[0] = 96, the 4 output channels) are zero-padded to the
+next multiple of 64 in the bf16 operand copies, so the GEMM tile constraints hold; padded outputs are exact zeros.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def _pad64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
+class Tape:
+    def __init__(self):
+        self.fns: List[Callable[[], None]] = []
+        self.grads: Dict[int, torch.Tensor] = {}
+        self.keep: List[torch.Tensor] = []
+
+    def add_grad(self, t: torch.Tensor, g: torch.Tensor) -> None:
+        k = id(t)
+        if k in self.grads:
+            self.grads[k] = ops.elementwise(0, self.grads[k], g)
+        else:
+            self.grads[k] = g
+            self.keep.append(t)
+
+    def pop_grad(self, t: torch.Tensor) -> Optional[torch.Tensor]:
+        return self.grads.pop(id(t), None)
+
+    def record(self, fn: Callable[[], None]) -> None:
+        self.fns.append(fn)
+
+    def backward(self) -> None:
+        for fn in reversed(self.fns):
+            fn()
+        self.fns.clear()
+
+
+class ConvW:
+    """bf16 GEMM operand + fp32 bias of one conv layer, and the fp32 gradient accumulators in GEMM layout."""
+
+    def __init__(self, kind: str, weight: nn.Parameter, bias: Optional[nn.Parameter], cin_pad: int, stride: int = 1):
+        self.kind, self.weight, self.bias, self.stride = kind, weight, bias, stride
+        w = weight.detach()
+        dev = w.device
+        if kind == "conv3":  # [co, ci, 3, 3] -> [co_pad, 9 * cin_pad], k index = tap * cin_pad + ci
+            co, ci = w.shape[0], w.shape[1]
+            self.co, self.ci, self.co_pad, self.ci_pad = co, ci, _pad64(co), cin_pad
+            m = torch.zeros(self.co_pad, 3, 3, cin_pad, device=dev)
+            m[:co, :, :, :ci] = w.permute(0, 2, 3, 1)
+            self.mat = m.view(self.co_pad, 9 * cin_pad)
+        elif kind == "conv1":  # [co, ci, 1, 1] -> [co_pad, cin_pad]
+            co, ci = w.shape[0], w.shape[1]
+            self.co, self.ci, self.co_pad, self.ci_pad = co, ci, _pad64(co), cin_pad
+            m = torch.zeros(self.co_pad, cin_pad, device=dev)
+            m[:co, :ci] = w.view(co, ci)
+            self.mat = m
+        elif kind == "convT":  # [ci, co, s, s] -> [(i, j, co_pad), cin_pad]
+            ci, co, s = w.shape[0], w.shape[1], w.shape[2]
+            self.co, self.ci, self.co_pad, self.ci_pad, self.s = co, ci, _pad64(co), cin_pad, s
+            m = torch.zeros(s, s, self.co_pad, cin_pad, device=dev)
+            m[:, :, :co, :ci] = w.permute(2, 3, 1, 0)
+            self.mat = m.view(s * s * self.co_pad, cin_pad)
+        else:
+            raise ValueError(kind)
+        self.w16 = self.mat.to(torch.bfloat16).contiguous()
+        n_out = self.w16.shape[0]
+        self.b32 = None
+        if bias is not None:
+            b = torch.zeros(self.co_pad, device=dev)
+            b[:self.co] = bias.detach()
+            self.b32 = b.repeat(self.s * self.s) if kind == "convT" else b
+        self.gw = None  # fp32 [n_out, K] accumulated by wgrad GEMMs
+        self.gb = None
+        self.n_out = n_out
+
+    def grad_buffers(self):
+        if self.gw is None:
+            self.gw = torch.zeros(self.w16.shape, dtype=torch.float32, device=self.w16.device)
+            self.gb = torch.zeros(self.n_out, dtype=torch.float32, device=self.w16.device)
+        return self.gw, self.gb
+
+    def flush_grads(self) -> None:
+        """GEMM-layout fp32 gradients -> the parameters' .grad (layout permutation + un-padding; plumbing)."""
+        if self.gw is None:
+            return
+        co, ci = self.co, self.ci
+        if self.kind == "conv3":
+            g = self.gw.view(self.co_pad, 3, 3, self.ci_pad)[:co, :, :, :ci].permute(0, 3, 1, 2)
+            gb = self.gb[:co]
+        elif self.kind == "conv1":
+            g = self.gw[:co, :ci].view(co, ci, 1, 1)
+            gb = self.gb[:co]
+        else:
+            s = self.s
+            g = self.gw.view(s, s, self.co_pad, self.ci_pad)[:, :, :co, :ci].permute(3, 2, 0, 1)
+            gb = self.gb.view(s * s, self.co_pad)[:, :co].sum(0)
+        if self.weight.requires_grad:
+            self.weight.grad = g.contiguous().clone() if self.weight.grad is None else self.weight.grad.add_(g)
+        if self.bias is not None and self.bias.requires_grad:
+            self.bias.grad = gb.clone() if self.bias.grad is None else self.bias.grad.add_(gb)
+        self.gw = self.gb = None
+
+
+# ------------------------------------------------------------------------------------------------
+# forward helpers (each records its backward on the tape)
+# ------------------------------------------------------------------------------------------------
+def _gemm_fwd(x, cw: ConvW, out_dtype=torch.bfloat16, relu=False, residual=None):
+    out = torch.empty(x.shape[0], cw.n_out, dtype=out_dtype, device=x.device)
+    ops.gemm(x, cw.w16, out, bias=cw.b32, relu=relu, residual=residual)
+    return out
+
+
+def _gemm_bwd(tape: Tape, dy, x_in, cw: ConvW, need_dx=True):
+    """dy [rows, n_out] bf16.  Accumulates weight/bias grads; returns d x_in."""
+    gw, gb = cw.grad_buffers()
+    ops.gemm(dy, x_in, gw, a_layout=1, b_layout=1, atomic=True)
+    if cw.b32 is not None:
+        ops.colsum_(dy, gb)
+    if not need_dx:
+        return None
+    dx = torch.empty(dy.shape[0], cw.w16.shape[1], dtype=torch.bfloat16, device=dy.device)
+    ops.gemm(dy, cw.w16, dx, b_layout=1)
+    return dx
+
+
+def conv1x1(tape: Tape, x, cw: ConvW, out_dtype=torch.bfloat16, need_dx=True):
+    y = _gemm_fwd(x, cw, out_dtype)
+
+    def bwd():
+        g = tape.pop_grad(y)
+        if g is None:
+            return
+        if g.dtype != torch.bfloat16:
+            g = g.to(torch.bfloat16)
+        dx = _gemm_bwd(tape, g.contiguous(), x, cw, need_dx)
+        if dx is not None:
+            tape.add_grad(x, dx)
+
+    tape.record(bwd)
+    return y
+
+
+def conv3x3(tape: Tape, x, B, H, W, cw: ConvW, relu=False, residual=None):
+    """3x3, pad 1, stride cw.stride.  Optional fused ReLU or fused `+ residual` (one of the two)."""
+    st = cw.stride
+    cols = ops.im2col3x3(x, B, H, W, st)
+    y = _gemm_fwd(cols, cw, relu=relu, residual=residual)
+    del cols  # re-gathered in backward: trades one memory-bound pass for not holding 9x the activation
+
+    def bwd():
+        g = tape.pop_grad(y)
+        if g is None:
+            return
+        if residual is not None:
+            tape.add_grad(residual, g)
+        if relu:
+            g = ops.elementwise(2, g, y)  # g * (y > 0)
+        cols_b = ops.im2col3x3(x, B, H, W, st)
+        dcols = _gemm_bwd(tape, g, cols_b, cw)
+        del cols_b
+        tape.add_grad(x, ops.col2im3x3(dcols, B, H, W, st))
+
+    tape.record(bwd)
+    return y
+
+
+def conv_transpose(tape: Tape, x, B, h, w, cw: ConvW):
+    """ConvTranspose2d with kernel == stride == s: GEMM to (i, j, co) columns, then depth-to-space."""
+    s = cw.s
+    deep = _gemm_fwd(x, cw)
+    y = ops.depth_to_space(deep, B, h, w, s)
+    del deep
+
+    def bwd():
+        g = tape.pop_grad(y)
+        if g is None:
+            return
+        gdeep = ops.space_to_depth(g, B, h, w, s)
+        tape.add_grad(x, _gemm_bwd(tape, gdeep, x, cw))
+
+    tape.record(bwd)
+    return y
+
+
+def relu(tape: Tape, x):
+    y = ops.elementwise(1, x)
+
+    def bwd():
+        g = tape.pop_grad(y)
+        if g is not None:
+            tape.add_grad(x, ops.elementwise(2, g, y))
+
+    tape.record(bwd)
+    return y
+
+
+def add(tape: Tape, a, b):
+    y = ops.elementwise(0, a, b)
+
+    def bwd():
+        g = tape.pop_grad(y)
+        if g is not None:
+            tape.add_grad(a, g)
+            tape.add_grad(b, g)
+
+    tape.record(bwd)
+    return y
+
+
+def resize(tape: Tape, x, B, Hi, Wi, Ho, Wo):
+    y = ops.bilinear_fwd(x, B, Hi, Wi, Ho, Wo)
+
+    def bwd():
+        g = tape.pop_grad(y)
+        if g is not None:
+            tape.add_grad(x, ops.bilinear_bwd(g, B, Hi, Wi, Ho, Wo))
+
+    tape.record(bwd)
+    return y
+
+
+def crop(tape: Tape, x, B, H, W, Hc, Wc):
+    """x[:, :Hc, :Wc] on an NHWC map (index op; torch slicing as plumbing)."""
+    if Hc == H and Wc == W:
+        return x
+    C = x.shape[1]
+    y = x.view(B, H, W, C)[:, :Hc, :Wc].reshape(B * Hc * Wc, C).contiguous()
+
+    def bwd():
+        g = tape.pop_grad(y)
+        if g is not None:
+            full = torch.zeros(B, H, W, C, dtype=g.dtype, device=g.device)
+            full[:, :Hc, :Wc] = g.view(B, Hc, Wc, C)
+            tape.add_grad(x, full.view(B * H * W, C))
+
+    tape.record(bwd)
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# the head
+# ------------------------------------------------------------------------------------------------
+class DPTWeights:
+    """Operand copies of one (DPTFeature, DPTRegressionProcessor) pair, rebuilt per forward from the fp32 masters."""
+
+    def __init__(self, feat: nn.Module, reg: nn.Module):
+        sc = feat.scratch
+        self.pre, self.up, self.rn = [], [], []
+        for j in range(4):
+            act = feat.act_postprocess[j]
+            c1 = ConvW("conv1", act[0].weight, act[0].bias, cin_pad=act[0].weight.shape[1])
+            self.pre.append(c1)
+            if j == 0 or j == 1:
+                self.up.append(ConvW("convT", act[1].weight, act[1].bias, cin_pad=c1.co_pad))
+            elif j == 3:
+                self.up.append(ConvW("conv3", act[1].weight, act[1].bias, cin_pad=c1.co_pad, stride=2))
+            else:
+                self.up.append(None)
+            cin = self.up[j].co_pad if self.up[j] is not None else c1.co_pad
+            self.rn.append(ConvW("conv3", sc.layer_rn[j].weight, None, cin_pad=cin))
+        f = self.rn[0].co_pad
+        self.fuse = []
+        for k in (1, 2, 3, 4):
+            blk = getattr(sc, f"refinenet{k}")
+            d = {"out": ConvW("conv1", blk.out_conv.weight, blk.out_conv.bias, cin_pad=f)}
+            for u in ("resConfUnit1", "resConfUnit2"):
+                if hasattr(blk, u):
+                    unit = getattr(blk, u)
+                    d[u] = (ConvW("conv3", unit.conv1.weight, unit.conv1.bias, cin_pad=f),
+                            ConvW("conv3", unit.conv2.weight, unit.conv2.bias, cin_pad=f))
+            self.fuse.append(d)
+        self.r1 = ConvW("conv3", reg.conv1.weight, reg.conv1.bias, cin_pad=f)
+        self.r2 = ConvW("conv3", reg.conv2[0].weight, reg.conv2[0].bias, cin_pad=self.r1.co_pad)
+        self.r3 = ConvW("conv1", reg.conv2[2].weight, reg.conv2[2].bias, cin_pad=self.r2.co_pad)
+
+    def all(self):
+        out = self.pre + [u for u in self.up if u is not None] + self.rn + [self.r1, self.r2, self.r3]
+        for d in self.fuse:
+            out.append(d["out"])
+            for u in ("resConfUnit1", "resConfUnit2"):
+                if u in d:
+                    out += list(d[u])
+        return out
+
+
+def _rcu(tape, z, B, H, W, unit, extra_skip=None):
+    """z + conv2(relu(conv1(relu(z)))) [+ extra_skip]; ReLU of conv1 fused in its epilogue, skip fused in conv2's."""
+    skip = z if extra_skip is None else add(tape, z, extra_skip)
+    t = conv3x3(tape, relu(tape, z), B, H, W, unit[0], relu=True)
+    return conv3x3(tape, t, B, H, W, unit[1], residual=skip)
+
+
+def _fusion(tape, a, b, B, H, W, d):
+    """FeatureFusionBlock_custom: a [+ RCU1(b)] -> RCU2 -> bilinear x2 (align_corners) -> 1x1 conv."""
+    out = a if b is None else _rcu(tape, b, B, H, W, d["resConfUnit1"], extra_skip=a)
+    out = _rcu(tape, out, B, H, W, d["resConfUnit2"])
+    out = resize(tape, out, B, H, W, 2 * H, 2 * W)
+    return conv1x1(tape, out, d["out"])
+
+
+def dpt_forward(tape: Tape, Wt: DPTWeights, feats: List[torch.Tensor], B: int, h: int, w: int, out_hw: Tuple[int, int]):
+    """feats: 4 token tensors bf16 [B*h*w, C_j].  Returns y fp32 [B*H*W, 64] (first `out_dim` columns valid)."""
+    maps, sizes = [], []
+    for j in range(4):
+        a = conv1x1(tape, feats[j], Wt.pre[j])
+        if j == 0 or j == 1:
+            s = Wt.up[j].s
+            x, hw = conv_transpose(tape, a, B, h, w, Wt.up[j]), (h * s, w * s)
+        elif j == 2:
+            x, hw = a, (h, w)
+        else:
+            x, hw = conv3x3(tape, a, B, h, w, Wt.up[j]), ops.conv_out_hw(h, w, 2)
+        maps.append(conv3x3(tape, x, B, hw[0], hw[1], Wt.rn[j]))
+        sizes.append(hw)
+    l0, l1, l2, l3 = maps
+    p4 = _fusion(tape, l3, None, B, sizes[3][0], sizes[3][1], Wt.fuse[3])
+    p4 = crop(tape, p4, B, 2 * sizes[3][0], 2 * sizes[3][1], sizes[2][0], sizes[2][1])  # dpt.py:213
+    p3 = _fusion(tape, p4, l2, B, sizes[2][0], sizes[2][1], Wt.fuse[2])
+    p2 = _fusion(tape, p3, l1, B, sizes[1][0], sizes[1][1], Wt.fuse[1])
+    p1 = _fusion(tape, p2, l0, B, sizes[0][0], sizes[0][1], Wt.fuse[0])
+    Hf, Wf = 2 * sizes[0][0], 2 * sizes[0][1]
+    c1 = conv3x3(tape, p1, B, Hf, Wf, Wt.r1)
+    u = resize(tape, c1, B, Hf, Wf, out_hw[0], out_hw[1])
+    c2 = conv3x3(tape, u, B, out_hw[0], out_hw[1], Wt.r2, relu=True)
+    return conv1x1(tape, c2, Wt.r3, out_dtype=torch.float32)

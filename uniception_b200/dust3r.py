@@ -12,10 +12,11 @@ from typing import List, Tuple
 import torch
 import torch.nn as nn
 
-from .encoders import CroCoEncoder
+from .encoders import CroCoEncoder, feature_take_indices
 from .info_sharing import MultiViewCrossAttentionTransformer, MultiViewCrossAttentionTransformerIFR
 from .params import ParamPack, get_pack
-from .prediction_heads import LinearFeature, PointMapWithConfidenceAdaptor
+from .prediction_heads import (DPTFeature, DPTHead, DPTRegressionProcessor, LinearFeature, PointMapWithConfidenceAdaptor,
+                               _HeadPostFn)
 from .rope import RoPE2D
 
 
@@ -62,6 +63,8 @@ class DUSt3R(nn.Module):
         # extension (not in the reference): override the hard-coded ViT-L / base-decoder sizes, used by tests
         encoder_kwargs: dict = None,
         info_sharing_kwargs: dict = None,
+        dpt_kwargs: dict = None,
+        dpt_indices: tuple = (5, 8),
         *args,
         **kwargs,
     ):
@@ -91,17 +94,29 @@ class DUSt3R(nn.Module):
         if self.pred_head_type == "linear":
             self.info_sharing = MultiViewCrossAttentionTransformer(**common)
         elif self.pred_head_type == "dpt":
-            raise NotImplementedError(
-                "uniception_b200: the DPT prediction head (SURVEY.md 8a rows a13-a15) is not built yet; use pred_head_type='linear'")
+            # intermediate (un-normalised) decoder features of blocks 5 and 8 + the final ones (dust3r.py:135-144)
+            self.info_sharing = MultiViewCrossAttentionTransformerIFR(indices=list(dpt_indices), norm_intermediate=False, **common)
         else:
             raise ValueError(f"Invalid prediction head type: {pred_head_type}. Must be 'linear' or 'dpt'.")
 
-        self.head1 = LinearFeature(input_feature_dim=self.info_sharing.dim, output_dim=pred_head_output_dim,
-                                   patch_size=self.encoder.patch_size,
-                                   pretrained_checkpoint_path=pretrained_pred_head_checkpoint_paths[0])
-        self.head2 = LinearFeature(input_feature_dim=self.info_sharing.dim, output_dim=pred_head_output_dim,
-                                   patch_size=self.encoder.patch_size,
-                                   pretrained_checkpoint_path=pretrained_pred_head_checkpoint_paths[1])
+        if self.pred_head_type == "linear":
+            self.head1 = LinearFeature(input_feature_dim=self.info_sharing.dim, output_dim=pred_head_output_dim,
+                                       patch_size=self.encoder.patch_size,
+                                       pretrained_checkpoint_path=pretrained_pred_head_checkpoint_paths[0])
+            self.head2 = LinearFeature(input_feature_dim=self.info_sharing.dim, output_dim=pred_head_output_dim,
+                                       patch_size=self.encoder.patch_size,
+                                       pretrained_checkpoint_path=pretrained_pred_head_checkpoint_paths[1])
+        else:
+            dims = [self.encoder.enc_embed_dim] + [self.info_sharing.dim] * 3
+            for k in (1, 2):  # dust3r.py:164-192: dpt_feature_head{k}, dpt_regressor_head{k}, head{k} = Sequential(both)
+                f = DPTFeature(patch_size=self.encoder.patch_size, hooks=[0, 1, 2, 3], input_feature_dims=dims,
+                               feature_dim=pred_head_feature_dim, pretrained_checkpoint_path=pretrained_pred_head_checkpoint_paths[k - 1],
+                               **(dpt_kwargs or {}))
+                r = DPTRegressionProcessor(input_feature_dim=pred_head_feature_dim, output_dim=pred_head_output_dim,
+                                           pretrained_checkpoint_path=pretrained_pred_head_regressor_checkpoint_paths[k - 1])
+                setattr(self, f"dpt_feature_head{k}", f)
+                setattr(self, f"dpt_regressor_head{k}", r)
+                setattr(self, f"head{k}", DPTHead(f, r))
 
         self.adaptor = PointMapWithConfidenceAdaptor(
             name="pointmap", pointmap_mode=depth_mode[0], pointmap_vmin=depth_mode[1], pointmap_vmax=depth_mode[2],
@@ -147,11 +162,20 @@ class DUSt3R(nn.Module):
             half = tok.shape[0] // 2
             t1, t2 = tok[:half], tok[half:]
         B = img1.shape[0]
-        (d1, d2), _ = self.info_sharing.forward_tokens([t1, t2], B, h, w, pk, "info_sharing.")
         cmin = float(self.adaptor.confidence_adaptor.vmin)
         cmax = float(self.adaptor.confidence_adaptor.vmax)
-        pts1, conf1 = self.head1.forward_fused(d1, B, h, w, pk, "head1.", cmin, cmax)
-        pts2, conf2 = self.head2.forward_fused(d2, B, h, w, pk, "head2.", cmin, cmax)
+        if self.pred_head_type == "linear":
+            (d1, d2), _ = self.info_sharing.forward_tokens([t1, t2], B, h, w, pk, "info_sharing.")
+            pts1, conf1 = self.head1.forward_fused(d1, B, h, w, pk, "head1.", cmin, cmax)
+            pts2, conf2 = self.head2.forward_fused(d2, B, h, w, pk, "head2.", cmin, cmax)
+        else:
+            take, _ = feature_take_indices(self.info_sharing.depth, self.info_sharing.indices)
+            (d1, d2), inter = self.info_sharing.forward_tokens([t1, t2], B, h, w, pk, "info_sharing.", take, False)
+            hw = (height1, width1)
+            y1 = self.head1.forward_tokens([t1, inter[0][0], inter[1][0], d1], B, h, w, hw)  # dust3r.py:293-306
+            y2 = self.head2.forward_tokens([t2, inter[0][1], inter[1][1], d2], B, h, w, hw)
+            pts1, conf1 = _HeadPostFn.apply(y1, B, height1, width1, cmin, cmax)
+            pts2, conf2 = _HeadPostFn.apply(y2, B, height1, width1, cmin, cmax)
         res1 = {"pts3d": pts1, "conf": conf1}
         res2 = {"pts3d_in_other_view": pts2, "conf": conf2}
         return res1, res2

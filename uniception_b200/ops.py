@@ -34,7 +34,8 @@ def _cuda(*ts):
 
 
 def gemm(a, b, out, *, a_layout=0, b_layout=0, bias=None, residual=None, aux_out=None, aux_in=None,
-         positions=None, rope_table=None, rope_cols=0, gelu=False, gelu_bwd=False, atomic=False, split_k=0):
+         positions=None, rope_table=None, rope_cols=0, gelu=False, gelu_bwd=False, atomic=False, split_k=0,
+         relu=False, relu_bwd=False):
     """out[m,n] = epilogue(sum_k A(m,k) B(n,k)); see include/uc_b200.h (uc_gemm).
     a: [m,k] (a_layout 0) or [k,m] (1); b: [n,k] (0) or [k,n] (1); bf16, inner dim contiguous."""
     _cuda(a, b, out)
@@ -58,6 +59,11 @@ def gemm(a, b, out, *, a_layout=0, b_layout=0, bias=None, residual=None, aux_out
     if gelu_bwd:
         assert aux_in is not None and aux_in.stride(0) == out.stride(0)
         epi |= L.EPI_GELU_BWD
+    if relu:
+        epi |= L.EPI_RELU
+    if relu_bwd:
+        assert aux_in is not None and aux_in.stride(0) == out.stride(0)
+        epi |= L.EPI_RELU_BWD
     if residual is not None:
         assert residual.dtype == torch.bfloat16 and residual.stride(0) == out.stride(0)
         epi |= L.EPI_RESIDUAL
@@ -216,10 +222,10 @@ def nchw_to_nlc(x: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
 
 def head_post_fwd(y: torch.Tensor, B: int, h: int, w: int, patch: int, conf_min=1.0, conf_max=math.inf):
     _cuda(y)
-    assert y.dtype == torch.float32 and y.is_contiguous() and y.shape == (B * h * w, 4 * patch * patch)
+    assert y.dtype == torch.float32 and y.is_contiguous() and y.shape[0] == B * h * w and y.shape[1] >= 4 * patch * patch
     pts = torch.empty(B, h * patch, w * patch, 3, dtype=torch.float32, device=y.device)
     conf = torch.empty(B, h * patch, w * patch, 1, dtype=torch.float32, device=y.device)
-    p = L.HeadPostFwdParams(_ptr(y), _ptr(pts), _ptr(conf), B, h, w, patch, float(conf_min), float(conf_max))
+    p = L.HeadPostFwdParams(_ptr(y), _ptr(pts), _ptr(conf), B, h, w, patch, float(conf_min), float(conf_max), y.stride(0))
     L.check(L.lib.uc_head_post_fwd(C.byref(p), _stream()))
     return pts, conf
 
@@ -227,8 +233,78 @@ def head_post_fwd(y: torch.Tensor, B: int, h: int, w: int, patch: int, conf_min=
 def head_post_bwd(y, dpts, dconf, B, h, w, patch, conf_min=1.0, conf_max=math.inf, dtype=torch.bfloat16):
     _cuda(y, dpts, dconf)
     dpts, dconf = dpts.contiguous(), dconf.contiguous()
-    dy = torch.empty(y.shape, dtype=dtype, device=y.device)
+    dense = y.shape[1] == 4 * patch * patch
+    dy = torch.empty(y.shape, dtype=dtype, device=y.device) if dense else torch.zeros(y.shape, dtype=dtype, device=y.device)
     p = L.HeadPostBwdParams(_ptr(y), _ptr(dpts), _ptr(dconf), _ptr(dy), _DT[dtype], B, h, w, patch,
-                            float(conf_min), float(conf_max))
+                            float(conf_min), float(conf_max), y.stride(0))
     L.check(L.lib.uc_head_post_bwd(C.byref(p), _stream()))
     return dy
+
+
+# ---- DPT head support (NHWC bf16 feature maps == token-major [B*H*W, C]) ----
+def conv_out_hw(H: int, W: int, stride: int):
+    return (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+
+
+def im2col3x3(x: torch.Tensor, B: int, H: int, W: int, stride: int = 1) -> torch.Tensor:
+    """x [B*H*W, C] bf16 -> cols [B*Ho*Wo, 9*C] (tap-major, pad 1)."""
+    _cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.shape[0] == B * H * W
+    C_ = x.shape[1]
+    Ho, Wo = conv_out_hw(H, W, stride)
+    cols = torch.empty(B * Ho * Wo, 9 * C_, dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib.uc_im2col3x3(_ptr(x), _ptr(cols), B, H, W, C_, stride, _stream()))
+    return cols
+
+
+def col2im3x3(dcols: torch.Tensor, B: int, H: int, W: int, stride: int = 1) -> torch.Tensor:
+    _cuda(dcols)
+    assert dcols.dtype == torch.bfloat16 and dcols.is_contiguous()
+    C_ = dcols.shape[1] // 9
+    dx = torch.empty(B * H * W, C_, dtype=torch.bfloat16, device=dcols.device)
+    L.check(L.lib.uc_col2im3x3(_ptr(dcols), _ptr(dx), B, H, W, C_, stride, _stream()))
+    return dx
+
+
+def depth_to_space(x: torch.Tensor, B: int, h: int, w: int, s: int) -> torch.Tensor:
+    """[B*h*w, s*s*C] (columns (i,j,c)) -> NHWC [B*(h*s)*(w*s), C]."""
+    _cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    C_ = x.shape[1] // (s * s)
+    out = torch.empty(B * h * s * w * s, C_, dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib.uc_depth_space(_ptr(x), _ptr(out), B, h, w, C_, s, 1, _stream()))
+    return out
+
+
+def space_to_depth(x: torch.Tensor, B: int, h: int, w: int, s: int) -> torch.Tensor:
+    _cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    C_ = x.shape[1]
+    out = torch.empty(B * h * w, s * s * C_, dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib.uc_depth_space(_ptr(x), _ptr(out), B, h, w, C_, s, 0, _stream()))
+    return out
+
+
+def bilinear_fwd(x: torch.Tensor, B: int, Hi: int, Wi: int, Ho: int, Wo: int) -> torch.Tensor:
+    _cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    out = torch.empty(B * Ho * Wo, x.shape[1], dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib.uc_bilinear_fwd(_ptr(x), _ptr(out), B, Hi, Wi, Ho, Wo, x.shape[1], _stream()))
+    return out
+
+
+def bilinear_bwd(dout: torch.Tensor, B: int, Hi: int, Wi: int, Ho: int, Wo: int) -> torch.Tensor:
+    _cuda(dout)
+    assert dout.dtype == torch.bfloat16 and dout.is_contiguous()
+    din = torch.empty(B * Hi * Wi, dout.shape[1], dtype=torch.bfloat16, device=dout.device)
+    L.check(L.lib.uc_bilinear_bwd(_ptr(dout), _ptr(din), B, Hi, Wi, Ho, Wo, dout.shape[1], _stream()))
+    return din
+
+
+def elementwise(op: int, a, b=None, c=None):
+    """0: a+b  1: relu(a)  2: a*(b>0)  3: a+b+c   (bf16, same shapes)"""
+    _cuda(a, b, c)
+    assert a.dtype == torch.bfloat16 and a.is_contiguous() and a.numel() % 8 == 0
+    out = torch.empty_like(a)
+    L.check(L.lib.uc_elementwise(op, _ptr(a), _ptr(b), _ptr(c), _ptr(out), a.numel(), _stream()))
+    return out

@@ -16,7 +16,7 @@ from typing import List, Tuple
 import torch
 import torch.nn as nn
 
-from . import fused
+from . import dpt_engine, fused, ops
 from .autograd_ops import LinearFn
 from .params import ParamPack, get_pack
 
@@ -216,3 +216,190 @@ class PointMapWithConfidenceAdaptor(ValueWithConfidenceAdaptor):
         """True when the fused head kernel implements exactly this configuration (the DUSt3R default)."""
         v, c = self.value_adaptor, self.confidence_adaptor
         return v.mode == "exp" and v.no_bounds and c.confidence_type == "exp"
+
+
+# ------------------------------------------------------------------------------------------------
+# DPT head (prediction_heads/dpt.py:32-311; libs/croco/dpt_block.py)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class DPTFeatureInput:
+    features_upsampled_8x: torch.Tensor
+    target_output_shape: Tuple[int, int]
+
+
+class _ResidualConvUnit(nn.Module):
+    """ResidualConvUnit_custom parameters (dpt_block.py:114-177), bn=False."""
+
+    def __init__(self, features: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(features, features, kernel_size=3, stride=1, padding=1, bias=True)
+        self.conv2 = nn.Conv2d(features, features, kernel_size=3, stride=1, padding=1, bias=True)
+
+
+class _FeatureFusionBlock(nn.Module):
+    """FeatureFusionBlock_custom parameters (dpt_block.py:180-255)."""
+
+    def __init__(self, features: int, with_unit1: bool = True):
+        super().__init__()
+        self.out_conv = nn.Conv2d(features, features, kernel_size=1, stride=1, padding=0, bias=True)
+        self.resConfUnit1 = _ResidualConvUnit(features)
+        self.resConfUnit2 = _ResidualConvUnit(features)
+        if not with_unit1:
+            del self.resConfUnit1  # dpt.py:83
+
+
+class DPTFeature(nn.Module):
+    """Parameter container with the reference's keys (incl. the three aliases of every layer_rn conv,
+    dpt_block.py:34-78): scratch.layer{1..4}_rn == scratch.layer_rn.{0..3} == input_process.{0..3}.1."""
+
+    def __init__(self, patch_size=16, main_tasks=("rgb",), hooks=(2, 5, 8, 11), input_feature_dims=(768, 768, 768, 768),
+                 layer_dims=(96, 192, 384, 768), feature_dim: int = 256, use_bn: bool = False, output_width_ratio=1,
+                 pretrained_checkpoint_path: str = None, checkpoint_gradient: bool = False, nonlinearity: str = "relu",
+                 *args, **kwargs):
+        super().__init__()
+        if use_bn or nonlinearity != "relu" or output_width_ratio != 1:
+            raise NotImplementedError("uniception_b200.DPTFeature: only use_bn=False, relu, output_width_ratio=1 are built")
+        self.patch_size = (patch_size, patch_size) if isinstance(patch_size, int) else tuple(patch_size)
+        self.main_tasks = main_tasks
+        self.hooks = list(hooks)
+        self.layer_dims = list(layer_dims)
+        self.feature_dim = feature_dim
+        self.input_feature_dims = list(input_feature_dims) if not isinstance(input_feature_dims, int) else [input_feature_dims] * 4
+        self.checkpoint_gradient = checkpoint_gradient
+        assert len(self.hooks) == 4 and len(self.input_feature_dims) == 4 and len(self.layer_dims) == 4
+        L = self.layer_dims
+        scratch = nn.Module()
+        scratch.layer1_rn = nn.Conv2d(L[0], feature_dim, kernel_size=3, stride=1, padding=1, bias=False)
+        scratch.layer2_rn = nn.Conv2d(L[1], feature_dim, kernel_size=3, stride=1, padding=1, bias=False)
+        scratch.layer3_rn = nn.Conv2d(L[2], feature_dim, kernel_size=3, stride=1, padding=1, bias=False)
+        scratch.layer4_rn = nn.Conv2d(L[3], feature_dim, kernel_size=3, stride=1, padding=1, bias=False)
+        scratch.layer_rn = nn.ModuleList([scratch.layer1_rn, scratch.layer2_rn, scratch.layer3_rn, scratch.layer4_rn])
+        scratch.refinenet1 = _FeatureFusionBlock(feature_dim)
+        scratch.refinenet2 = _FeatureFusionBlock(feature_dim)
+        scratch.refinenet3 = _FeatureFusionBlock(feature_dim)
+        scratch.refinenet4 = _FeatureFusionBlock(feature_dim, with_unit1=False)
+        self.scratch = scratch
+        D = self.input_feature_dims
+        act = [
+            nn.Sequential(nn.Conv2d(D[0], L[0], kernel_size=1), nn.ConvTranspose2d(L[0], L[0], kernel_size=4, stride=4, padding=0)),
+            nn.Sequential(nn.Conv2d(D[1], L[1], kernel_size=1), nn.ConvTranspose2d(L[1], L[1], kernel_size=2, stride=2, padding=0)),
+            nn.Sequential(nn.Conv2d(D[2], L[2], kernel_size=1)),
+            nn.Sequential(nn.Conv2d(D[3], L[3], kernel_size=1), nn.Conv2d(L[3], L[3], kernel_size=3, stride=2, padding=1)),
+        ]
+        self.act_postprocess = act  # plain list (not registered), like the reference
+        self.input_process = nn.ModuleList([nn.Sequential(a, l) for a, l in zip(act, scratch.layer_rn)])
+        if pretrained_checkpoint_path is not None:
+            print(f"Loading pretrained DPT dense feature head from {pretrained_checkpoint_path}")
+            ckpt = torch.load(pretrained_checkpoint_path, weights_only=False)
+            print(self.load_state_dict(ckpt["model"]))
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("uniception_b200: run DPTFeature through DPTHead(feature, regressor) or DUSt3R(pred_head_type='dpt')")
+
+
+class DPTRegressionProcessor(nn.Module):
+    """prediction_heads/dpt.py:238-311 parameters: conv1 (3x3, C -> C/2), conv2 = [3x3 C/2 -> hidden, ReLU, 1x1 hidden -> out]."""
+
+    def __init__(self, input_feature_dim: int, output_dim: int, hidden_dims=None, pretrained_checkpoint_path: str = None,
+                 checkpoint_gradient: bool = False, *args, **kwargs):
+        super().__init__()
+        if hidden_dims is None:
+            hidden_dims = [input_feature_dim // 2] * 2
+        assert isinstance(hidden_dims, (list, tuple)) and len(hidden_dims) == 2
+        self.output_dim = output_dim
+        self.checkpoint_gradient = checkpoint_gradient
+        self.conv1 = nn.Conv2d(input_feature_dim, hidden_dims[0], kernel_size=3, stride=1, padding=1)
+        self.conv2 = nn.Sequential(nn.Conv2d(hidden_dims[0], hidden_dims[1], kernel_size=3, stride=1, padding=1), nn.ReLU(True),
+                                   nn.Conv2d(hidden_dims[1], output_dim, kernel_size=1, stride=1, padding=0))
+        if pretrained_checkpoint_path is not None:
+            print(f"Loading pretrained DPT regression processor from {pretrained_checkpoint_path}")
+            ckpt = torch.load(pretrained_checkpoint_path, weights_only=False)
+            print(self.load_state_dict(ckpt["model"]))
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("uniception_b200: run DPTRegressionProcessor through DPTHead(feature, regressor) or DUSt3R(pred_head_type='dpt')")
+
+
+class _DPTHeadFn(torch.autograd.Function):
+    """tokens (4 x bf16 [B*h*w, C_j]) -> raw head output fp32 [B*H*W, 64] (first output_dim columns valid)."""
+
+    @staticmethod
+    def forward(ctx, feat_mod, reg_mod, B, h, w, out_hw, t0, t1, t2, t3, *params):
+        toks = [t.contiguous() if t.dtype == torch.bfloat16 else t.to(torch.bfloat16).contiguous() for t in (t0, t1, t2, t3)]
+        Wt = dpt_engine.DPTWeights(feat_mod, reg_mod)
+        tape = dpt_engine.Tape()
+        y = dpt_engine.dpt_forward(tape, Wt, toks, B, h, w, out_hw)
+        ctx.tape, ctx.Wt, ctx.toks, ctx.y = tape, Wt, toks, y
+        ctx.in_dtypes = [t.dtype for t in (t0, t1, t2, t3)]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        tape, Wt, toks = ctx.tape, ctx.Wt, ctx.toks
+        g = dy.contiguous()
+        tape.add_grad(ctx.y, g if g.dtype == torch.bfloat16 else g.to(torch.bfloat16))
+        tape.backward()
+        for cw in Wt.all():
+            cw.flush_grads()
+        grads = []
+        for t, dt in zip(toks, ctx.in_dtypes):
+            gt = tape.pop_grad(t)
+            grads.append(None if gt is None else (gt if gt.dtype == dt else gt.to(dt)))
+        ctx.tape = ctx.Wt = ctx.toks = ctx.y = None
+        return (None, None, None, None, None, None, *grads) + (None,) * (len(ctx.needs_input_grad) - 10)
+
+
+class _HeadPostFn(torch.autograd.Function):
+    """pointmap(exp) + confidence(exp) adaptor + BHWC layout on a [B*H*W, ld] fp32 head output (patch = 1)."""
+
+    @staticmethod
+    def forward(ctx, y, B, H, W, conf_min, conf_max):
+        pts, conf = ops.head_post_fwd(y, B, H, W, 1, conf_min, conf_max)
+        ctx.save_for_backward(y)
+        ctx.cfg = (B, H, W, conf_min, conf_max)
+        return pts, conf
+
+    @staticmethod
+    def backward(ctx, dpts, dconf):
+        (y,) = ctx.saved_tensors
+        B, H, W, cmin, cmax = ctx.cfg
+        if dpts is None:
+            dpts = torch.zeros(B, H, W, 3, device=y.device)
+        if dconf is None:
+            dconf = torch.zeros(B, H, W, 1, device=y.device)
+        dy = ops.head_post_bwd(y, dpts.float(), dconf.float(), B, H, W, 1, cmin, cmax, dtype=torch.float32)
+        return dy, None, None, None, None, None
+
+
+class DPTHead(nn.Module):
+    """`nn.Sequential(DPTFeature, DPTRegressionProcessor)` of factory/dust3r.py:178,192 on the B200 engine.
+    Keeps the Sequential's state-dict keys (`0.*`, `1.*`)."""
+
+    def __init__(self, feature: DPTFeature, regressor: DPTRegressionProcessor):
+        super().__init__()
+        self.add_module("0", feature)
+        self.add_module("1", regressor)
+
+    @property
+    def feature(self) -> DPTFeature:
+        return getattr(self, "0")
+
+    @property
+    def regressor(self) -> DPTRegressionProcessor:
+        return getattr(self, "1")
+
+    def forward_tokens(self, toks: List[torch.Tensor], B: int, h: int, w: int, out_hw: Tuple[int, int]) -> torch.Tensor:
+        params = list(self.parameters())
+        return _DPTHeadFn.apply(self.feature, self.regressor, B, h, w, tuple(out_hw), *toks, *params)
+
+    def forward(self, head_input: PredictionHeadLayeredInput) -> PixelTaskOutput:
+        feats = head_input.list_features
+        assert len(feats) == 4, "DPT head expects 4 hooked feature maps"
+        if not feats[0].is_cuda:
+            raise RuntimeError("uniception_b200.DPTHead runs on CUDA only (no CPU fallback)")
+        B, _, h, w = feats[0].shape
+        H, W = head_input.target_output_shape
+        toks = [fused.NchwToNlcFn.apply(f) for f in feats]
+        y = self.forward_tokens(toks, B, h, w, (H, W))
+        od = self.regressor.output_dim
+        return PixelTaskOutput(decoded_channels=y[:, :od].reshape(B, H, W, od).permute(0, 3, 1, 2).contiguous())
