@@ -152,6 +152,9 @@ typedef struct {
   float* dbeta;  /* [C] fp32, accumulated */
   int32_t rows, C;
   int32_t dy_dtype, x_dtype;
+  float* dx_colsum; /* optional [C] fp32, accumulated: column sums of the bf16 dx this call writes -- the bias gradient of
+                       the Linear whose output gradient dx is (fc2 / proj of the next sub-block in backward order), so that
+                       tensor is not re-read by uc_colsum */
 } uc_layernorm_bwd_params;
 UC_API int uc_layernorm_bwd(const uc_layernorm_bwd_params* p, uc_stream_t stream);
 

@@ -17,6 +17,10 @@ from golden_utils import load, weights
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+# the fp32 oracle is the checker: keep cuDNN / cuBLAS out of TF32, as the reference's own KAT does
+# (examples/models/dust3r/dust3r.py:198-230 compares with TF32 disabled)
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
 
 
 def _autocast_err(fn_fp32_inputs):
@@ -237,7 +241,10 @@ def test_dust3r_dpt_vs_reference_golden_fwd_bwd():
     img1, img2 = a["img1"].to(DEV), a["img2"].to(DEV)
     r1, r2 = m({"img": img1, "instance": cfg["inst1"], "data_norm_type": "dust3r"},
                {"img": img2, "instance": cfg["inst2"], "data_norm_type": "dust3r"})
-    sd = {k: v.to(DEV).requires_grad_(True) for k, v in weights(cfg).items()}
+    # The DPT state dict holds every layer_rn conv under three keys and every head tensor again under head{k}.0/1.*
+    # (dpt_block.py:34-78, dust3r.py:178); load_state_dict lets the LAST alias win, so the oracle must read the
+    # module's resolved state dict (as oracle/make_golden.py does), not the raw seeded one.
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
     o1, o2 = _oracle_dpt(sd, img1, img2, cfg)
     with torch.autocast("cuda", dtype=torch.bfloat16):
         l1, _ = _oracle_dpt({k: v.detach() for k, v in sd.items()}, img1, img2, cfg)

@@ -96,3 +96,37 @@ def test_dust3r_linear_golden(name):
     dig = np.array([[float(sd[k].grad.double().sum()), float(sd[k].grad.double().norm())] for k in cfg["grad_keys"]])
     ref = a["grad_digest"].numpy()
     assert np.allclose(dig[:, 1], ref[:, 1], rtol=2e-4, atol=1e-6)
+
+
+def test_dust3r_dpt_golden():
+    """DPT heads: the oracle reproduces the reference's golden outputs and gradients.
+    The DPT state dict aliases every layer_rn conv under three keys and every head tensor again under head{k}.0/1.*
+    (dpt_block.py:34-78, dust3r.py:178); `load_state_dict` lets the last alias win, so the oracle reads the state dict
+    RESOLVED by our parameter container -- which also pins that container's alias order to the reference's."""
+    import uniception_b200 as U
+
+    cfg, a = load("dust3r_tiny_dpt")
+    m = U.DUSt3R(name="t", img_size=tuple(cfg["hw"]), pred_head_type="dpt", pred_head_feature_dim=32,
+                 encoder_kwargs=dict(enc_embed_dim=cfg["C_enc"], enc_depth=cfg["enc_depth"], enc_num_heads=cfg["enc_heads"]),
+                 info_sharing_kwargs=dict(depth=cfg["dec_depth"], dim=cfg["C_dec"], num_heads=cfg["dec_heads"]),
+                 dpt_kwargs=dict(layer_dims=[12, 24, 48, 96]), dpt_indices=tuple(cfg["ifr_indices"]))
+    assert list(m.state_dict().keys()) == list(cfg["shapes"].keys())  # same keys in the same (alias) order as the reference
+    m.load_state_dict(weights(cfg))
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    img1, img2 = a["img1"], a["img2"]
+    B, _, H, W = img1.shape
+    feat = O.croco_encoder(sd, "encoder.", torch.cat((img1, img2), 0), cfg["enc_depth"], cfg["enc_heads"])
+    f1, f2 = feat.chunk(2, dim=0)
+    (d1, d2), inter = O.info_sharing(sd, "info_sharing.", [f1, f2], cfg["dec_depth"], cfg["dec_heads"],
+                                     indices=cfg["ifr_indices"], norm_intermediate=False)
+    o1 = O.dpt_regressor(sd, "dpt_regressor_head1.", O.dpt_feature(sd, "dpt_feature_head1.", [f1, inter[0][0], inter[1][0], d1]), (H, W))
+    o2 = O.dpt_regressor(sd, "dpt_regressor_head2.", O.dpt_feature(sd, "dpt_feature_head2.", [f2, inter[0][1], inter[1][1], d2]), (H, W))
+    p1, c1 = O.pointmap_conf_adaptor(o1)
+    p2, c2 = O.pointmap_conf_adaptor(o2)
+    _close(p1.permute(0, 2, 3, 1), a["pts3d_1"])
+    _close(c1.permute(0, 2, 3, 1), a["conf_1"])
+    _close(p2.permute(0, 2, 3, 1), a["pts3d_2"])
+    _close(c2.permute(0, 2, 3, 1), a["conf_2"])
+    (p1.sum() + c1.sum() + p2.sum() + c2.sum()).backward()
+    _close(sd["encoder.enc_blocks.0.attn.qkv.weight"].grad, a["grad_qkv0"], 1e-4)
+    _close(sd["info_sharing.multi_view_branches.1.0.cross_attn.projk.weight"].grad, a["grad_projk"], 1e-4)

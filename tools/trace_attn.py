@@ -1,4 +1,6 @@
-"""Cycle trace of one CTA of the attention-backward kernels (debug aid)."""
+"""Cycle trace of CTA (0,0) of the pipelined attention-backward kernel (bring-up aid).
+    python tools/trace_attn.py            # encoder shape B16 H16 N1024
+Columns are cycles since the CTA's first recorded event."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -14,19 +16,18 @@ dqkv = torch.empty_like(qkv)
 for _ in range(2):
     ops.attn_bwd(q, k, v, o, do, lse, B, H, N, N, 0.125, dqkv[:, :Cc], dqkv[:, Cc:2 * Cc], dqkv[:, 2 * Cc:])
 torch.cuda.synchronize()
-trace = torch.zeros(2048, dtype=torch.int64, device="cuda")
-fn = _lib.lib.uc_debug_set_trace
+trace = torch.zeros(3 * 64 * 8, dtype=torch.int64, device="cuda")
+fn = _lib.lib.uc_debug_set_attn_trace
 fn.argtypes = [ctypes.c_void_p]
 fn(trace.data_ptr())
 ops.attn_bwd(q, k, v, o, do, lse, B, H, N, N, 0.125, dqkv[:, :Cc], dqkv[:, Cc:2 * Cc], dqkv[:, 2 * Cc:])
 torch.cuda.synchronize()
 fn(None)
-tt = trace.cpu().view(2, 2, 64, 8)
-for mode in (0, 1):
-    t = tt[mode]
-    base = int(t[0, 0, 0])
-    print(f"MODE {mode}: tile | MMA: sfull_ok sdp_issued ds_ready_ok acc_issued | EXP: sdp_ok ld_done math_done st_done   (cycles since first event)")
-    for i in range(4, 12):
-        m = [int(x) - base for x in t[0, i, :4]]
-        e = [int(x) - base for x in t[1, i, :4]]
-        print(f"{i:3d} | {m[0]:7d} {m[1]:7d} {m[2]:7d} {m[3]:7d} | {e[0]:7d} {e[1]:7d} {e[2]:7d} {e[3]:7d}")
+t = trace.cpu().view(3, 64, 8)
+base = int(t[t > 0].min())
+print("sub | MMA: loop_top sdp(j+1)_issued ds_ready(j)_seen acc_issued | EXP(warp2): top sdp_full_seen ld_done math_done arrived | DRAIN(tile=j/2): top dq_full_seen stored")
+for j in range(16):
+    m = [int(x) - base for x in t[0, j, :4]]
+    e = [int(x) - base for x in t[1, j, :5]]
+    d = [int(x) - base for x in t[2, j // 2, :3]] if j % 2 == 1 else []
+    print(f"{j:3d} | " + " ".join(f"{x:7d}" for x in m) + " | " + " ".join(f"{x:7d}" for x in e) + " | " + " ".join(f"{x:7d}" for x in d))

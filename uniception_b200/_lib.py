@@ -60,6 +60,7 @@ class LayerNormBwdParams(C.Structure):
         ("dy", vp), ("x", vp), ("dres", vp), ("dx", vp), ("gamma", vp), ("mean", vp), ("rstd", vp),
         ("dgamma", vp), ("dbeta", vp),
         ("rows", i32), ("C", i32), ("dy_dtype", i32), ("x_dtype", i32),
+        ("dx_colsum", vp),
     ]
 
 

@@ -3,6 +3,7 @@
 // All are HBM-bound: 128-bit loads/stores, warp-shuffle reductions, fp32 statistics, grids sized in
 // multiples of the SM count.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace uc {
 namespace {
@@ -158,6 +159,68 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(uc_layernorm_fwd_par
   }
 }
 
+// Hot-path variant: bf16 in -> bf16 out, C == CH * 256.  The row stays in its packed 16-byte form (CH uint4 per
+// lane), so the kernel needs < 64 registers and 32 warps are resident per SM; the NEXT row of the warp is requested
+// before the current one is reduced (one exposed memory latency per warp, not per row).
+template <int CH>
+__global__ void __launch_bounds__(256, CH >= 4 ? 3 : 4) layernorm_fwd_bf16_kernel(uc_layernorm_fwd_params p) {
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * (blockDim.x >> 5);
+  const float inv_c = 1.0f / (float)(CH * 256);
+  const uint4* xin = static_cast<const uint4*>(p.x);
+  uint4* yout = static_cast<uint4*>(p.y);
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  uint4 cur[CH], nxt[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) cur[c] = __ldg(xin + (int64_t)row * (CH * 32) + c * 32 + lane);
+  for (; row < p.rows; row += stride) {
+    const int nrow = row + stride;
+    if (nrow < p.rows) {
+#pragma unroll
+      for (int c = 0; c < CH; ++c) nxt[c] = __ldg(xin + (int64_t)nrow * (CH * 32) + c * 32 + lane);
+    }
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      s0 += (bf16_lo(cur[c].x) + bf16_hi(cur[c].x)) + (bf16_lo(cur[c].y) + bf16_hi(cur[c].y));
+      s1 += (bf16_lo(cur[c].z) + bf16_hi(cur[c].z)) + (bf16_lo(cur[c].w) + bf16_hi(cur[c].w));
+    }
+    const float mean = warp_sum(s0 + s1) * inv_c;
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const uint32_t w[4] = {cur[c].x, cur[c].y, cur[c].z, cur[c].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float d0 = bf16_lo(w[j]) - mean, d1 = bf16_hi(w[j]) - mean;
+        q0 = fmaf(d0, d0, q0);
+        q1 = fmaf(d1, d1, q1);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q0 + q1) * inv_c + p.eps);
+    if (lane == 0) {
+      if (p.mean) p.mean[row] = mean;
+      if (p.rstd) p.rstd[row] = rstd;
+    }
+    const float nm = -mean * rstd;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int col = c * 256 + lane * 8;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + col)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + col) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + col)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + col) + 1);
+      uint4 o;
+      o.x = pack_bf16(fmaf(fmaf(bf16_lo(cur[c].x), rstd, nm), g0.x, b0.x), fmaf(fmaf(bf16_hi(cur[c].x), rstd, nm), g0.y, b0.y));
+      o.y = pack_bf16(fmaf(fmaf(bf16_lo(cur[c].y), rstd, nm), g0.z, b0.z), fmaf(fmaf(bf16_hi(cur[c].y), rstd, nm), g0.w, b0.w));
+      o.z = pack_bf16(fmaf(fmaf(bf16_lo(cur[c].z), rstd, nm), g1.x, b1.x), fmaf(fmaf(bf16_hi(cur[c].z), rstd, nm), g1.y, b1.y));
+      o.w = pack_bf16(fmaf(fmaf(bf16_lo(cur[c].w), rstd, nm), g1.z, b1.z), fmaf(fmaf(bf16_hi(cur[c].w), rstd, nm), g1.w, b1.w));
+      yout[(int64_t)row * (CH * 32) + c * 32 + lane] = o;
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) cur[c] = nxt[c];
+  }
+}
+
 // dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)) [+ dres];  dgamma += sum dy*xhat;  dbeta += sum dy
 // One warp per row, latency-bound: x, dy and dres of a row are requested TOGETHER (one exposed memory latency per
 // row) and kept in registers in their packed 16-byte form; only the 2*CH*8 dgamma/dbeta partial sums persist across
@@ -280,6 +343,115 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(uc_layernorm_bwd_
       atomicAdd(p.dgamma + i, red[i]);
       atomicAdd(p.dbeta + i, red[p.C + i]);
     }
+  }
+}
+
+// Hot-path variant (bf16 x / dy / dres, C % 128 == 0): a BLOCK of C/4 threads walks batches of G rows, thread <-> 4
+// columns.  Only 3 x 4 column partials (dgamma, dbeta, colsum(dx)) persist in registers, so the kernel fits 3+ blocks per
+// SM with G rows x 3 tensors of 8-byte loads in flight per thread; the 2G row sums of a batch are reduced with a
+// 16-shuffle value-halving butterfly per warp and two block barriers.
+template <int G>
+__global__ void __launch_bounds__(256) layernorm_bwd_rows_kernel(uc_layernorm_bwd_params p) {
+  __shared__ float part[8][2 * G];
+  __shared__ float tot[2 * G];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int col = threadIdx.x * 4;
+  const float inv_c = 1.0f / (float)p.C;
+  const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
+  const uint2* xin = static_cast<const uint2*>(p.x) + threadIdx.x;
+  const uint2* dyin = static_cast<const uint2*>(p.dy) + threadIdx.x;
+  const uint2* rin = p.dres ? static_cast<const uint2*>(p.dres) + threadIdx.x : nullptr;
+  uint2* dxout = static_cast<uint2*>(p.dx) + threadIdx.x;
+  const int rowq = p.C >> 2;  // uint2 per row
+  float dg[4] = {0, 0, 0, 0}, db[4] = {0, 0, 0, 0}, dc[4] = {0, 0, 0, 0};
+  for (int row0 = blockIdx.x * G; row0 < p.rows; row0 += gridDim.x * G) {
+    uint2 rx[G], rdy[G], rr[G];
+    float mean[G], rstd[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int row = min(row0 + g, p.rows - 1);  // tail rows are clamped (re-read) and masked below
+      rx[g] = __ldg(xin + (int64_t)row * rowq);
+      rdy[g] = __ldg(dyin + (int64_t)row * rowq);
+      rr[g] = rin ? __ldg(rin + (int64_t)row * rowq) : make_uint2(0u, 0u);
+      mean[g] = __ldg(p.mean + row);
+      rstd[g] = __ldg(p.rstd + row);
+    }
+    float s[2 * G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float live = (row0 + g < p.rows) ? 1.0f : 0.0f;
+      const float x4[4] = {bf16_lo(rx[g].x), bf16_hi(rx[g].x), bf16_lo(rx[g].y), bf16_hi(rx[g].y)};
+      const float d4[4] = {bf16_lo(rdy[g].x) * live, bf16_hi(rdy[g].x) * live, bf16_lo(rdy[g].y) * live, bf16_hi(rdy[g].y) * live};
+      const float g4[4] = {gm.x, gm.y, gm.z, gm.w};
+      const float nm = -mean[g] * rstd[g];
+      float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = fmaf(x4[j], rstd[g], nm);
+        const float gy = g4[j] * d4[j];
+        a1 += gy;
+        a2 = fmaf(gy, xh, a2);
+        dg[j] = fmaf(d4[j], xh, dg[j]);
+        db[j] += d4[j];
+      }
+      s[g] = a1;
+      s[G + g] = a2;
+    }
+    // warp reduction of 2G values with value halving: lane l ends with the warp total of value l >> (5 - log2(2G))
+#pragma unroll
+    for (int n = G, k = 16; n >= 1; n >>= 1, k >>= 1) {
+      const bool up = (lane & k) != 0;
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        const float send = up ? s[i] : s[i + n];
+        const float keep = up ? s[i + n] : s[i];
+        s[i] = keep + __shfl_xor_sync(0xffffffffu, send, k);
+      }
+    }
+    constexpr int kRest = 32 / (2 * G);  // lanes that still hold partial sums of the same value
+#pragma unroll
+    for (int k = kRest >> 1; k >= 1; k >>= 1) s[0] += __shfl_xor_sync(0xffffffffu, s[0], k);
+    if ((lane & (kRest - 1)) == 0) part[warp][lane / kRest] = s[0];
+    __syncthreads();
+    if (threadIdx.x < 2 * G) {
+      float t = 0.f;
+      for (int w = 0; w < nwarps; ++w) t += part[w][threadIdx.x];
+      tot[threadIdx.x] = t * inv_c;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      if (row0 + g >= p.rows) break;
+      const float s1 = tot[g], s2 = tot[G + g];
+      const float x4[4] = {bf16_lo(rx[g].x), bf16_hi(rx[g].x), bf16_lo(rx[g].y), bf16_hi(rx[g].y)};
+      const float d4[4] = {bf16_lo(rdy[g].x), bf16_hi(rdy[g].x), bf16_lo(rdy[g].y), bf16_hi(rdy[g].y)};
+      const float r4[4] = {bf16_lo(rr[g].x), bf16_hi(rr[g].x), bf16_lo(rr[g].y), bf16_hi(rr[g].y)};
+      const float g4[4] = {gm.x, gm.y, gm.z, gm.w};
+      const float nm = -mean[g] * rstd[g];
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = fmaf(x4[j], rstd[g], nm);
+        const float t = fmaf(-xh, s2, fmaf(g4[j], d4[j], -s1));
+        o[j] = round_bf16(fmaf(t, rstd[g], r4[j]));
+        dc[j] += o[j];
+      }
+      uint2 w;
+      w.x = pack_bf16(o[0], o[1]);
+      w.y = pack_bf16(o[2], o[3]);
+      dxout[(int64_t)(row0 + g) * rowq] = w;
+    }
+  }
+  if (p.dgamma) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(p.dgamma + col + j, dg[j]);
+      atomicAdd(p.dbeta + col + j, db[j]);
+    }
+  }
+  if (p.dx_colsum) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(p.dx_colsum + col + j, dc[j]);
   }
 }
 
@@ -491,6 +663,16 @@ extern "C" int uc_layernorm_fwd(const uc_layernorm_fwd_params* p, uc_stream_t st
   const int grid = grid_for((int64_t)p->rows * 32, 256, 8);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int ch = (p->C + 255) / 256;
+  if (p->x_dtype == UC_DTYPE_BF16 && p->y_dtype == UC_DTYPE_BF16 && p->C % 256 == 0 && ch >= 2 && ch <= 4 &&
+      ((uintptr_t)p->x % 16 == 0) && ((uintptr_t)p->y % 16 == 0)) {
+    // persistent: 3-4 blocks of 8 warps per SM, each warp walks rows with a one-row prefetch
+    int g = sm_count() * (ch >= 4 ? 3 : 4);
+    if (g > (p->rows + 7) / 8) g = (p->rows + 7) / 8;
+    if (ch == 2) layernorm_fwd_bf16_kernel<2><<<g, 256, 0, stream>>>(*p);
+    else if (ch == 3) layernorm_fwd_bf16_kernel<3><<<g, 256, 0, stream>>>(*p);
+    else layernorm_fwd_bf16_kernel<4><<<g, 256, 0, stream>>>(*p);
+    return check_launch("uc_layernorm_fwd");
+  }
   if (ch <= 1) layernorm_fwd_kernel<1><<<grid, 256, 0, stream>>>(*p);
   else if (ch <= 2) layernorm_fwd_kernel<2><<<grid, 256, 0, stream>>>(*p);
   else if (ch <= 3) layernorm_fwd_kernel<3><<<grid, 256, 0, stream>>>(*p);
@@ -504,8 +686,27 @@ extern "C" int uc_layernorm_bwd(const uc_layernorm_bwd_params* p, uc_stream_t st
   UC_REQUIRE(p->C % 8 == 0 && p->C <= 256 * LN_MAX_CHUNKS && p->rows > 0, UC_ERR_BAD_SHAPE,
              "uc_layernorm_bwd: C=%d must be a multiple of 8 and <= %d", p->C, 256 * LN_MAX_CHUNKS);
   UC_REQUIRE((p->dgamma == nullptr) == (p->dbeta == nullptr), UC_ERR_BAD_SHAPE, "uc_layernorm_bwd: dgamma/dbeta must both be set");
-  const int grid = grid_for((int64_t)p->rows * 32, 256, 2);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (p->x_dtype == UC_DTYPE_BF16 && p->dy_dtype == UC_DTYPE_BF16 && p->C % 128 == 0 && p->C <= 1024 &&
+      ((uintptr_t)p->x % 8 == 0) && ((uintptr_t)p->dy % 8 == 0) && ((uintptr_t)p->dx % 8 == 0) && ((uintptr_t)p->dres % 8 == 0)) {
+    constexpr int G = 4;
+    static const int g_env = [] { const char* e = getenv("UC_LN_BWD_G"); return e ? atoi(e) : 4; }();
+    const int threads = p->C / 4;
+    const int per_sm = 768 / threads >= 1 ? (768 / threads) : 1;  // ~24 warps per SM
+    int grid = sm_count() * per_sm;
+    if (g_env == 8) {
+      const int need = (p->rows + 7) / 8;
+      if (grid > need) grid = need;
+      layernorm_bwd_rows_kernel<8><<<grid, threads, 0, stream>>>(*p);
+    } else {
+      const int need = (p->rows + G - 1) / G;
+      if (grid > need) grid = need;
+      layernorm_bwd_rows_kernel<G><<<grid, threads, 0, stream>>>(*p);
+    }
+    return check_launch("uc_layernorm_bwd");
+  }
+  UC_REQUIRE(p->dx_colsum == nullptr, UC_ERR_UNSUPPORTED, "uc_layernorm_bwd: dx_colsum needs bf16 inputs and C %% 128 == 0, C <= 1024");
+  const int grid = grid_for((int64_t)p->rows * 32, 256, 2);
   const size_t sm = 2 * p->C * sizeof(float);
   const int ch = (p->C + 255) / 256;
   const bool bf = p->x_dtype == UC_DTYPE_BF16 && p->dy_dtype == UC_DTYPE_BF16;

@@ -350,7 +350,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 constexpr int G2_BN = 256;
 constexpr int G2_STAGES = 5;
 constexpr uint32_t G2_A_BYTES = 128 * BK * 2, G2_B_BYTES = 128 * BK * 2, G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
-constexpr uint32_t G2_STG_BYTES = NUM_EPI_WARPS * 2 * 4096;  // per epilogue warp: two 32-row x 128-byte staging tiles
+constexpr uint32_t G2_STG_WARP = 2 * 4096;  // per epilogue warp: two 32-row x 128-byte staging tiles (see the epilogue)
+constexpr uint32_t G2_STG_BYTES = NUM_EPI_WARPS * G2_STG_WARP;
 constexpr uint32_t G2_SMEM = G2_STAGES * G2_STAGE_BYTES + G2_STG_BYTES + 1024 + 256;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
@@ -367,7 +368,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
-  auto ld_bar = [&](int e) { return bar_base + 8u * (2 * STAGES + 6 + e); };  // per epilogue warp: staged input tile landed
+  auto ld_bar = [&](int e, int which) { return bar_base + 8u * (2 * STAGES + 6 + 2 * e + which); };  // per epilogue warp: input tile A / B landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -386,7 +387,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 2 * NUM_EPI_WARPS);  // leader: epilogue warps of both CTAs
     }
-    for (int e = 0; e < NUM_EPI_WARPS; ++e) mbar_init(ld_bar(e), 1);
+    for (int e = 0; e < NUM_EPI_WARPS; ++e) { mbar_init(ld_bar(e, 0), 1); mbar_init(ld_bar(e, 1), 1); }
     fence_barrier_init();
   }
   cluster_sync_all();  // barrier inits visible to the peer before any remote arrive / TMA credit
@@ -484,12 +485,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int e = warp - 2;
     const int lane_group = warp & 3;
     const int col_half = e >> 2;
-    const uint32_t stg = stg_base + e * 8192;  // [0]: C tile, [1]: GELU pre-activation tile
+    const uint32_t stg = stg_base + e * G2_STG_WARP;
+    // two tiles per warp.  plain: C of unit u -> buf[u];  GELU: C -> buf0, pre-activation -> buf1;  GELU'/ReLU'/residual:
+    // the input tile of unit u lands in buf[u] (TMA load, prefetched one unit ahead) and is overwritten IN PLACE by the
+    // unit's output (each lane has read its own 16-byte chunks before it writes them)
+    const uint32_t buf0 = stg, buf1 = stg + 4096;
     const bool f32 = g.c_f32 != 0;
     const bool atomic = (g.epilogue & UC_EPI_ATOMIC) != 0;
     const bool has_aux = (g.epilogue & UC_EPI_GELU) != 0;
     const bool has_in = (g.epilogue & (UC_EPI_GELU_BWD | UC_EPI_RELU_BWD | UC_EPI_RESIDUAL)) != 0;  // aux_in / residual tile, via TMA
-    uint32_t ld_phase = 0;
+    uint32_t ph_a = 0, ph_b = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     auto stage_and_store = [&](const CUtensorMap* tm, uint32_t buf, const uint32_t (&w)[32], int col, int row0, bool reduce) {
@@ -516,17 +521,35 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int kb0 = split * g.kb_per_split;
       const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
       if (kb0 >= kb1) continue;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
       const int row0 = m0 + lane_group * 32;
       const int row = row0 + lane;
       const bool row_ok = row < g.m;
+      const int nw = n0 + col_half * (BN / 2);  // first column of this warp's 128-column half
+      if (!f32 && has_in) {
+        // input tile of unit 0 ([32 rows x 64 cols] bf16 of aux_in / residual) requested BEFORE waiting for the accumulator
+        if (lane == 0) {
+          tma_store_wait_read1();  // the previous tile's unit-0 store has finished reading buf0
+          mbar_arrive_expect_tx(ld_bar(e, 0), 4096);
+          tma_load_2d(buf0, &tmAux, ld_bar(e, 0), nw, row0);
+        }
+        __syncwarp();
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
       int pos_y = 0, pos_x = 0;
       if ((g.epilogue & UC_EPI_ROPE) && row_ok) {
         pos_y = g.positions[2 * row];
         pos_x = g.positions[2 * row + 1];
       }
       const uint32_t tbase = tmem_base + (uint32_t(lane_group * 32) << 16) + uint32_t(acc * BN + col_half * (BN / 2));
+      auto release_acc = [&]() {  // this warp has read all of its accumulator columns
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) mbar_arrive(tempty_bar(acc));
+          else mbar_arrive_cluster(tempty_bar(acc), 0);
+        }
+      };
       if (f32) {
         // 4 units of 32 fp32 columns (128 B rows)
 #pragma unroll 1
@@ -535,65 +558,90 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           __syncwarp();
           tmem_ld32(tbase + u * 32, r);
           tmem_ld_wait();
-          const int n = n0 + col_half * (BN / 2) + u * 32;
+          const int n = nw + u * 32;
           float v[32], pre[32];
           epilogue_math(g, row, n, pos_y, pos_x, row_ok, r, v, pre);
           uint32_t w[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j]);
-          stage_and_store(&tmC, stg, w, n, row0, atomic);
+          stage_and_store(&tmC, buf0, w, n, row0, atomic);
         }
+        release_acc();
       } else {
-        // 2 units of 64 bf16 columns (128 B rows)
-#pragma unroll 1
-        for (int u = 0; u < 2; ++u) {
-          uint32_t r0[32], r1[32];
-          const int n = n0 + col_half * (BN / 2) + u * 64;
-          __syncwarp();
-          if (has_in && lane == 0) {  // [32 rows x 64 cols] bf16 input tile -> staging tile 1 (free: no aux_out in these modes)
-            tma_store_wait_read0();
-            mbar_arrive_expect_tx(ld_bar(e), 4096);
-            tma_load_2d(stg + 4096, &tmAux, ld_bar(e), n, row0);
-          }
-          tmem_ld32(tbase + u * 64, r0);
-          tmem_ld32(tbase + u * 64 + 32, r1);
-          tmem_ld_wait();
-          float v0[32], v1[32], p0[32], p1[32];
-          if (has_in) {
-            mbar_wait(ld_bar(e), ld_phase);
-            ld_phase ^= 1u;
-            float h0[32], h1[32];
+        // bf16 out: 4 chunks of 32 columns = 2 staged units of 64 columns (128 B rows), software-pipelined: the
+        // TMEM load of chunk c+1 and the TMA load of the other unit's input tile are in flight behind chunk c's math
+        uint32_t ra[32], rb[32];
+        __syncwarp();
+        tmem_ld32(tbase, ra);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+        for (int c = 0; c < 4; ++c) {
+          const int u = c >> 1, hf = c & 1;
+          uint32_t(&rc)[32] = (c & 1) ? rb : ra;
+          uint32_t(&rn)[32] = (c & 1) ? ra : rb;
+          tmem_ld_wait();
+          if (c + 1 < 4) tmem_ld32(tbase + 32 * (c + 1), rn);
+          else release_acc();
+          const int n = nw + c * 32;
+          float v[32], pre[32], h[32];
+          if (has_in) {
+            if (hf == 0) {
+              if (u == 0) {
+                if (lane == 0) {
+                  tma_store_wait_read0();  // the previous tile's unit-1 store has finished reading buf1
+                  mbar_arrive_expect_tx(ld_bar(e, 1), 4096);
+                  tma_load_2d(buf1, &tmAux, ld_bar(e, 1), nw + 64, row0);
+                }
+                mbar_wait(ld_bar(e, 0), ph_a);
+                ph_a ^= 1u;
+              } else {
+                mbar_wait(ld_bar(e, 1), ph_b);
+                ph_b ^= 1u;
+              }
+            }
+            const uint32_t inb = u ? buf1 : buf0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
               uint32_t a0, a1, a2, a3;
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
-                           : "r"(stg + 4096 + lane * 128 + ((j ^ (lane & 7)) << 4)));
-              float* h = (j < 4) ? &h0[8 * j] : &h1[8 * (j - 4)];
-              h[0] = bf16_lo(a0); h[1] = bf16_hi(a0); h[2] = bf16_lo(a1); h[3] = bf16_hi(a1);
-              h[4] = bf16_lo(a2); h[5] = bf16_hi(a2); h[6] = bf16_lo(a3); h[7] = bf16_hi(a3);
+                           : "r"(inb + lane * 128 + (((hf * 4 + j) ^ (lane & 7)) << 4)));
+              h[8 * j + 0] = bf16_lo(a0); h[8 * j + 1] = bf16_hi(a0); h[8 * j + 2] = bf16_lo(a1); h[8 * j + 3] = bf16_hi(a1);
+              h[8 * j + 4] = bf16_lo(a2); h[8 * j + 5] = bf16_hi(a2); h[8 * j + 6] = bf16_lo(a3); h[8 * j + 7] = bf16_hi(a3);
             }
-            epilogue_math(g, row, n, pos_y, pos_x, row_ok, r0, v0, p0, h0);
-            epilogue_math(g, row, n + 32, pos_y, pos_x, row_ok, r1, v1, p1, h1);
+            epilogue_math(g, row, n, pos_y, pos_x, row_ok, rc, v, pre, h);
           } else {
-            epilogue_math(g, row, n, pos_y, pos_x, row_ok, r0, v0, p0);
-            epilogue_math(g, row, n + 32, pos_y, pos_x, row_ok, r1, v1, p1);
+            epilogue_math(g, row, n, pos_y, pos_x, row_ok, rc, v, pre);
           }
-          uint32_t w[32];
-          if (has_aux) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { w[j] = pack_bf16(p0[2 * j], p0[2 * j + 1]); w[16 + j] = pack_bf16(p1[2 * j], p1[2 * j + 1]); }
-            stage_and_store(&tmAux, stg + 4096, w, n, row0, false);
+          const uint32_t outb = (has_aux || u == 0) ? buf0 : buf1;
+          if (hf == 0 && !has_in) {  // staging tile free once the bulk store that last read it has completed
+            if (lane == 0) {
+              if (has_aux) tma_store_wait_read0();
+              else tma_store_wait_read1();
+            }
+            __syncwarp();
           }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { w[j] = pack_bf16(v0[2 * j], v0[2 * j + 1]); w[16 + j] = pack_bf16(v1[2 * j], v1[2 * j + 1]); }
-          stage_and_store(&tmC, stg, w, n, row0, false);
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t so = lane * 128 + (((hf * 4 + j) ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(outb + so), "r"(pack_bf16(v[8 * j], v[8 * j + 1])),
+                         "r"(pack_bf16(v[8 * j + 2], v[8 * j + 3])), "r"(pack_bf16(v[8 * j + 4], v[8 * j + 5])),
+                         "r"(pack_bf16(v[8 * j + 6], v[8 * j + 7]))
+                         : "memory");
+            if (has_aux)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf1 + so), "r"(pack_bf16(pre[8 * j], pre[8 * j + 1])),
+                           "r"(pack_bf16(pre[8 * j + 2], pre[8 * j + 3])), "r"(pack_bf16(pre[8 * j + 4], pre[8 * j + 5])),
+                           "r"(pack_bf16(pre[8 * j + 6], pre[8 * j + 7]))
+                           : "memory");
+          }
+          if (hf == 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (has_aux) tma_store_2d(&tmAux, buf1, n - 32, row0);
+              tma_store_2d(&tmC, outb, n - 32, row0);
+              tma_store_commit();
+            }
+          }
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (rank == 0) mbar_arrive(tempty_bar(acc));
-        else mbar_arrive_cluster(tempty_bar(acc), 0);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;

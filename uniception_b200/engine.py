@@ -84,17 +84,19 @@ def linear_fwd(pk: ParamPack, name: str, x, *, residual=None, rope: Optional[Rop
 
 
 def linear_bwd(pk: ParamPack, name: str, dy, x_in, *, need_dx=True, gelu_pre=None, w16=None, wgrad=None, bgrad=None,
-               train_w=None):
+               train_w=None, bias_done=False):
     """dy [rows, out] bf16, x_in [rows, in] bf16.  Accumulates dW, db; returns dx (bf16) or None.
-    gelu_pre: dx is additionally multiplied by gelu'(gelu_pre) (the producer of x_in was GELU)."""
+    gelu_pre: dx is additionally multiplied by gelu'(gelu_pre) (the producer of x_in was GELU).
+    bias_done: db = colsum(dy) was already accumulated by the kernel that produced dy (uc_layernorm_bwd's dx_colsum)."""
     w = pk.w16(name + ".weight") if w16 is None else w16
     if train_w is None:
         train_w = pk.requires_grad(name + ".weight")
     if train_w:
         gw = pk.grad(name + ".weight") if wgrad is None else wgrad
         ops.gemm(dy, x_in, gw, a_layout=1, b_layout=1, atomic=True)
-        gb = pk.grad(name + ".bias") if bgrad is None else bgrad
-        ops.colsum_(dy, gb)
+        if not bias_done:
+            gb = pk.grad(name + ".bias") if bgrad is None else bgrad
+            ops.colsum_(dy, gb)
     if not need_dx:
         return None
     dx = _empty(dy.shape[0], w.shape[1], dy)
@@ -109,10 +111,23 @@ def ln_fwd(pk: ParamPack, name: str, x, out_dtype=torch.bfloat16):
     return ops.layernorm_fwd(x, pk.w32(name + ".weight"), pk.w32(name + ".bias"), LN_EPS, out_dtype)
 
 
-def ln_bwd(pk: ParamPack, name: str, dy, x, mean, rstd, dres=None):
+def ln_bwd(pk: ParamPack, name: str, dy, x, mean, rstd, dres=None, colsum=None):
+    """colsum: fp32 [C] bias-gradient buffer of the Linear that will consume this call's dx as ITS output gradient
+    (see `bias_sink`); the column sums of dx are accumulated there by the same kernel."""
     train = pk.requires_grad(name + ".weight")
     return ops.layernorm_bwd(dy, x, pk.w32(name + ".weight"), mean, rstd,
-                             pk.grad(name + ".weight") if train else None, pk.grad(name + ".bias") if train else None, dres=dres)
+                             pk.grad(name + ".weight") if train else None, pk.grad(name + ".bias") if train else None, dres=dres,
+                             dx_colsum=colsum)
+
+
+def bias_sink(pk: ParamPack, linear_name: Optional[str], like: Optional[torch.Tensor] = None):
+    """Gradient buffer of `linear_name`.bias if that Linear trains and the fused column sum applies, else None."""
+    if linear_name is None or not pk.requires_grad(linear_name + ".weight"):
+        return None
+    g = pk.grad(linear_name + ".bias")
+    if g.shape[0] % 128 != 0 or g.shape[0] > 1024:  # uc_layernorm_bwd's fast path (csrc/elementwise.cu)
+        return None
+    return g
 
 
 # ------------------------------------------------------------------------------------------------
@@ -129,18 +144,19 @@ def self_attn_fwd(pk, p, x, B, N, H, rope: Optional[Rope], norm: str, saved: lis
     return x2
 
 
-def self_attn_bwd(pk, p, dx2, B, N, H, rope: Optional[Rope], norm: str, saved):
-    """dx2: gradient w.r.t. the sub-block output (bf16).  Returns gradient w.r.t. its input."""
+def self_attn_bwd(pk, p, dx2, B, N, H, rope: Optional[Rope], norm: str, saved, bias_done=False, out_sink=None):
+    """dx2: gradient w.r.t. the sub-block output (bf16).  Returns gradient w.r.t. its input.
+    bias_done: colsum(dx2) already sits in attn.proj.bias.grad; out_sink: bias-gradient buffer fed by the returned dx."""
     x, mean, rstd, h1, qkv, o, lse = saved
     C = H * 64
-    d_o = linear_bwd(pk, p + "attn.proj", dx2, o)
+    d_o = linear_bwd(pk, p + "attn.proj", dx2, o, bias_done=bias_done)
     dqkv = torch.empty_like(qkv)
     ops.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, d_o, lse, B, H, N, N, 0.125,
                  dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:],
                  q_positions=rope.pos if rope is not None else None, k_positions=rope.pos if rope is not None else None,
                  rope_table=rope.table if rope is not None else None)
     d_h1 = linear_bwd(pk, p + "attn.qkv", dqkv, h1)
-    return ln_bwd(pk, p + norm, d_h1, x, mean, rstd, dres=dx2)
+    return ln_bwd(pk, p + norm, d_h1, x, mean, rstd, dres=dx2, colsum=out_sink)
 
 
 def mlp_fwd(pk, p, x, norm: str, saved: list):
@@ -151,11 +167,11 @@ def mlp_fwd(pk, p, x, norm: str, saved: list):
     return x2
 
 
-def mlp_bwd(pk, p, dx2, norm: str, saved):
+def mlp_bwd(pk, p, dx2, norm: str, saved, bias_done=False, out_sink=None):
     x, mean, rstd, h, pre, act = saved
-    d_pre = linear_bwd(pk, p + "mlp.fc2", dx2, act, gelu_pre=pre)
+    d_pre = linear_bwd(pk, p + "mlp.fc2", dx2, act, gelu_pre=pre, bias_done=bias_done)
     d_h = linear_bwd(pk, p + "mlp.fc1", d_pre, h)
-    return ln_bwd(pk, p + norm, d_h, x, mean, rstd, dres=dx2)
+    return ln_bwd(pk, p + norm, d_h, x, mean, rstd, dres=dx2, colsum=out_sink)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -198,8 +214,12 @@ def encoder_bwd(pk: ParamPack, p: str, saved, d_out: Optional[torch.Tensor], dep
     """d_out: gradient w.r.t. the normalised output tokens ([B*N, C] bf16 or fp32), or None."""
     B, N, rope = saved["B"], saved["N"], saved["rope"]
     x, mean, rstd = saved["final"]
-    dx = ln_bwd(pk, p + "enc_norm", d_out.contiguous(), x, mean, rstd) if d_out is not None else None
     inter_at = {i: (k, xi, m, r) for k, (i, xi, m, r) in enumerate(saved["inter"])}
+    # Bias gradients of fc2 / proj are column sums of the residual-stream gradient; the LayerNorm-backward kernel that
+    # PRODUCES that gradient accumulates them (`sink`), unless an intermediate-feature tap still adds to it afterwards.
+    sink = bias_sink(pk, f"{p}enc_blocks.{depth - 1}.mlp.fc2") if (depth > 0 and (depth - 1) not in inter_at) else None
+    dx = ln_bwd(pk, p + "enc_norm", d_out.contiguous(), x, mean, rstd, colsum=sink) if d_out is not None else None
+    done = dx is not None and sink is not None
     for i in reversed(range(depth)):
         if i in inter_at:
             k, xi, m, r = inter_at[i]
@@ -214,12 +234,19 @@ def encoder_bwd(pk: ParamPack, p: str, saved, d_out: Optional[torch.Tensor], dep
             continue
         bs = saved["blocks"][i]
         bp = f"{p}enc_blocks.{i}."
-        dx = mlp_bwd(pk, bp, dx, "norm2", bs[1])
-        dx = self_attn_bwd(pk, bp, dx, B, N, heads, rope, "norm1", bs[0])
+        sink = bias_sink(pk, bp + "attn.proj")
+        dx = mlp_bwd(pk, bp, dx, "norm2", bs[1], bias_done=done, out_sink=sink)
+        if i > 0:
+            nxt = bias_sink(pk, f"{p}enc_blocks.{i - 1}.mlp.fc2") if (i - 1) not in inter_at else None
+        else:
+            nxt = bias_sink(pk, p + "patch_embed.proj")
+        dx = self_attn_bwd(pk, bp, dx, B, N, heads, rope, "norm1", bs[0], bias_done=sink is not None, out_sink=nxt)
+        done = nxt is not None
         pk.notify_done(bp)  # this block's gradients are final -> its all-reduce bucket may start
     if dx is not None and pk.requires_grad(p + "patch_embed.proj.weight"):
         ops.gemm(dx, saved["cols"], pk.grad(p + "patch_embed.proj.weight"), a_layout=1, b_layout=1, atomic=True)
-        ops.colsum_(dx, pk.grad(p + "patch_embed.proj.bias"))
+        if not (done and depth > 0):
+            ops.colsum_(dx, pk.grad(p + "patch_embed.proj.bias"))
     return None
 
 
@@ -244,11 +271,11 @@ def _cross_fwd(pk, p, x, y, B, Nq, Nk, H, rope_q: Optional[Rope], rope_k: Option
     return x2
 
 
-def _cross_bwd(pk, p, dx2, B, Nq, Nk, H, rope_q, rope_k, saved, has_norm_y: bool):
+def _cross_bwd(pk, p, dx2, B, Nq, Nk, H, rope_q, rope_k, saved, has_norm_y: bool, bias_done=False, out_sink=None):
     """Returns (dx, d_yn): gradient w.r.t. the block's own stream and w.r.t. norm_y(y) (bf16)."""
     x, mean, rstd, h2, q, kv, o, lse, y, yn, ymean, yrstd = saved
     C = H * 64
-    d_o = linear_bwd(pk, p + "cross_attn.proj", dx2, o)
+    d_o = linear_bwd(pk, p + "cross_attn.proj", dx2, o, bias_done=bias_done)
     dq = torch.empty_like(q)
     dkv = torch.empty_like(kv)
     ops.attn_bwd(q, kv[:, :C], kv[:, C:], o, d_o, lse, B, H, Nq, Nk, 0.125, dq, dkv[:, :C], dkv[:, C:],
@@ -260,7 +287,7 @@ def _cross_bwd(pk, p, dx2, B, Nq, Nk, H, rope_q, rope_k, saved, has_norm_y: bool
     gkv = pk.grad_span(p + "cross_attn.projk.weight", p + "cross_attn.projv.weight").view(2 * C, -1)
     gbkv = pk.grad_span(p + "cross_attn.projk.bias", p + "cross_attn.projv.bias")
     d_yn = linear_bwd(pk, "", dkv, yn, w16=wkv, wgrad=gkv, bgrad=gbkv, train_w=pk.requires_grad(p + "cross_attn.projk.weight"))
-    dx = ln_bwd(pk, p + "norm2", d_h2, x, mean, rstd, dres=dx2)
+    dx = ln_bwd(pk, p + "norm2", d_h2, x, mean, rstd, dres=dx2, colsum=out_sink)
     return dx, d_yn
 
 
@@ -316,12 +343,23 @@ def decoder_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[torch.Te
                 d_inter: Sequence[Sequence[Optional[torch.Tensor]]] = (), has_proj_embed: bool = True, has_norm_y: bool = True,
                 need_input_grad: bool = True):
     B, N, nv, rope, rope_o = saved["B"], saved["N"], saved["nv"], saved["rope"], saved["rope_o"]
+    inter_levels = sorted({k for (k, _, _, _, _) in saved["inter"]})
+
+    def stream_sink(v: int, k: int):
+        """Bias buffer fed by the FINAL gradient of view v's token stream entering level k from above (k = -1: the
+        decoder input): fc2 of block (v, k), or proj_embed; None when an intermediate tap still adds to that gradient."""
+        if k >= 0:
+            return None if k in inter_levels else bias_sink(pk, f"{p}multi_view_branches.{v}.{k}.mlp.fc2")
+        return bias_sink(pk, p + "proj_embed") if has_proj_embed else None
+
     dxs: List[Optional[torch.Tensor]] = [None] * nv
+    done = [False] * nv  # colsum(dxs[v]) already accumulated into its consumer's bias gradient
     for v in range(nv):
         if d_outs[v] is not None:
             x, m, r = saved["final"][v]
-            dxs[v] = ln_bwd(pk, p + "norm", d_outs[v].contiguous(), x, m, r)
-    inter_levels = sorted({k for (k, _, _, _, _) in saved["inter"]})
+            sink = stream_sink(v, depth - 1)
+            dxs[v] = ln_bwd(pk, p + "norm", d_outs[v].contiguous(), x, m, r, colsum=sink)
+            done[v] = sink is not None
     for k in reversed(range(depth)):
         if k in inter_levels:
             li = inter_levels.index(k)
@@ -339,18 +377,27 @@ def decoder_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[torch.Te
         lvl = saved["blocks"][k]
         d_own: List[Optional[torch.Tensor]] = [None] * nv
         d_yn: List[Optional[torch.Tensor]] = [None] * nv
+        own_done = [False] * nv
+        fold_ln = nv == 2 and has_norm_y  # the norm_y backward of the OTHER view produces the final stream gradient
         for v in range(nv):
             if dxs[v] is None:
                 continue
             bp = f"{p}multi_view_branches.{v}.{k}."
             bs = lvl[v]
-            dx = mlp_bwd(pk, bp, dxs[v], "norm3", bs[2])
-            dx, d_yn[v] = _cross_bwd(pk, bp, dx, B, N, N * (nv - 1), heads, rope, rope_o, bs[1], has_norm_y)
-            d_own[v] = self_attn_bwd(pk, bp, dx, B, N, heads, rope, "norm1", bs[0])
+            s_cross = bias_sink(pk, bp + "cross_attn.proj")
+            dx = mlp_bwd(pk, bp, dxs[v], "norm3", bs[2], bias_done=done[v], out_sink=s_cross)
+            s_attn = bias_sink(pk, bp + "attn.proj")
+            dx, d_yn[v] = _cross_bwd(pk, bp, dx, B, N, N * (nv - 1), heads, rope, rope_o, bs[1], has_norm_y,
+                                     bias_done=s_cross is not None, out_sink=s_attn)
+            # if no fold follows for this view (the other view carries no gradient), norm1's backward is final
+            s_own = stream_sink(v, k - 1) if (nv == 2 and dxs[1 - v] is None) else None
+            d_own[v] = self_attn_bwd(pk, bp, dx, B, N, heads, rope, "norm1", bs[0], bias_done=s_attn is not None, out_sink=s_own)
+            own_done[v] = s_own is not None
             if not has_norm_y:
                 pk.notify_done(bp)
         # fold the cross-view gradients: d tokens_v(k-1) = d_own[v] + sum_{u != v} norm_y_u'(d_yn[u])|_v
         new: List[Optional[torch.Tensor]] = list(d_own)
+        new_done = list(own_done)
         for u in range(nv):
             if d_yn[u] is None:
                 continue
@@ -359,10 +406,13 @@ def decoder_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[torch.Te
             if nv == 2:
                 v = 1 - u
                 if has_norm_y:
-                    new[v] = ln_bwd(pk, bp + "norm_y", d_yn[u], y, ymean, yrstd, dres=new[v])
+                    sink = stream_sink(v, k - 1) if fold_ln else None
+                    new[v] = ln_bwd(pk, bp + "norm_y", d_yn[u], y, ymean, yrstd, dres=new[v], colsum=sink)
+                    new_done[v] = sink is not None
                     pk.notify_done(bp)
                 else:
                     new[v] = d_yn[u] if new[v] is None else new[v] + d_yn[u]
+                    new_done[v] = False
             else:
                 dy = ln_bwd(pk, bp + "norm_y", d_yn[u], y, ymean, yrstd) if has_norm_y else d_yn[u]
                 parts = dy.view(B, nv - 1, N, -1)
@@ -370,13 +420,14 @@ def decoder_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[torch.Te
                 for j, v in enumerate(others):
                     g = parts[:, j].reshape(B * N, -1)
                     new[v] = g.contiguous() if new[v] is None else new[v] + g
-        dxs = new
+                    new_done[v] = False
+        dxs, done = new, new_done
     d_in: List[Optional[torch.Tensor]] = [None] * nv
     for v in range(nv):
         if dxs[v] is None:
             continue
         if has_proj_embed:
-            d_in[v] = linear_bwd(pk, p + "proj_embed", dxs[v], saved["in"][v], need_dx=need_input_grad)
+            d_in[v] = linear_bwd(pk, p + "proj_embed", dxs[v], saved["in"][v], need_dx=need_input_grad, bias_done=done[v])
         else:
             d_in[v] = dxs[v]
     return d_in

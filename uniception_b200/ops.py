@@ -130,8 +130,9 @@ def layernorm_fwd(x, gamma, beta, eps, out_dtype=torch.bfloat16, save_stats=True
     return y.view(x.shape), mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dres=None):
-    """dx (bf16) = LN'(dy) [+ dres]; dgamma/dbeta (fp32 [C]) are accumulated in place."""
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dres=None, dx_colsum=None):
+    """dx (bf16) = LN'(dy) [+ dres]; dgamma/dbeta (fp32 [C]) are accumulated in place; dx_colsum (fp32 [C], optional)
+    += column sums of dx (the bias gradient of the Linear that consumes dx as its output gradient)."""
     _cuda(dy, x, gamma)
     C_ = x.shape[-1]
     x2, dy2 = x.reshape(-1, C_), dy.reshape(-1, C_)
@@ -140,7 +141,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dres=None):
         assert dres.dtype == torch.bfloat16 and dres.is_contiguous()
     dx = torch.empty_like(x2, dtype=torch.bfloat16)
     p = L.LayerNormBwdParams(_ptr(dy2), _ptr(x2), _ptr(dres), _ptr(dx), _ptr(gamma), _ptr(mean), _ptr(rstd),
-                             _ptr(dgamma), _ptr(dbeta), x2.shape[0], C_, _DT[dy2.dtype], _DT[x2.dtype])
+                             _ptr(dgamma), _ptr(dbeta), x2.shape[0], C_, _DT[dy2.dtype], _DT[x2.dtype], _ptr(dx_colsum))
     L.check(L.lib.uc_layernorm_bwd(C.byref(p), _stream()))
     return dx.view(x.shape)
 
