@@ -100,6 +100,8 @@ typedef struct {
   const void* aux_in;         /* [m][ldc] bf16 (UC_EPI_GELU_BWD pre-activation) */
   const int32_t* positions;   /* [m][2] int32 (y,x) per row (UC_EPI_ROPE) */
   const float* rope_table;    /* [P][16][2] fp32 (cos,sin) from uc_rope2d_table */
+  float* c_colsum;            /* optional [n] fp32, accumulated: column sums of the bf16 C this call writes (the bias gradient
+                                 of the Linear whose output gradient C is, e.g. fc1 when C = dgrad(fc2) * GELU'); bf16 C only */
 } uc_gemm_params;
 
 UC_API int uc_gemm(const uc_gemm_params* p, uc_stream_t stream);

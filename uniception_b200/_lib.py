@@ -36,6 +36,7 @@ class GemmParams(C.Structure):
         ("lda", i64), ("ldb", i64), ("ldc", i64),
         ("c_dtype", i32), ("epilogue", i32), ("split_k", i32), ("rope_cols", i32),
         ("bias", vp), ("residual", vp), ("aux_out", vp), ("aux_in", vp), ("positions", vp), ("rope_table", vp),
+        ("c_colsum", vp),
     ]
 
 

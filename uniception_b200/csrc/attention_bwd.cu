@@ -19,13 +19,17 @@
 
 namespace uc {
 
-// Optional cycle trace of CTA (0,0) of the pipelined backward kernel (bring-up aid, tools/trace_attn.py):
-// trace[role][sub-tile][event] = clock64().  Null (the default) costs one predictable branch per event.
+// Optional cycle trace of CTA (0,0) of the pipelined backward kernel (bring-up aid, tools/trace_attn.py; build with
+// -DUC_ATTN_TRACE): trace[role][sub-tile][event] = clock64().
 __device__ long long* g_attn_trace = nullptr;
+#ifdef UC_ATTN_TRACE
 #define UC_TRACE(role, j, ev)                                                                       \
   do {                                                                                              \
     if (trace_on && (j) < 64) g_attn_trace[((role) * 64 + (j)) * 8 + (ev)] = clock64();             \
   } while (0)
+#else
+#define UC_TRACE(role, j, ev) do { } while (0)
+#endif
 
 int make_head_map(CUtensorMap* m, const void* base, int H, int N, int B, long long ld, int box_rows);
 
@@ -429,7 +433,9 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int b = bh / a.H, h = bh % a.H;
   const int num_q_tiles = (a.Nq + 127) / 128;
   const int n_sub = 2 * num_q_tiles;
+#ifdef UC_ATTN_TRACE
   const bool trace_on = g_attn_trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmDQ);

@@ -346,25 +346,33 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(uc_layernorm_bwd_
   }
 }
 
-// Hot-path variant (bf16 x / dy / dres, C % 128 == 0): a BLOCK of C/4 threads walks batches of G rows, thread <-> 4
-// columns.  Only 3 x 4 column partials (dgamma, dbeta, colsum(dx)) persist in registers, so the kernel fits 3+ blocks per
-// SM with G rows x 3 tensors of 8-byte loads in flight per thread; the 2G row sums of a batch are reduced with a
-// 16-shuffle value-halving butterfly per warp and two block barriers.
+// Hot-path variant (bf16 x / dy / dres, C % 128 == 0, C <= 1024).  One 768-thread block per SM holds S = 768 / (C/4)
+// independent TEAMS of C/4 threads; a team walks batches of G rows with thread <-> 4 columns, so only 3 x 4 column
+// partials (dgamma, dbeta, colsum(dx)) persist in registers and G rows x 3 tensors of 8-byte loads are in flight per
+// thread.  The 2G row sums of a batch are reduced with a value-halving shuffle butterfly per warp and two TEAM barriers
+// (bar.sync with a team id).  At the end the teams' column partials are combined in shared memory and leave as ONE
+// red.global.add.v4.f32 per 4 columns per block: same-address L2 atomics serialise (~30 ns each), so 148 of them per
+// column instead of one per (team, column) is the difference between a 2 us and a 25 us tail.
 template <int G>
-__global__ void __launch_bounds__(256) layernorm_bwd_rows_kernel(uc_layernorm_bwd_params p) {
-  __shared__ float part[8][2 * G];
-  __shared__ float tot[2 * G];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int col = threadIdx.x * 4;
+__global__ void __launch_bounds__(768, 1) layernorm_bwd_rows_kernel(uc_layernorm_bwd_params p) {
+  __shared__ float part[4][8][2 * G];
+  __shared__ float tot[4][2 * G];
+  __shared__ __align__(16) float colacc[3][1024];
+  const int team_threads = p.C >> 2;
+  const int team = threadIdx.x / team_threads, tid = threadIdx.x - team * team_threads;
+  const int teams = blockDim.x / team_threads;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = team_threads >> 5;
+  const int col = tid * 4;
   const float inv_c = 1.0f / (float)p.C;
+  for (int i = threadIdx.x; i < 3 * 1024; i += blockDim.x) (&colacc[0][0])[i] = 0.f;
   const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
-  const uint2* xin = static_cast<const uint2*>(p.x) + threadIdx.x;
-  const uint2* dyin = static_cast<const uint2*>(p.dy) + threadIdx.x;
-  const uint2* rin = p.dres ? static_cast<const uint2*>(p.dres) + threadIdx.x : nullptr;
-  uint2* dxout = static_cast<uint2*>(p.dx) + threadIdx.x;
+  const uint2* xin = static_cast<const uint2*>(p.x) + tid;
+  const uint2* dyin = static_cast<const uint2*>(p.dy) + tid;
+  const uint2* rin = p.dres ? static_cast<const uint2*>(p.dres) + tid : nullptr;
+  uint2* dxout = static_cast<uint2*>(p.dx) + tid;
   const int rowq = p.C >> 2;  // uint2 per row
   float dg[4] = {0, 0, 0, 0}, db[4] = {0, 0, 0, 0}, dc[4] = {0, 0, 0, 0};
-  for (int row0 = blockIdx.x * G; row0 < p.rows; row0 += gridDim.x * G) {
+  for (int row0 = (blockIdx.x * teams + team) * G; row0 < p.rows; row0 += gridDim.x * teams * G) {
     uint2 rx[G], rdy[G], rr[G];
     float mean[G], rstd[G];
 #pragma unroll
@@ -397,7 +405,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_rows_kernel(uc_layernorm_bw
       s[g] = a1;
       s[G + g] = a2;
     }
-    // warp reduction of 2G values with value halving: lane l ends with the warp total of value l >> (5 - log2(2G))
+    // warp reduction of 2G values with value halving: lane l ends with the warp total of value l / kRest
 #pragma unroll
     for (int n = G, k = 16; n >= 1; n >>= 1, k >>= 1) {
       const bool up = (lane & k) != 0;
@@ -411,18 +419,18 @@ __global__ void __launch_bounds__(256) layernorm_bwd_rows_kernel(uc_layernorm_bw
     constexpr int kRest = 32 / (2 * G);  // lanes that still hold partial sums of the same value
 #pragma unroll
     for (int k = kRest >> 1; k >= 1; k >>= 1) s[0] += __shfl_xor_sync(0xffffffffu, s[0], k);
-    if ((lane & (kRest - 1)) == 0) part[warp][lane / kRest] = s[0];
-    __syncthreads();
-    if (threadIdx.x < 2 * G) {
+    if ((lane & (kRest - 1)) == 0) part[team][warp][lane / kRest] = s[0];
+    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(team_threads) : "memory");
+    if (tid < 2 * G) {
       float t = 0.f;
-      for (int w = 0; w < nwarps; ++w) t += part[w][threadIdx.x];
-      tot[threadIdx.x] = t * inv_c;
+      for (int w = 0; w < nwarps; ++w) t += part[team][w][tid];
+      tot[team][tid] = t * inv_c;
     }
-    __syncthreads();
+    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(team_threads) : "memory");
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       if (row0 + g >= p.rows) break;
-      const float s1 = tot[g], s2 = tot[G + g];
+      const float s1 = tot[team][g], s2 = tot[team][G + g];
       const float x4[4] = {bf16_lo(rx[g].x), bf16_hi(rx[g].x), bf16_lo(rx[g].y), bf16_hi(rx[g].y)};
       const float d4[4] = {bf16_lo(rdy[g].x), bf16_hi(rdy[g].x), bf16_lo(rdy[g].y), bf16_hi(rdy[g].y)};
       const float r4[4] = {bf16_lo(rr[g].x), bf16_hi(rr[g].x), bf16_lo(rr[g].y), bf16_hi(rr[g].y)};
@@ -442,16 +450,25 @@ __global__ void __launch_bounds__(256) layernorm_bwd_rows_kernel(uc_layernorm_bw
       dxout[(int64_t)(row0 + g) * rowq] = w;
     }
   }
-  if (p.dgamma) {
+  // combine the teams' column partials in shared memory, then one vector reduction per 4 columns per block
+  __syncthreads();  // colacc zero-initialised
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      atomicAdd(p.dgamma + col + j, dg[j]);
-      atomicAdd(p.dbeta + col + j, db[j]);
-    }
+  for (int j = 0; j < 4; ++j) {
+    atomicAdd(&colacc[0][col + j], dg[j]);
+    atomicAdd(&colacc[1][col + j], db[j]);
+    atomicAdd(&colacc[2][col + j], dc[j]);
   }
-  if (p.dx_colsum) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) atomicAdd(p.dx_colsum + col + j, dc[j]);
+  __syncthreads();
+  if (team == 0) {
+    if (p.dgamma) {
+      const float4 a = *reinterpret_cast<const float4*>(&colacc[0][col]), b = *reinterpret_cast<const float4*>(&colacc[1][col]);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.dgamma + col), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.dbeta + col), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+    }
+    if (p.dx_colsum) {
+      const float4 c = *reinterpret_cast<const float4*>(&colacc[2][col]);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.dx_colsum + col), "f"(c.x), "f"(c.y), "f"(c.z), "f"(c.w) : "memory");
+    }
   }
 }
 
@@ -688,21 +705,16 @@ extern "C" int uc_layernorm_bwd(const uc_layernorm_bwd_params* p, uc_stream_t st
   UC_REQUIRE((p->dgamma == nullptr) == (p->dbeta == nullptr), UC_ERR_BAD_SHAPE, "uc_layernorm_bwd: dgamma/dbeta must both be set");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (p->x_dtype == UC_DTYPE_BF16 && p->dy_dtype == UC_DTYPE_BF16 && p->C % 128 == 0 && p->C <= 1024 &&
-      ((uintptr_t)p->x % 8 == 0) && ((uintptr_t)p->dy % 8 == 0) && ((uintptr_t)p->dx % 8 == 0) && ((uintptr_t)p->dres % 8 == 0)) {
-    constexpr int G = 4;
-    static const int g_env = [] { const char* e = getenv("UC_LN_BWD_G"); return e ? atoi(e) : 4; }();
-    const int threads = p->C / 4;
-    const int per_sm = 768 / threads >= 1 ? (768 / threads) : 1;  // ~24 warps per SM
-    int grid = sm_count() * per_sm;
-    if (g_env == 8) {
-      const int need = (p->rows + 7) / 8;
-      if (grid > need) grid = need;
-      layernorm_bwd_rows_kernel<8><<<grid, threads, 0, stream>>>(*p);
-    } else {
-      const int need = (p->rows + G - 1) / G;
-      if (grid > need) grid = need;
-      layernorm_bwd_rows_kernel<G><<<grid, threads, 0, stream>>>(*p);
-    }
+      ((uintptr_t)p->x % 8 == 0) && ((uintptr_t)p->dy % 8 == 0) && ((uintptr_t)p->dx % 8 == 0) && ((uintptr_t)p->dres % 8 == 0) &&
+      ((uintptr_t)p->dgamma % 16 == 0) && ((uintptr_t)p->dbeta % 16 == 0) && ((uintptr_t)p->dx_colsum % 16 == 0)) {
+    // one block per SM: 768 threads = 3 teams (C = 1024) / 4 teams (C = 768) / ... of C/4 threads
+    const int team_threads = p->C / 4;
+    int teams = 768 / team_threads;
+    if (teams > 4) teams = 4;
+    int grid = sm_count();
+    const int need = (p->rows + 4 * teams - 1) / (4 * teams);
+    if (grid > need) grid = need;
+    layernorm_bwd_rows_kernel<4><<<grid, teams * team_threads, 0, stream>>>(*p);
     return check_launch("uc_layernorm_bwd");
   }
   UC_REQUIRE(p->dx_colsum == nullptr, UC_ERR_UNSUPPORTED, "uc_layernorm_bwd: dx_colsum needs bf16 inputs and C %% 128 == 0, C <= 1024");

@@ -34,6 +34,7 @@ struct GemmArgs {
   const __nv_bfloat16* aux_in;
   const int* positions;
   const float* rope_table;
+  float* colsum;  // optional [n]: += column sums of the bf16 C tile (pair kernel epilogue)
 };
 
 template <int BN>
@@ -71,11 +72,12 @@ __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* p, const float (
 }
 
 // Fused epilogue math on one 32-column chunk of one accumulator row (fp32 bits in r[]):
-// bias -> 2-D RoPE -> GELU (pre-activation returned in pre[]) / GELU' -> residual.  No stores.
+// bias -> 2-D RoPE -> GELU (bf16 pre-activation returned packed in prep[]) / GELU' -> residual.  No stores.
+template <int MASK = -1>
 __device__ __forceinline__ void epilogue_math(const GemmArgs& g, int row, int n, int pos_y, int pos_x, bool row_ok,
-                                              const uint32_t (&r)[32], float (&v)[32], float (&pre)[32],
+                                              const uint32_t (&r)[32], float (&v)[32], uint32_t (&prep)[16] /* packed bf16 pre-activation */,
                                               const float* hin = nullptr /* staged aux_in / residual values, or load */) {
-  const int epi = g.epilogue;
+  const int epi = g.epilogue & MASK;  // MASK: flags this instantiation can see (everything else is compiled out)
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
   if (epi & UC_EPI_BIAS) {
@@ -106,10 +108,13 @@ __device__ __forceinline__ void epilogue_math(const GemmArgs& g, int row, int n,
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
   if (epi & UC_EPI_GELU) {
+    // the pre-activation is rounded to bf16 by the pack that its store needs anyway (F2FP, not the XU-pipe F2F)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      pre[j] = round_bf16(v[j]);
-      v[j] = gelu_erf(pre[j]);
+    for (int j = 0; j < 16; ++j) {
+      const uint32_t pk = pack_bf16(v[2 * j], v[2 * j + 1]);
+      prep[j] = pk;
+      v[2 * j] = gelu_erf(bf16_lo(pk));
+      v[2 * j + 1] = gelu_erf(bf16_hi(pk));
     }
   }
   if ((epi & UC_EPI_RELU_BWD) && row_ok) {
@@ -149,10 +154,15 @@ __device__ __forceinline__ void epilogue_math(const GemmArgs& g, int row, int n,
 
 // epilogue math + direct row-per-thread global stores (single-CTA kernels)
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int row, int n, int pos_y, int pos_x, const uint32_t (&r)[32]) {
-  float v[32], pre[32];
-  epilogue_math(g, row, n, pos_y, pos_x, true, r, v, pre);
+  float v[32];
+  uint32_t prep[16];
+  epilogue_math(g, row, n, pos_y, pos_x, true, r, v, prep);
   const size_t off = (size_t)row * g.ldc + n;
-  if (g.epilogue & UC_EPI_GELU) store_row32_bf16(g.aux_out + off, pre);
+  if (g.epilogue & UC_EPI_GELU) {
+    uint4* q = reinterpret_cast<uint4*>(g.aux_out + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = make_uint4(prep[4 * i], prep[4 * i + 1], prep[4 * i + 2], prep[4 * i + 3]);
+  }
   if (g.c_f32) {
     float* cp = reinterpret_cast<float*>(g.c) + off;
     if (g.epilogue & UC_EPI_ATOMIC) {
@@ -354,6 +364,9 @@ constexpr uint32_t G2_STG_WARP = 2 * 4096;  // per epilogue warp: two 32-row x 1
 constexpr uint32_t G2_STG_BYTES = NUM_EPI_WARPS * G2_STG_WARP;
 constexpr uint32_t G2_SMEM = G2_STAGES * G2_STAGE_BYTES + G2_STG_BYTES + 1024 + 256;
 
+// MASK / F32: epilogue flags and output type this instantiation handles.  One generic kernel with run-time flags is
+// 12 K SASS instructions (~200 KB): the epilogue warps then stall on instruction fetch (ncu: 1.0 "no_instruction" per issue).
+template <int MASK, bool F32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, const GemmArgs g) {
@@ -490,10 +503,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // the input tile of unit u lands in buf[u] (TMA load, prefetched one unit ahead) and is overwritten IN PLACE by the
     // unit's output (each lane has read its own 16-byte chunks before it writes them)
     const uint32_t buf0 = stg, buf1 = stg + 4096;
-    const bool f32 = g.c_f32 != 0;
-    const bool atomic = (g.epilogue & UC_EPI_ATOMIC) != 0;
-    const bool has_aux = (g.epilogue & UC_EPI_GELU) != 0;
-    const bool has_in = (g.epilogue & (UC_EPI_GELU_BWD | UC_EPI_RELU_BWD | UC_EPI_RESIDUAL)) != 0;  // aux_in / residual tile, via TMA
+    constexpr bool f32 = F32;
+    const int epi_flags = g.epilogue & MASK;
+    const bool atomic = (epi_flags & UC_EPI_ATOMIC) != 0;
+    const bool has_aux = (epi_flags & UC_EPI_GELU) != 0;
+    const bool has_in = (epi_flags & (UC_EPI_GELU_BWD | UC_EPI_RELU_BWD | UC_EPI_RESIDUAL)) != 0;  // aux_in / residual tile, via TMA
     uint32_t ph_a = 0, ph_b = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -537,7 +551,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       int pos_y = 0, pos_x = 0;
-      if ((g.epilogue & UC_EPI_ROPE) && row_ok) {
+      if ((epi_flags & UC_EPI_ROPE) && row_ok) {
         pos_y = g.positions[2 * row];
         pos_x = g.positions[2 * row + 1];
       }
@@ -559,8 +573,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tmem_ld32(tbase + u * 32, r);
           tmem_ld_wait();
           const int n = nw + u * 32;
-          float v[32], pre[32];
-          epilogue_math(g, row, n, pos_y, pos_x, row_ok, r, v, pre);
+          float v[32];
+          uint32_t prep[16];
+          epilogue_math<MASK>(g, row, n, pos_y, pos_x, row_ok, r, v, prep);
           uint32_t w[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j]);
@@ -582,7 +597,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (c + 1 < 4) tmem_ld32(tbase + 32 * (c + 1), rn);
           else release_acc();
           const int n = nw + c * 32;
-          float v[32], pre[32], h[32];
+          float v[32], h[32];
+          uint32_t prep[16];
           if (has_in) {
             if (hf == 0) {
               if (u == 0) {
@@ -607,9 +623,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               h[8 * j + 0] = bf16_lo(a0); h[8 * j + 1] = bf16_hi(a0); h[8 * j + 2] = bf16_lo(a1); h[8 * j + 3] = bf16_hi(a1);
               h[8 * j + 4] = bf16_lo(a2); h[8 * j + 5] = bf16_hi(a2); h[8 * j + 6] = bf16_lo(a3); h[8 * j + 7] = bf16_hi(a3);
             }
-            epilogue_math(g, row, n, pos_y, pos_x, row_ok, rc, v, pre, h);
+            epilogue_math<MASK>(g, row, n, pos_y, pos_x, row_ok, rc, v, prep, h);
           } else {
-            epilogue_math(g, row, n, pos_y, pos_x, row_ok, rc, v, pre);
+            epilogue_math<MASK>(g, row, n, pos_y, pos_x, row_ok, rc, v, prep);
           }
           const uint32_t outb = (has_aux || u == 0) ? buf0 : buf1;
           if (hf == 0 && !has_in) {  // staging tile free once the bulk store that last read it has completed
@@ -627,9 +643,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                          "r"(pack_bf16(v[8 * j + 6], v[8 * j + 7]))
                          : "memory");
             if (has_aux)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf1 + so), "r"(pack_bf16(pre[8 * j], pre[8 * j + 1])),
-                           "r"(pack_bf16(pre[8 * j + 2], pre[8 * j + 3])), "r"(pack_bf16(pre[8 * j + 4], pre[8 * j + 5])),
-                           "r"(pack_bf16(pre[8 * j + 6], pre[8 * j + 7]))
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf1 + so), "r"(prep[4 * j]), "r"(prep[4 * j + 1]),
+                           "r"(prep[4 * j + 2]), "r"(prep[4 * j + 3])
                            : "memory");
           }
           if (hf == 1) {
@@ -639,6 +654,25 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               if (has_aux) tma_store_2d(&tmAux, buf1, n - 32, row0);
               tma_store_2d(&tmC, outb, n - 32, row0);
               tma_store_commit();
+            }
+            if (g.colsum) {
+              // column sums of the staged [32 rows x 64 cols] bf16 tile: lane <-> columns 2*lane, 2*lane+1 (conflict-free:
+              // the 128B swizzle spreads the 8 16-byte chunks of a row over all banks)
+              float s0 = 0.f, s1 = 0.f;
+              const int rows_valid = min(32, g.m - row0);
+#pragma unroll 8
+              for (int rr = 0; rr < rows_valid; ++rr) {
+                uint32_t w2;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w2)
+                             : "r"(outb + rr * 128 + ((uint32_t((lane >> 2) ^ (rr & 7))) << 4) + (lane & 3) * 4));
+                s0 += bf16_lo(w2);
+                s1 += bf16_hi(w2);
+              }
+              const int nc = n - 32 + 2 * lane;
+              if (nc < g.n) {
+                atomicAdd(g.colsum + nc, s0);
+                atomicAdd(g.colsum + nc + 1, s1);
+              }
             }
           }
         }
@@ -657,16 +691,33 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
-int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux, const GemmArgs& g,
-            int grid, cudaStream_t stream) {
+template <int MASK, bool F32>
+int launch2_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux, const GemmArgs& g,
+                 int grid, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<MASK, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
     UC_REQUIRE(e == cudaSuccess, UC_ERR_CUDA, "uc_gemm: cudaFuncSetAttribute(gemm2) failed: %s", cudaGetErrorString(e));
     configured = true;
   }
-  gemm2_kernel<<<grid, GEMM_THREADS, G2_SMEM, stream>>>(tmA, tmB, tmC, tmAux, g);
+  gemm2_kernel<MASK, F32><<<grid, GEMM_THREADS, G2_SMEM, stream>>>(tmA, tmB, tmC, tmAux, g);
   return check_launch("uc_gemm(cta_pair)");
+}
+
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux, const GemmArgs& g,
+            int grid, cudaStream_t stream) {
+  constexpr int kGeneric = UC_EPI_BIAS | UC_EPI_ROPE | UC_EPI_RESIDUAL | UC_EPI_RELU | UC_EPI_RELU_BWD;
+  const int e = g.epilogue;
+  if (g.c_f32) {
+    if (e == UC_EPI_ATOMIC) return launch2_inst<UC_EPI_ATOMIC, true>(tmA, tmB, tmC, tmAux, g, grid, stream);
+    if ((e & ~kGeneric) == 0) return launch2_inst<kGeneric, true>(tmA, tmB, tmC, tmAux, g, grid, stream);
+    return launch2_inst<-1, true>(tmA, tmB, tmC, tmAux, g, grid, stream);
+  }
+  if ((e & ~(UC_EPI_BIAS | UC_EPI_GELU)) == 0 && (e & UC_EPI_GELU))
+    return launch2_inst<UC_EPI_BIAS | UC_EPI_GELU, false>(tmA, tmB, tmC, tmAux, g, grid, stream);
+  if (e == UC_EPI_GELU_BWD) return launch2_inst<UC_EPI_GELU_BWD, false>(tmA, tmB, tmC, tmAux, g, grid, stream);
+  if ((e & ~kGeneric) == 0) return launch2_inst<kGeneric, false>(tmA, tmB, tmC, tmAux, g, grid, stream);
+  return launch2_inst<-1, false>(tmA, tmB, tmC, tmAux, g, grid, stream);
 }
 
 template <int BN>
@@ -711,6 +762,7 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
   UC_REQUIRE(!(epi & UC_EPI_ROPE) || (p->positions && p->rope_table && p->rope_cols % 64 == 0), UC_ERR_BAD_SHAPE,
              "uc_gemm: UC_EPI_ROPE needs positions, rope_table and rope_cols %% 64 == 0");
   UC_REQUIRE(!(epi & UC_EPI_ATOMIC) || p->c_dtype == UC_DTYPE_F32, UC_ERR_BAD_DTYPE, "uc_gemm: atomic epilogue needs fp32 C");
+  UC_REQUIRE(!p->c_colsum || (p->c_dtype == UC_DTYPE_BF16 && p->n % 8 == 0), UC_ERR_BAD_DTYPE, "uc_gemm: c_colsum needs bf16 C");
 
   const int num_kb = (p->k + BK - 1) / BK;
   const int sms = sm_count();
@@ -737,6 +789,9 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
       const long long waves = (tiles + slots - 1) / slots;
       // split-K (wgrad) fills the machine by itself, so only the per-tile efficiency matters there
       double eff = (atomic ? 1.0 : double(tiles) / double(waves * slots)) * rate[i];
+      // the GELU / GELU' epilogues are issue-bound: only the pair kernel's staged, software-pipelined, specialised
+      // epilogue keeps up with the MMA pipe (decoder fc1 at K=768: 86 us single-CTA vs the pair kernel)
+      if (is_pair && (epi & (UC_EPI_GELU | UC_EPI_GELU_BWD))) eff *= 1.5;
       if (is_pair && pair_env == 1) eff = 10.0;
       if (eff > best) { best = eff; bn = cand[i]; pair = is_pair; }
     }
@@ -792,6 +847,7 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
   g.aux_out = static_cast<__nv_bfloat16*>(p->aux_out);
   g.aux_in = static_cast<const __nv_bfloat16*>(p->aux_in);
   g.positions = p->positions; g.rope_table = p->rope_table;
+  g.colsum = (pair && p->c_dtype == UC_DTYPE_BF16) ? p->c_colsum : nullptr;
 
   const long long total = (long long)num_m * num_n * split_k;
   if (pair) {
@@ -815,7 +871,9 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
     return launch2(tmA, tmB, tmC, tmAux, g, 2 * clusters, stream);
   }
   const int grid = (int)(total < sms ? total : sms);
-  if (bn == 256) return launch<256>(tmA, tmB, g, grid, stream);
-  if (bn == 128) return launch<128>(tmA, tmB, g, grid, stream);
-  return launch<64>(tmA, tmB, g, grid, stream);
+  int r = bn == 256 ? launch<256>(tmA, tmB, g, grid, stream) : bn == 128 ? launch<128>(tmA, tmB, g, grid, stream)
+                                                                         : launch<64>(tmA, tmB, g, grid, stream);
+  if (r == 0 && p->c_colsum)  // single-CTA kernels have no staged tile: one extra pass over C
+    r = uc_colsum(p->c, UC_DTYPE_BF16, p->ldc, p->m, p->n, p->c_colsum, stream_);
+  return r;
 }

@@ -84,10 +84,11 @@ def linear_fwd(pk: ParamPack, name: str, x, *, residual=None, rope: Optional[Rop
 
 
 def linear_bwd(pk: ParamPack, name: str, dy, x_in, *, need_dx=True, gelu_pre=None, w16=None, wgrad=None, bgrad=None,
-               train_w=None, bias_done=False):
+               train_w=None, bias_done=False, dx_sink=None):
     """dy [rows, out] bf16, x_in [rows, in] bf16.  Accumulates dW, db; returns dx (bf16) or None.
     gelu_pre: dx is additionally multiplied by gelu'(gelu_pre) (the producer of x_in was GELU).
-    bias_done: db = colsum(dy) was already accumulated by the kernel that produced dy (uc_layernorm_bwd's dx_colsum)."""
+    bias_done: db = colsum(dy) was already accumulated by the kernel that produced dy (uc_layernorm_bwd's dx_colsum or
+    uc_gemm's c_colsum); dx_sink: fp32 [in] buffer that receives colsum(dx) from this call's dgrad GEMM epilogue."""
     w = pk.w16(name + ".weight") if w16 is None else w16
     if train_w is None:
         train_w = pk.requires_grad(name + ".weight")
@@ -101,9 +102,9 @@ def linear_bwd(pk: ParamPack, name: str, dy, x_in, *, need_dx=True, gelu_pre=Non
         return None
     dx = _empty(dy.shape[0], w.shape[1], dy)
     if gelu_pre is not None:
-        ops.gemm(dy, w, dx, b_layout=1, gelu_bwd=True, aux_in=gelu_pre)
+        ops.gemm(dy, w, dx, b_layout=1, gelu_bwd=True, aux_in=gelu_pre, c_colsum=dx_sink)
     else:
-        ops.gemm(dy, w, dx, b_layout=1)
+        ops.gemm(dy, w, dx, b_layout=1, c_colsum=dx_sink)
     return dx
 
 
@@ -169,8 +170,9 @@ def mlp_fwd(pk, p, x, norm: str, saved: list):
 
 def mlp_bwd(pk, p, dx2, norm: str, saved, bias_done=False, out_sink=None):
     x, mean, rstd, h, pre, act = saved
-    d_pre = linear_bwd(pk, p + "mlp.fc2", dx2, act, gelu_pre=pre, bias_done=bias_done)
-    d_h = linear_bwd(pk, p + "mlp.fc1", d_pre, h)
+    fc1_sink = pk.grad(p + "mlp.fc1.bias") if pk.requires_grad(p + "mlp.fc1.weight") else None
+    d_pre = linear_bwd(pk, p + "mlp.fc2", dx2, act, gelu_pre=pre, bias_done=bias_done, dx_sink=fc1_sink)  # fc1.bias.grad = colsum(d_pre)
+    d_h = linear_bwd(pk, p + "mlp.fc1", d_pre, h, bias_done=fc1_sink is not None)
     return ln_bwd(pk, p + norm, d_h, x, mean, rstd, dres=dx2, colsum=out_sink)
 
 

@@ -35,8 +35,9 @@ def _cuda(*ts):
 
 def gemm(a, b, out, *, a_layout=0, b_layout=0, bias=None, residual=None, aux_out=None, aux_in=None,
          positions=None, rope_table=None, rope_cols=0, gelu=False, gelu_bwd=False, atomic=False, split_k=0,
-         relu=False, relu_bwd=False):
+         relu=False, relu_bwd=False, c_colsum=None):
     """out[m,n] = epilogue(sum_k A(m,k) B(n,k)); see include/uc_b200.h (uc_gemm).
+    c_colsum (fp32 [n], optional) += column sums of the bf16 `out` written by this call.
     a: [m,k] (a_layout 0) or [k,m] (1); b: [n,k] (0) or [k,n] (1); bf16, inner dim contiguous."""
     _cuda(a, b, out)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16, "uc_gemm operands are bf16"
@@ -72,7 +73,7 @@ def gemm(a, b, out, *, a_layout=0, b_layout=0, bias=None, residual=None, aux_out
     p = L.GemmParams(
         _ptr(a), _ptr(b), _ptr(out), m, n, k, a_layout, b_layout, a.stride(0), b.stride(0), out.stride(0),
         _DT[out.dtype], epi, split_k, rope_cols,
-        _ptr(bias), _ptr(residual), _ptr(aux_out), _ptr(aux_in), _ptr(positions), _ptr(rope_table),
+        _ptr(bias), _ptr(residual), _ptr(aux_out), _ptr(aux_in), _ptr(positions), _ptr(rope_table), _ptr(c_colsum),
     )
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
