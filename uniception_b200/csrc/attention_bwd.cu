@@ -1,19 +1,21 @@
 // Fused attention backward (uc_attn_bwd): dQ, dK, dV of softmax(q k^T * scale) v with recomputation,
 // head_dim 64.  Three kernels:
 //   1. attn_bwd_delta  : delta[q] = sum_d dO[q,d] * O[q,d]                       (memory-bound)
-//   2. attn_bwd_main   : one CTA per (128-key tile, batch*head), loop over 128-query tiles, all five
+//   2. attn_bwd_pipe   : one CTA per (128-key tile, batch*head), loop over 64-query SUB-TILES, all five
 //                        GEMMs on tcgen05, transposed formulation so that thread == key row:
-//        S^T  = K  Q_i^T     (SS)      dP^T = V dO_i^T     (SS)
-//        P^T  = exp2(S^T c - lse_i),   dS^T = P^T o (dP^T - delta_i)            (registers)
-//        dV  += P^T  dO_i    (TS: P^T  from TMEM, dO_i MN-major from the same smem tile)
-//        dK  += dS^T Q_i     (TS: dS^T from TMEM, Q_i  MN-major)
-//        dQ_i = dS   K       (SS: dS written to smem as an MN-major A tile, K MN-major) -> TMEM -> smem ->
-//                            cp.reduce.async.bulk.tensor (TMA add-reduction into the fp32 dq accumulator)
+//        S^T  = K  Q_j^T     (SS)      dP^T = V dO_j^T     (SS)       both double-buffered in TMEM
+//        P^T  = exp2(S^T c - lse_j),   dS^T = P^T o (dP^T - delta_j)            (registers)
+//        dV  += P^T  dO_j    (TS: P^T  from TMEM, dO_j MN-major from the same smem tile)
+//        dK  += dS^T Q_j     (TS: dS^T from TMEM, Q_j  MN-major; or SS from the dS smem tile)
+//        dQ_i = dS   K       (SS, once per 128 queries: dS written to smem as an MN-major A tile, K MN-major) -> TMEM ->
+//                            smem -> cp.reduce.async.bulk.tensor (TMA add-reduction into the fp32 dq accumulator)
 //   3. attn_bwd_finish : dq = bf16(scale * dq_acc) with optional inverse 2-D RoPE  (memory-bound)
 // dK gets `scale` and the optional inverse RoPE in the main kernel's epilogue.
-//   warp 0: TMA producer | warp 1: MMA issuer | warps 2..9: softmax/dS (two threads per key row, 64 query
-//   columns each) | warps 10..13: dQ drain (TMEM -> swizzled smem -> TMA reduce-add)
-// TMEM columns: S^T/P^T [0,128) | dP^T/dS^T [128,256) | dV [256,320) | dK [320,384) | dQ [384,448).
+//   warp 0: TMA producer | warp 1: MMA issuer | warps 2..9: softmax/dS (two threads per key row, 32 query
+//   columns each per sub-tile) | warps 10..13: dQ drain (TMEM -> swizzled smem -> TMA reduce-add)
+// TMEM columns: S^T/P^T and dP^T/dS^T x 2 buffers [0,256) | dV [256,320) | dK [320,384) | dQ [384,448).
+// Measured (profiles/r01f_*): a 128x64x16 MMA costs ~64 clk whatever its mode (A-operand fetch bound), so the five
+// GEMMs of a 128x128 tile pair cost >= 40 x 64 = 2560 clk; the serial predecessor of this kernel took 5800, this one 3600.
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -37,12 +39,7 @@ namespace {
 
 constexpr int BW_THREADS = 448;  // TMA, MMA, 8 softmax/dS warps (two threads per key row), 4 dQ-drain warps
 constexpr uint32_t BW_TILE = 128 * 64 * 2;  // 16 KB
-// smem: K, V, 2 x (Q, dO), dS (32 KB), 2 x (lse2, delta) floats, barriers
-constexpr uint32_t BW_OFF_K = 0, BW_OFF_V = BW_TILE, BW_OFF_QDO = 2 * BW_TILE, BW_OFF_DS = 6 * BW_TILE,
-                   BW_OFF_DQ = 8 * BW_TILE /* fp32 [2 boxes][128 q][32 d], 128B-swizzled, TMA-reduce source */,
-                   BW_OFF_STATS = 10 * BW_TILE, BW_OFF_BAR = 10 * BW_TILE + 2048;
-constexpr uint32_t BW_SMEM = BW_OFF_BAR + 256 + 1024;
-constexpr uint32_t BT_SP = 0, BT_DP = 128, BT_DV = 256, BT_DK = 320, BT_DQ = 384, BT_COLS = 512;
+constexpr uint32_t BT_DV = 256, BT_DK = 320, BT_DQ = 384, BT_COLS = 512;  // accumulators; S^T / dP^T buffers: pt_sp / pt_dp
 
 struct AttnBwdArgs {
   const float* lse;
@@ -69,6 +66,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // delta[b][h][q] = sum_d dO * O ; 8 lanes per (token, head), 8 elements per lane
 __global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, float* __restrict__ delta,
                                       int B, int H, int N, long long ldo, long long lddo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)B * N * H * 8;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int sub = idx & 7;
@@ -94,6 +93,8 @@ __global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ o, const
 __global__ void attn_bwd_finish_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, long long rows, int H, long long lddq,
                                        float scale, const int* __restrict__ pos, const float* __restrict__ table) {
   // each thread: one 32-wide half-head: 16 (u,v) pairs
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = rows * H * 2;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int half = idx & 1;
@@ -124,271 +125,6 @@ __global__ void attn_bwd_finish_kernel(const float* __restrict__ acc, __nv_bfloa
       t.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]); t.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
       dst[i] = t;
     }
-  }
-}
-
-__global__ void __launch_bounds__(BW_THREADS, 1)
-attn_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-                     const __grid_constant__ CUtensorMap tmDQ, const AttnBwdArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t sK = smem_base + BW_OFF_K, sV = smem_base + BW_OFF_V, sDS = smem_base + BW_OFF_DS;
-  auto sQ = [&](int st) { return smem_base + BW_OFF_QDO + st * 2 * BW_TILE; };
-  auto sdO = [&](int st) { return smem_base + BW_OFF_QDO + st * 2 * BW_TILE + BW_TILE; };
-  float* stats = reinterpret_cast<float*>(smem_gen + BW_OFF_STATS);  // [2 stages][2][128]
-  const uint32_t bar = smem_base + BW_OFF_BAR;
-  const uint32_t kv_full = bar;
-  auto qdo_full = [&](int st) { return bar + 8u * (1 + st); };
-  auto qdo_empty = [&](int st) { return bar + 8u * (3 + st); };
-  const uint32_t sdp_full = bar + 8u * 5, ds_ready = bar + 8u * 6, dq_full = bar + 8u * 7, dq_free = bar + 8u * 8,
-                 fin_full = bar + 8u * 9, tmem_slot = bar + 8u * 10;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kv0 = blockIdx.x * 128;
-  const int bh = blockIdx.y;
-  const int b = bh / a.H, h = bh % a.H;
-  const int num_q_tiles = (a.Nq + 127) / 128;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmDQ);
-    mbar_init(kv_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(qdo_full(s), 1); mbar_init(qdo_empty(s), 1); }
-    mbar_init(sdp_full, 1);
-    mbar_init(ds_ready, 8);
-    mbar_init(dq_full, 1);
-    mbar_init(dq_free, 4);
-    mbar_init(fin_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, BT_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-  if (warp == 0) {
-    // whole warp loops (uniform control flow); one elected lane issues the TMA copies
-    if (elect_one()) {
-      mbar_arrive_expect_tx(kv_full, 2 * BW_TILE);
-      tma_load_3d(sK, &tmK, kv_full, h * 64, kv0, b);
-      tma_load_3d(sV, &tmV, kv_full, h * 64, kv0, b);
-    }
-    __syncwarp();
-    for (int i = 0; i < num_q_tiles; ++i) {
-      const int st = i & 1;
-      mbar_wait(qdo_empty(st), ((i >> 1) & 1) ^ 1u);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(qdo_full(st), 2 * BW_TILE);
-        tma_load_3d(sQ(st), &tmQ, qdo_full(st), h * 64, i * 128, b);
-        tma_load_3d(sdO(st), &tmdO, qdo_full(st), h * 64, i * 128, b);
-      }
-      __syncwarp();
-    }
-  } else if (warp == 1) {
-    // whole warp loops; operands stay in uniform registers; one elected lane issues tcgen05.mma / commit
-    const uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);   // K-major x K-major
-    const uint32_t id_ts = umma_idesc_bf16(128, 64, 0, 1);   // A in TMEM, B MN-major
-    const uint32_t id_dq = umma_idesc_bf16(128, 64, 1, 1);   // A MN-major (dS in smem), B MN-major
-    mbar_wait(kv_full, 0);
-    const uint64_t kd = umma_desc_kmajor(sK), vd = umma_desc_kmajor(sV);
-    const uint64_t ds_mn = umma_desc_mnmajor(sDS, 16384), k_mn = umma_desc_mnmajor(sK, 8192);
-    for (int i = 0; i < num_q_tiles; ++i) {
-      const int st = i & 1;
-      mbar_wait(qdo_full(st), (i >> 1) & 1);
-      tc_fence_after();
-      const uint64_t qd = umma_desc_kmajor(sQ(st)), dod = umma_desc_kmajor(sdO(st));
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          umma_ss(tmem_base + BT_SP, kd + uint64_t(k * 2), qd + uint64_t(k * 2), id_s, k > 0);
-          umma_ss(tmem_base + BT_DP, vd + uint64_t(k * 2), dod + uint64_t(k * 2), id_s, k > 0);
-        }
-        umma_commit(sdp_full);
-      }
-      __syncwarp();
-      mbar_wait(ds_ready, i & 1);
-      if (i > 0) mbar_wait(dq_free, (i - 1) & 1);
-      tc_fence_after();
-      const uint64_t do_mn = umma_desc_mnmajor(sdO(st), 8192), q_mn = umma_desc_mnmajor(sQ(st), 8192);
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          umma_ts(tmem_base + BT_DV, tmem_base + BT_SP + (k >> 2) * 64 + (k & 3) * 8, do_mn + uint64_t(k * 128), id_ts, (i > 0 || k > 0) ? 1u : 0u);
-          umma_ts(tmem_base + BT_DK, tmem_base + BT_DP + (k >> 2) * 64 + (k & 3) * 8, q_mn + uint64_t(k * 128), id_ts, (i > 0 || k > 0) ? 1u : 0u);
-          umma_ss(tmem_base + BT_DQ, ds_mn + uint64_t(k * 128), k_mn + uint64_t(k * 128), id_dq, k > 0);
-        }
-        umma_commit(dq_full);
-        umma_commit(qdo_empty(st));
-      }
-      __syncwarp();
-    }
-    if (elect_one()) umma_commit(fin_full);
-    __syncwarp();
-  } else if (warp < 10) {
-    // ===================== softmax / dS: two threads per key row =====================
-    const int lane_group = warp & 3;
-    const int half = (warp - 2) >> 2;  // query columns [64*half, 64*half+64) of each tile; head columns [32*half, +32) in the epilogue
-    const uint32_t lane_addr = uint32_t(lane_group * 32) << 16;
-    const int r = lane_group * 32 + lane;   // key row inside the tile
-    const int ct = threadIdx.x - 64;        // 0..255
-    const uint32_t ds_row = sDS + r * 128;
-    auto load_stat = [&](int tile) -> float {  // threads 0..127: lse*log2e, 128..255: delta, of query (tile, ct&127)
-      const int q = tile * 128 + (ct & 127);
-      if (q >= a.Nq) return ct < 128 ? INFINITY : 0.f;
-      const long long off = ((long long)b * a.H + h) * a.Nq + q;
-      return ct < 128 ? a.lse[off] * 1.4426950408889634f : a.delta[off];
-    };
-    stats[ct] = load_stat(0);
-    for (int i = 0; i < num_q_tiles; ++i) {
-      const int st = i & 1;
-      float* lse2 = stats + st * 256;
-      float* dl = lse2 + 128;
-      named_bar_sync(1, 256);  // stats(i) visible; everyone is done with iteration i-1
-      const float next_stat = (i + 1 < num_q_tiles) ? load_stat(i + 1) : 0.f;  // latency hidden behind this tile's work
-      mbar_wait(sdp_full, i & 1);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = 2 * half; c < 2 * half + 2; ++c) {
-        uint32_t s[32], dp[32];
-        tmem_ld32(tmem_base + lane_addr + BT_SP + c * 32, s);
-        tmem_ld32(tmem_base + lane_addr + BT_DP + c * 32, dp);
-        tmem_ld_wait();
-        uint32_t pk[16], dk[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int q = c * 32 + 2 * j;
-          const float p0 = fast_exp2(__uint_as_float(s[2 * j]) * a.scale_log2 - lse2[q]);
-          const float p1 = fast_exp2(__uint_as_float(s[2 * j + 1]) * a.scale_log2 - lse2[q + 1]);
-          const float d0 = p0 * (__uint_as_float(dp[2 * j]) - dl[q]);
-          const float d1 = p1 * (__uint_as_float(dp[2 * j + 1]) - dl[q + 1]);
-          pk[j] = pack_bf16(p0, p1);
-          dk[j] = pack_bf16(d0, d1);
-        }
-        // packed P^T / dS^T overwrite the already-consumed fp32 columns of THIS thread's half only:
-        // queries [0,64) -> columns [0,32), queries [64,128) -> columns [64,96) of the region
-        tmem_st16(tmem_base + lane_addr + BT_SP + (c >> 1) * 64 + (c & 1) * 16, pk);
-        tmem_st16(tmem_base + lane_addr + BT_DP + (c >> 1) * 64 + (c & 1) * 16, dk);
-        // dS -> smem as MN-major A tile: [q-block of 64][key row r][64 q] with the 128B swizzle
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int q8 = c * 4 + g;                  // 16-byte chunk index along q (0..15)
-          const uint32_t addr = ds_row + (q8 >> 3) * 16384 + (((q8 & 7) ^ (r & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(dk[4 * g]), "r"(dk[4 * g + 1]),
-                       "r"(dk[4 * g + 2]), "r"(dk[4 * g + 3])
-                       : "memory");
-        }
-      }
-      tmem_st_wait();
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ds_ready);
-      stats[(st ^ 1) * 256 + ct] = next_stat;
-    }
-    // ---- epilogue: dV, dK (x scale, inverse RoPE) ----
-    mbar_wait(fin_full, 0);
-    tc_fence_after();
-    const int kv = kv0 + r;
-    const bool ok = kv < a.Nk;
-    const long long tok = (long long)b * a.Nk + kv;
-    {
-      const int c = half;
-      uint32_t v[32];
-      tmem_ld32(tmem_base + lane_addr + BT_DV + c * 32, v);
-      tmem_ld_wait();
-      if (ok) {
-        uint4* dst = reinterpret_cast<uint4*>(a.dv + tok * a.lddv + h * 64 + c * 32);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 t;
-          t.x = pack_bf16(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1]));
-          t.y = pack_bf16(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]));
-          t.z = pack_bf16(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
-          t.w = pack_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
-          dst[g] = t;
-        }
-      }
-      __syncwarp();
-    }
-    {
-      const int c = half;
-      uint32_t raw[32];
-      tmem_ld32(tmem_base + lane_addr + BT_DK + c * 32, raw);
-      tmem_ld_wait();
-      if (ok) {
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * a.scale;
-        if (a.k_positions) {
-          const float* tr = a.rope_table + (long long)a.k_positions[2 * tok + c] * 32;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float cs = tr[2 * j], sn = -tr[2 * j + 1];
-            const float u = v[j], w = v[j + 16];
-            v[j] = u * cs - w * sn;
-            v[j + 16] = w * cs + u * sn;
-          }
-        }
-        uint4* dst = reinterpret_cast<uint4*>(a.dk + tok * a.lddk + h * 64 + c * 32);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 t;
-          t.x = pack_bf16(v[8 * g], v[8 * g + 1]); t.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
-          t.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); t.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
-          dst[g] = t;
-        }
-      }
-      __syncwarp();
-    }
-  } else {
-    // ===================== dQ drain: TMEM -> swizzled smem -> TMA reduce-add =====================
-    const int lane_group = warp & 3;
-    const uint32_t lane_addr = uint32_t(lane_group * 32) << 16;
-    const int r = lane_group * 32 + lane;
-    const uint32_t sDQ = smem_base + BW_OFF_DQ;
-    const bool issuer = (warp == 10 && lane == 0);
-    for (int i = 0; i < num_q_tiles; ++i) {
-      mbar_wait(dq_full, i & 1);
-      tc_fence_after();
-      uint32_t v0[32], v1[32];
-      tmem_ld32(tmem_base + lane_addr + BT_DQ, v0);
-      tmem_ld32(tmem_base + lane_addr + BT_DQ + 32, v1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(dq_free);          // TMEM dQ region may be overwritten by the next tile
-      if (issuer) tma_store_wait_read0();            // previous reduction has finished reading the staging tile
-      named_bar_sync(2, 128);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t off = r * 128 + ((j ^ (r & 7)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDQ + off), "r"(v0[4 * j]), "r"(v0[4 * j + 1]),
-                     "r"(v0[4 * j + 2]), "r"(v0[4 * j + 3]) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDQ + 16384 + off), "r"(v1[4 * j]), "r"(v1[4 * j + 1]),
-                     "r"(v1[4 * j + 2]), "r"(v1[4 * j + 3]) : "memory");
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(2, 128);
-      if (issuer) {
-        tma_reduce_add_3d(&tmDQ, sDQ, h * 64, i * 128, b);
-        tma_reduce_add_3d(&tmDQ, sDQ + 16384, h * 64 + 32, i * 128, b);
-        tma_store_commit();
-      }
-    }
-    if (issuer) tma_store_wait0();
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, BT_COLS);
   }
 }
 
@@ -458,6 +194,8 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_launch_dependents();  // after the TMEM allocation (common.cuh: PDL rules)
+  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -731,9 +469,9 @@ extern "C" int uc_attn_bwd(const uc_attn_bwd_params* p, uc_stream_t stream_) {
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    attn_bwd_delta_kernel<<<(int)blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(p->o),
-                                                           static_cast<const __nv_bfloat16*>(p->d_o), p->delta, p->B, p->H, p->Nq,
-                                                           p->ldo, p->ldo);
+    cudaError_t le = launch_pdl(attn_bwd_delta_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(p->o),
+                                static_cast<const __nv_bfloat16*>(p->d_o), p->delta, p->B, p->H, p->Nq, (long long)p->ldo, (long long)p->ldo);
+    UC_REQUIRE(le == cudaSuccess, UC_ERR_CUDA, "uc_attn_bwd(delta): launch failed: %s", cudaGetErrorString(le));
     int r = check_launch("uc_attn_bwd(delta)");
     if (r) return r;
   }
@@ -752,12 +490,6 @@ extern "C" int uc_attn_bwd(const uc_attn_bwd_params* p, uc_stream_t stream_) {
     uint32_t box[3] = {32, 128, 1};
     if ((r = make_tensor_map(&tmDQ, p->dq_acc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return r;
   }
-  static bool configured = false;
-  if (!configured) {
-    e = cudaFuncSetAttribute(attn_bwd_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM);
-    UC_REQUIRE(e == cudaSuccess, UC_ERR_CUDA, "uc_attn_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-    configured = true;
-  }
   AttnBwdArgs a;
   a.lse = p->lse; a.delta = p->delta; a.dq_acc = p->dq_acc;
   a.dk = static_cast<__nv_bfloat16*>(p->dk);
@@ -769,26 +501,28 @@ extern "C" int uc_attn_bwd(const uc_attn_bwd_params* p, uc_stream_t stream_) {
   a.k_positions = p->k_positions;
   a.rope_table = p->rope_table;
   dim3 grid((p->Nk + 127) / 128, p->B * p->H);
-  static int variant = -1;  // bring-up switch: UC_ATTN_BWD=0 serial kernel, 1 pipelined (TS dK), 2 pipelined (SS dK)
-  if (variant < 0) {
-    const char* ev = getenv("UC_ATTN_BWD");
-    variant = ev ? atoi(ev) : 1;
+  static const int dk_ss = [] { const char* ev = getenv("UC_ATTN_BWD_DK_SS"); return ev ? atoi(ev) : 0; }();  // bring-up switch
+  static bool configured = false;
+  if (!configured) {
     e = cudaFuncSetAttribute(attn_bwd_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
     UC_REQUIRE(e == cudaSuccess, UC_ERR_CUDA, "uc_attn_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(attn_bwd_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
     UC_REQUIRE(e == cudaSuccess, UC_ERR_CUDA, "uc_attn_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    configured = true;
   }
-  if (variant == 0) attn_bwd_main_kernel<<<grid, BW_THREADS, BW_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, a);
-  else if (variant == 1) attn_bwd_pipe_kernel<false><<<grid, BW_THREADS, P_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, a);
-  else attn_bwd_pipe_kernel<true><<<grid, BW_THREADS, P_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, a);
+  e = dk_ss ? launch_pdl(attn_bwd_pipe_kernel<true>, grid, dim3(BW_THREADS), P_SMEM, stream, tmQ, tmK, tmV, tmdO, tmDQ, a)
+            : launch_pdl(attn_bwd_pipe_kernel<false>, grid, dim3(BW_THREADS), P_SMEM, stream, tmQ, tmK, tmV, tmdO, tmDQ, a);
+  UC_REQUIRE(e == cudaSuccess, UC_ERR_CUDA, "uc_attn_bwd(main): launch failed: %s", cudaGetErrorString(e));
   if ((r = check_launch("uc_attn_bwd(main)"))) return r;
   {
     const long long total = rows_q * p->H * 2;
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    attn_bwd_finish_kernel<<<(int)blocks, 256, 0, stream>>>(p->dq_acc, static_cast<__nv_bfloat16*>(p->dq), rows_q, p->H, p->lddq,
-                                                            p->scale, p->q_positions, p->rope_table);
+    cudaError_t le = launch_pdl(attn_bwd_finish_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, (const float*)p->dq_acc,
+                                static_cast<__nv_bfloat16*>(p->dq), (long long)rows_q, p->H, (long long)p->lddq, p->scale,
+                                (const int*)p->q_positions, (const float*)p->rope_table);
+    UC_REQUIRE(le == cudaSuccess, UC_ERR_CUDA, "uc_attn_bwd(finish): launch failed: %s", cudaGetErrorString(le));
     r = check_launch("uc_attn_bwd(finish)");
   }
   return r;

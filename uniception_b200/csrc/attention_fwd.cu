@@ -86,6 +86,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_launch_dependents();  // after the TMEM allocation (common.cuh: PDL rules)
+  pdl_wait();
 
   if (warp == 0) {
     // whole warp loops (uniform control flow); one elected lane issues the TMA copies
@@ -286,6 +288,7 @@ extern "C" int uc_attn_fwd(const uc_attn_fwd_params* p, uc_stream_t stream_) {
   a.scale = p->scale;
   a.scale_log2 = p->scale * 1.4426950408889634f;
   dim3 grid((p->Nq + AT_BM - 1) / AT_BM, p->B * p->H);
-  attn_fwd_kernel<<<grid, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, a);
+  cudaError_t le = launch_pdl(attn_fwd_kernel, grid, dim3(AT_THREADS), AT_SMEM, stream, tmQ, tmK, tmV, a);
+  UC_REQUIRE(le == cudaSuccess, UC_ERR_CUDA, "uc_attn_fwd: launch failed: %s", cudaGetErrorString(le));
   return check_launch("uc_attn_fwd");
 }

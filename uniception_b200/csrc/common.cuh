@@ -33,6 +33,30 @@ int make_tensor_map(CUtensorMap* out, const void* base, CUtensorMapDataType dtyp
 
 int sm_count();
 
+// Programmatic dependent launch (PDL): every hot-path kernel is launched with the programmatic-stream-serialization
+// attribute, triggers its dependents after its own set-up (barrier init, TMEM allocation) and calls pdl_wait() before it
+// touches global memory.  The next kernel's CTAs therefore become resident and run their prologue on SMs the
+// predecessor's tail has vacated instead of after a full grid drain.  Rules that keep this deadlock-free:
+//  * pdl_launch_dependents() only AFTER tcgen05.alloc (a waiting dependent holding TMEM must never block a primary CTA
+//    that has not allocated yet; dependents launch only once ALL primary CTAs have triggered);
+//  * every thread of every CTA executes pdl_wait() before it exits, so grid completion implies predecessor completion.
+// UC_PDL=0 in the environment launches everything fully serialised (A/B and debugging).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------
@@ -62,6 +86,10 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+
+// ---- programmatic dependent launch ----
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

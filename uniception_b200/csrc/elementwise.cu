@@ -170,6 +170,8 @@ __global__ void __launch_bounds__(256, CH >= 4 ? 3 : 4) layernorm_fwd_bf16_kerne
   const uint4* xin = static_cast<const uint4*>(p.x);
   uint4* yout = static_cast<uint4*>(p.y);
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= p.rows) return;
   uint4 cur[CH], nxt[CH];
 #pragma unroll
@@ -365,6 +367,8 @@ __global__ void __launch_bounds__(768, 1) layernorm_bwd_rows_kernel(uc_layernorm
   const int col = tid * 4;
   const float inv_c = 1.0f / (float)p.C;
   for (int i = threadIdx.x; i < 3 * 1024; i += blockDim.x) (&colacc[0][0])[i] = 0.f;
+  pdl_launch_dependents();
+  pdl_wait();
   const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
   const uint2* xin = static_cast<const uint2*>(p.x) + tid;
   const uint2* dyin = static_cast<const uint2*>(p.dy) + tid;
@@ -500,6 +504,8 @@ __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __
 __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x, int dtype, int64_t ld, int rows, int cols,
                                                      float* __restrict__ out) {
   __shared__ float red[8][256];
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -685,9 +691,10 @@ extern "C" int uc_layernorm_fwd(const uc_layernorm_fwd_params* p, uc_stream_t st
     // persistent: 3-4 blocks of 8 warps per SM, each warp walks rows with a one-row prefetch
     int g = sm_count() * (ch >= 4 ? 3 : 4);
     if (g > (p->rows + 7) / 8) g = (p->rows + 7) / 8;
-    if (ch == 2) layernorm_fwd_bf16_kernel<2><<<g, 256, 0, stream>>>(*p);
-    else if (ch == 3) layernorm_fwd_bf16_kernel<3><<<g, 256, 0, stream>>>(*p);
-    else layernorm_fwd_bf16_kernel<4><<<g, 256, 0, stream>>>(*p);
+    cudaError_t le = ch == 2   ? launch_pdl(layernorm_fwd_bf16_kernel<2>, dim3(g), dim3(256), 0, stream, *p)
+                     : ch == 3 ? launch_pdl(layernorm_fwd_bf16_kernel<3>, dim3(g), dim3(256), 0, stream, *p)
+                               : launch_pdl(layernorm_fwd_bf16_kernel<4>, dim3(g), dim3(256), 0, stream, *p);
+    UC_REQUIRE(le == cudaSuccess, UC_ERR_CUDA, "uc_layernorm_fwd: launch failed: %s", cudaGetErrorString(le));
     return check_launch("uc_layernorm_fwd");
   }
   if (ch <= 1) layernorm_fwd_kernel<1><<<grid, 256, 0, stream>>>(*p);
@@ -714,7 +721,8 @@ extern "C" int uc_layernorm_bwd(const uc_layernorm_bwd_params* p, uc_stream_t st
     int grid = sm_count();
     const int need = (p->rows + 4 * teams - 1) / (4 * teams);
     if (grid > need) grid = need;
-    layernorm_bwd_rows_kernel<4><<<grid, teams * team_threads, 0, stream>>>(*p);
+    cudaError_t le = launch_pdl(layernorm_bwd_rows_kernel<4>, dim3(grid), dim3(teams * team_threads), 0, stream, *p);
+    UC_REQUIRE(le == cudaSuccess, UC_ERR_CUDA, "uc_layernorm_bwd: launch failed: %s", cudaGetErrorString(le));
     return check_launch("uc_layernorm_bwd");
   }
   UC_REQUIRE(p->dx_colsum == nullptr, UC_ERR_UNSUPPORTED, "uc_layernorm_bwd: dx_colsum needs bf16 inputs and C %% 128 == 0, C <= 1024");
@@ -754,7 +762,9 @@ extern "C" int uc_colsum(const void* x, int32_t x_dtype, int64_t ld, int32_t row
   int slabs = (sm_count() * 4 + grid.x - 1) / grid.x;
   if (slabs > (rows + 7) / 8) slabs = (rows + 7) / 8;
   grid.y = slabs < 1 ? 1 : slabs;
-  colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(x, x_dtype, ld, rows, cols, out);
+  cudaError_t le = launch_pdl(colsum_kernel, grid, dim3(256), 0, static_cast<cudaStream_t>(stream_), x, (int)x_dtype, (int64_t)ld,
+                              (int)rows, (int)cols, out);
+  UC_REQUIRE(le == cudaSuccess, UC_ERR_CUDA, "uc_colsum: launch failed: %s", cudaGetErrorString(le));
   return check_launch("uc_colsum");
 }
 

@@ -220,6 +220,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_launch_dependents();  // after the TMEM allocation (common.cuh: PDL rules)
+  pdl_wait();               // operands / epilogue inputs may come from the previous kernel in the stream
 
   const int total = g.num_m * g.num_n * g.split_k;
 
@@ -413,6 +415,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_launch_dependents();  // after the TMEM allocation (common.cuh: PDL rules)
+  pdl_wait();
 
   const int total = g.num_m * g.num_n * g.split_k;  // num_m counts 256-row blocks here
 
@@ -700,7 +704,8 @@ int launch2_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
     UC_REQUIRE(e == cudaSuccess, UC_ERR_CUDA, "uc_gemm: cudaFuncSetAttribute(gemm2) failed: %s", cudaGetErrorString(e));
     configured = true;
   }
-  gemm2_kernel<MASK, F32><<<grid, GEMM_THREADS, G2_SMEM, stream>>>(tmA, tmB, tmC, tmAux, g);
+  cudaError_t le = launch_pdl(gemm2_kernel<MASK, F32>, dim3(grid), dim3(GEMM_THREADS), G2_SMEM, stream, tmA, tmB, tmC, tmAux, g);
+  UC_REQUIRE(le == cudaSuccess, UC_ERR_CUDA, "uc_gemm(cta_pair): launch failed: %s", cudaGetErrorString(le));
   return check_launch("uc_gemm(cta_pair)");
 }
 
@@ -728,7 +733,8 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, in
     UC_REQUIRE(e == cudaSuccess, UC_ERR_CUDA, "uc_gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     configured = true;
   }
-  gemm_kernel<BN><<<grid, GEMM_THREADS, Cfg<BN>::SMEM, stream>>>(tmA, tmB, g);
+  cudaError_t le = launch_pdl(gemm_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg<BN>::SMEM, stream, tmA, tmB, g);
+  UC_REQUIRE(le == cudaSuccess, UC_ERR_CUDA, "uc_gemm: launch failed: %s", cudaGetErrorString(le));
   return check_launch("uc_gemm");
 }
 

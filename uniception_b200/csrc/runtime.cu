@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <atomic>
 
 #include "common.cuh"
@@ -69,6 +70,11 @@ int make_tensor_map(CUtensorMap* out, const void* base, CUtensorMapDataType dtyp
              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), box[0],
              rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, base);
   return UC_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("UC_PDL"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 int sm_count() {
