@@ -205,7 +205,8 @@ UC_API int uc_attn_bwd(const uc_attn_bwd_params* p, uc_stream_t stream);
 /* ------------------------------------------------------------------------------------------
  * Patch-embed front end (libs/croco/patch_embed.py:68-82): gathers non-overlapping p x p patches of
  * an fp32 NCHW image into bf16 rows [B*h*w][3*p*p] (column order c, i, j == conv weight layout),
- * so that the conv is `uc_gemm`.  Bit-exact gather + one bf16 rounding.
+ * so that the conv is `uc_gemm`.  Bit-exact gather + one bf16 rounding.  Row pitch of `cols_bf16`: 3*p*p when p % 8 == 0,
+ * otherwise 3*p*p rounded up to a multiple of 64 elements with zero pad columns (p = 14: 588 -> 640).
  * ------------------------------------------------------------------------------------------ */
 UC_API int uc_patchify(const float* img, void* cols_bf16, int32_t B, int32_t C, int32_t H, int32_t W, int32_t patch,
                 uc_stream_t stream);

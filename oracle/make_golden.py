@@ -243,6 +243,50 @@ def _oracle_dpt_forward(sd, img1, img2, enc_depth, enc_heads, dec_depth, dec_hea
             {"pts3d_in_other_view": p2.permute(0, 2, 3, 1), "conf": c2.permute(0, 2, 3, 1)})
 
 
+def golden_depth_c5(name, seed, B=2, hw=(42, 56), patch=14, C=128, depth=4, heads=2, indices=(0, 1, 2, 3)):
+    """BASELINE.json configs[4] in miniature: ViT encoder with PATCH 14 (intermediate-feature returner) -> DPTFeature ->
+    DPTRegressionProcessor -> DepthAdaptor(exp), all the reference's own modules (the in-tree CroCo encoder
+    stands in for the un-vendored DINOv2; prediction_heads/dpt.py:180-311, adaptors.py:233-257)."""
+    from uniception.models.encoders.base import ViTEncoderInput
+    from uniception.models.encoders.croco import CroCoIntermediateFeatureReturner
+    from uniception.models.prediction_heads.adaptors import DepthAdaptor
+    from uniception.models.prediction_heads.base import AdaptorInput, PredictionHeadLayeredInput
+    from uniception.models.prediction_heads.dpt import DPTFeature, DPTRegressionProcessor
+
+    m = nn.Module()
+    m.encoder = CroCoIntermediateFeatureReturner(name="enc", data_norm_type="dust3r", img_size=hw, patch_size=patch, enc_embed_dim=C,
+                                                 enc_depth=depth, enc_num_heads=heads, indices=list(indices), intermediates_only=True)
+    m.dpt_feature_head = DPTFeature(patch_size=patch, hooks=[0, 1, 2, 3], input_feature_dims=[C] * 4, layer_dims=[12, 24, 48, 96],
+                                    feature_dim=32)
+    m.dpt_regressor_head = DPTRegressionProcessor(input_feature_dim=32, output_dim=1)
+    adaptor = DepthAdaptor(name="depth", mode="exp")
+    sd, shapes = _load_seeded(m, seed)
+    img = _img((B, 3, *hw), seed + 1)
+    feats = [o.features for o in m.encoder(ViTEncoderInput(image=img, data_norm_type="dust3r"))]
+    dense = m.dpt_feature_head(PredictionHeadLayeredInput(list_features=feats, target_output_shape=hw))
+    raw = m.dpt_regressor_head(dense).decoded_channels
+    out = adaptor(AdaptorInput(adaptor_feature=raw, output_shape_hw=hw)).value
+    out.sum().backward()
+    params = dict(m.named_parameters())
+    # oracle on the same (alias-resolved) weights
+    osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    _, ointer = O.croco_encoder(osd, "encoder.", img, depth, heads, patch, indices=list(indices), norm_intermediate=True)
+    oraw = O.dpt_regressor(osd, "dpt_regressor_head.", O.dpt_feature(osd, "dpt_feature_head.", ointer), hw)
+    oout = O.depth_adaptor(oraw, "exp")
+    for i, (a, b) in enumerate(zip(ointer, feats)):
+        _check(f"{name} hook{i}", a, b)
+    _check(f"{name} raw", oraw, raw)
+    _check(f"{name} depth", oout, out)
+    oout.sum().backward()
+    k0 = "encoder.enc_blocks.0.attn.qkv.weight"
+    _check(f"{name} grad {k0}", osd[k0].grad, params[k0].grad, 1e-4)
+    _check(f"{name} grad patch_embed", osd["encoder.patch_embed.proj.weight"].grad, params["encoder.patch_embed.proj.weight"].grad, 1e-4)
+    _save(name, dict(seed=seed, B=B, hw=list(hw), patch=patch, C=C, depth=depth, heads=heads, indices=list(indices),
+                     shapes={k: list(v) for k, v in shapes.items()}),
+          dict(img=img, raw=raw, depth=out, hook0=feats[0], hook3=feats[3], grad_qkv0=params[k0].grad,
+               grad_patch=params["encoder.patch_embed.proj.weight"].grad))
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -256,6 +300,7 @@ def main():
     golden_dust3r("dust3r_tiny_linear", "linear", seed=21)
     golden_dust3r("dust3r_tiny_linear_sym", "linear", seed=22, B=4, symmetrized=True)
     golden_dust3r("dust3r_tiny_dpt", "dpt", seed=23, hw=(32, 32))
+    golden_depth_c5("depth_c5_tiny_patch14", seed=31)
 
 
 if __name__ == "__main__":

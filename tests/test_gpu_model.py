@@ -270,3 +270,58 @@ def test_dust3r_dpt_vs_reference_golden_fwd_bwd():
     cos = dot / math.sqrt(na * nb)
     print(f"dpt whole-model gradient cosine {cos:.5f}")
     assert cos >= 0.995
+
+
+def test_c5_depth_patch14_vs_reference_golden():
+    """BASELINE configs[4] in miniature: ViT encoder with patch 14 (ragged token counts, padded patch-embed pitch) ->
+    DPT feature head -> regression processor -> DepthAdaptor(exp), forward vs the reference's golden and backward vs
+    the oracle's autograd."""
+    from golden_utils import c5_modules
+    from uniception_b200.prediction_heads import DPTHead, PredictionHeadLayeredInput
+
+    cfg, a = load("depth_c5_tiny_patch14")
+    m = c5_modules(cfg)
+    m.load_state_dict(weights(cfg))
+    m = m.to(DEV)
+    head = DPTHead(m.dpt_feature_head, m.dpt_regressor_head)
+    adaptor = U.DepthAdaptor(name="depth", mode="exp")
+    img = a["img"].to(DEV)
+    hw = tuple(cfg["hw"])
+    feats = [o.features for o in m.encoder(U.ViTEncoderInput(image=img, data_norm_type="dust3r"))]
+    assert feats[0].shape == a["hook0"].shape
+    raw = head(PredictionHeadLayeredInput(list_features=feats, target_output_shape=hw)).decoded_channels
+    depth = adaptor(U.AdaptorInput(adaptor_feature=raw, output_shape_hw=hw)).value
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+
+    def oracle():
+        _, inter = O.croco_encoder(sd, "encoder.", img, cfg["depth"], cfg["heads"], cfg["patch"], indices=cfg["indices"])
+        return inter, O.dpt_regressor(sd, "dpt_regressor_head.", O.dpt_feature(sd, "dpt_feature_head.", inter), hw)
+
+    inter, oraw = oracle()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        _, lraw = oracle()
+    ref_err = O.parity(lraw.float(), oraw)[1]
+    e_hook = O.parity(feats[3], a["hook3"].to(DEV))[1]
+    e_raw = O.parity(raw, a["raw"].to(DEV))[1]
+    e_depth = O.parity(depth, a["depth"].to(DEV))[1]
+    print(f"c5 patch14: hook3 rel {e_hook:.3e}, raw head rel {e_raw:.3e}, depth rel {e_depth:.3e} (autocast-bf16 oracle raw: {ref_err:.3e})")
+    assert O.parity(oraw, a["raw"].to(DEV))[1] <= 1e-4  # oracle (GPU fp32, TF32 off) == reference golden
+    assert e_hook <= 2e-2
+    assert e_raw <= 2.0 * ref_err + 5e-3, (e_raw, ref_err)
+    assert e_depth <= 3.0 * ref_err + 1e-2, (e_depth, ref_err)
+    # backward through encoder + head: gradient direction vs the oracle's autograd
+    for p_ in m.parameters():
+        p_.grad = None
+    raw.sum().backward()
+    oraw.sum().backward()
+    dot = na = nb = 0.0
+    for k, p_ in m.named_parameters():
+        if p_.grad is None or sd[k].grad is None:
+            continue
+        g, r = p_.grad.double().flatten(), sd[k].grad.double().flatten()
+        dot += float(g @ r); na += float(g @ g); nb += float(r @ r)
+    cos = dot / math.sqrt(na * nb)
+    print(f"c5 patch14 whole-pipeline gradient cosine {cos:.5f}")
+    assert cos >= 0.995
+    gp = m.encoder.patch_embed.proj.weight.grad
+    assert gp is not None and O.parity(gp, sd["encoder.patch_embed.proj.weight"].grad)[1] <= 5e-2

@@ -130,3 +130,24 @@ def test_dust3r_dpt_golden():
     (p1.sum() + c1.sum() + p2.sum() + c2.sum()).backward()
     _close(sd["encoder.enc_blocks.0.attn.qkv.weight"].grad, a["grad_qkv0"], 1e-4)
     _close(sd["info_sharing.multi_view_branches.1.0.cross_attn.projk.weight"].grad, a["grad_projk"], 1e-4)
+
+
+def test_depth_c5_patch14_golden():
+    """BASELINE configs[4] in miniature (patch 14, DPT depth head, DepthAdaptor exp): oracle == reference golden."""
+    from golden_utils import c5_modules
+
+    cfg, a = load("depth_c5_tiny_patch14")
+    m = c5_modules(cfg)
+    assert list(m.state_dict().keys()) == list(cfg["shapes"].keys())
+    m.load_state_dict(weights(cfg))
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}  # aliases resolved
+    _, inter = O.croco_encoder(sd, "encoder.", a["img"], cfg["depth"], cfg["heads"], cfg["patch"], indices=cfg["indices"])
+    _close(inter[0], a["hook0"])
+    _close(inter[3], a["hook3"])
+    raw = O.dpt_regressor(sd, "dpt_regressor_head.", O.dpt_feature(sd, "dpt_feature_head.", inter), tuple(cfg["hw"]))
+    _close(raw, a["raw"])
+    out = O.depth_adaptor(raw, "exp")
+    _close(out, a["depth"])
+    out.sum().backward()
+    _close(sd["encoder.enc_blocks.0.attn.qkv.weight"].grad, a["grad_qkv0"], 1e-4)
+    _close(sd["encoder.patch_embed.proj.weight"].grad, a["grad_patch"], 1e-4)

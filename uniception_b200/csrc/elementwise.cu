@@ -497,6 +497,26 @@ __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __
   }
 }
 
+// any patch size (e.g. 14 for the 518x518 / DINOv2-style grids): one thread per output element, row pitch Kp = K rounded
+// up to 64 elements (GEMM K / N granularity), pad columns zero
+__global__ void patchify_generic_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ cols, int B, int C, int H, int W,
+                                        int p, int Kp) {
+  const int h = H / p, w = W / p, K = C * p * p;
+  const int64_t total = (int64_t)B * h * w * Kp;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = idx % Kp;
+    const int64_t tok = idx / Kp;
+    float v = 0.f;
+    if (k < K) {
+      const int j = k % p, i = (k / p) % p, c = k / (p * p);
+      const int px = tok % w, py = (tok / w) % h;
+      const int64_t b = tok / ((int64_t)w * h);
+      v = __ldg(img + ((b * C + c) * H + (py * p + i)) * W + px * p + j);
+    }
+    cols[idx] = __float2bfloat16_rn(v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // column sums (bias gradients): out[col] += sum_rows x[row][col]
 // block = 8 warps; a warp covers 256 columns (8 per lane); blockIdx.y strides over row slabs
@@ -748,11 +768,18 @@ extern "C" int uc_patchify(const float* img, void* cols, int32_t B, int32_t C, i
                            uc_stream_t stream_) {
   UC_REQUIRE(img && cols, UC_ERR_BAD_SHAPE, "uc_patchify: null pointer");
   // same divisibility assertions as PatchEmbedDust3R.forward (libs/croco/patch_embed.py:71-76)
-  UC_REQUIRE(patch % 8 == 0 && H % patch == 0 && W % patch == 0, UC_ERR_BAD_SHAPE,
-             "uc_patchify: image %dx%d is not a multiple of patch size %d (patch %% 8 == 0 required)", H, W, patch);
-  const int64_t total = (int64_t)B * C * H * W / 8;
-  patchify_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      img, static_cast<__nv_bfloat16*>(cols), B, C, H, W, patch);
+  UC_REQUIRE(patch > 0 && H % patch == 0 && W % patch == 0, UC_ERR_BAD_SHAPE,
+             "uc_patchify: image %dx%d is not a multiple of patch size %d", H, W, patch);
+  if (patch % 8 == 0) {
+    const int64_t total = (int64_t)B * C * H * W / 8;
+    patchify_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        img, static_cast<__nv_bfloat16*>(cols), B, C, H, W, patch);
+  } else {
+    const int Kp = (C * patch * patch + 63) / 64 * 64;
+    const int64_t total = (int64_t)B * (H / patch) * (W / patch) * Kp;
+    patchify_generic_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        img, static_cast<__nv_bfloat16*>(cols), B, C, H, W, patch, Kp);
+  }
   return check_launch("uc_patchify");
 }
 

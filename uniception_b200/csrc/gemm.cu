@@ -359,21 +359,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // `empty` / `tmem_full` are released in both CTAs by a multicast tcgen05.commit; the peer's epilogue warps arrive
 // remotely on the leader's `tmem_empty`.
 // ------------------------------------------------------------------------------------------------
-constexpr int G2_BN = 256;
-constexpr int G2_STAGES = 5;
-constexpr uint32_t G2_A_BYTES = 128 * BK * 2, G2_B_BYTES = 128 * BK * 2, G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+constexpr uint32_t G2_A_BYTES = 128 * BK * 2;
 constexpr uint32_t G2_STG_WARP = 2 * 4096;  // per epilogue warp: two 32-row x 128-byte staging tiles (see the epilogue)
 constexpr uint32_t G2_STG_BYTES = NUM_EPI_WARPS * G2_STG_WARP;
-constexpr uint32_t G2_SMEM = G2_STAGES * G2_STAGE_BYTES + G2_STG_BYTES + 1024 + 256;
+template <int BN>
+struct Cfg2 {  // BN = 256: 256 x 256 tiles; BN = 128: 256 x 128 tiles (n = 768 shapes: 3 waves of half tiles instead of 2 full ones)
+  static constexpr int STAGES = BN == 256 ? 5 : 6;
+  static constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = G2_A_BYTES + B_BYTES;
+  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + G2_STG_BYTES + 1024 + 512;
+};
 
 // MASK / F32: epilogue flags and output type this instantiation handles.  One generic kernel with run-time flags is
 // 12 K SASS instructions (~200 KB): the epilogue warps then stall on instruction fetch (ncu: 1.0 "no_instruction" per issue).
-template <int MASK, bool F32>
+template <int MASK, bool F32, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, const GemmArgs g) {
-  constexpr int STAGES = G2_STAGES;
-  constexpr int BN = G2_BN;
+  constexpr int STAGES = Cfg2<BN>::STAGES;
+  constexpr uint32_t G2_STAGE_BYTES = Cfg2<BN>::STAGE_BYTES;
+  constexpr int NCH = BN / 2 / 32;  // 32-column chunks per epilogue warp
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stg_base = smem_base + STAGES * G2_STAGE_BYTES;
@@ -428,7 +433,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int split = item % g.split_k;
       const int tile = item / g.split_k;
       const int m0 = (g.n_fastest ? (tile / g.num_n) : (tile % g.num_m)) * 256 + 128 * (int)rank;
-      const int n0 = (g.n_fastest ? (tile % g.num_n) : (tile / g.num_m)) * BN + 128 * (int)rank;
+      const int n0 = (g.n_fastest ? (tile % g.num_n) : (tile / g.num_m)) * BN + (BN / 2) * (int)rank;
       const int kb0 = split * g.kb_per_split;
       const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -446,8 +451,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (!g.b_mn) {
             tma2_load_2d(sb, &tmB, full_bar(stage), kb * BK, n0);
           } else {
-            tma2_load_2d(sb, &tmB, full_bar(stage), n0, kb * BK);
-            tma2_load_2d(sb + 8192, &tmB, full_bar(stage), n0 + 64, kb * BK);
+#pragma unroll
+            for (int j = 0; j < BN / 2 / 64; ++j) tma2_load_2d(sb + j * 8192, &tmB, full_bar(stage), n0 + j * 64, kb * BK);
           }
         }
         __syncwarp();
@@ -542,11 +547,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int row0 = m0 + lane_group * 32;
       const int row = row0 + lane;
       const bool row_ok = row < g.m;
-      const int nw = n0 + col_half * (BN / 2);  // first column of this warp's 128-column half
+      const int nw = n0 + col_half * (BN / 2);  // first column of this warp's half of the tile
       if (!f32 && has_in) {
         // input tile of unit 0 ([32 rows x 64 cols] bf16 of aux_in / residual) requested BEFORE waiting for the accumulator
         if (lane == 0) {
-          tma_store_wait_read1();  // the previous tile's unit-0 store has finished reading buf0
+          if (NCH == 4) tma_store_wait_read1();  // the previous tile's unit-0 store has finished reading buf0
+          else tma_store_wait_read0();
           mbar_arrive_expect_tx(ld_bar(e, 0), 4096);
           tma_load_2d(buf0, &tmAux, ld_bar(e, 0), nw, row0);
         }
@@ -569,9 +575,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       };
       if (f32) {
-        // 4 units of 32 fp32 columns (128 B rows)
+        // NCH units of 32 fp32 columns (128 B rows)
 #pragma unroll 1
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < NCH; ++u) {
           uint32_t r[32];
           __syncwarp();
           tmem_ld32(tbase + u * 32, r);
@@ -593,12 +599,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
         tmem_ld32(tbase, ra);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NCH; ++c) {
           const int u = c >> 1, hf = c & 1;
           uint32_t(&rc)[32] = (c & 1) ? rb : ra;
           uint32_t(&rn)[32] = (c & 1) ? ra : rb;
           tmem_ld_wait();
-          if (c + 1 < 4) tmem_ld32(tbase + 32 * (c + 1), rn);
+          if (c + 1 < NCH) tmem_ld32(tbase + 32 * (c + 1), rn);
           else release_acc();
           const int n = nw + c * 32;
           float v[32], h[32];
@@ -606,7 +612,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (has_in) {
             if (hf == 0) {
               if (u == 0) {
-                if (lane == 0) {
+                if (NCH == 4 && lane == 0) {
                   tma_store_wait_read0();  // the previous tile's unit-1 store has finished reading buf1
                   mbar_arrive_expect_tx(ld_bar(e, 1), 4096);
                   tma_load_2d(buf1, &tmAux, ld_bar(e, 1), nw + 64, row0);
@@ -634,7 +640,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint32_t outb = (has_aux || u == 0) ? buf0 : buf1;
           if (hf == 0 && !has_in) {  // staging tile free once the bulk store that last read it has completed
             if (lane == 0) {
-              if (has_aux) tma_store_wait_read0();
+              if (has_aux || NCH != 4) tma_store_wait_read0();
               else tma_store_wait_read1();
             }
             __syncwarp();
@@ -695,34 +701,35 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
-template <int MASK, bool F32>
+template <int MASK, bool F32, int BN>
 int launch2_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux, const GemmArgs& g,
                  int grid, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<MASK, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<MASK, F32, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::SMEM);
     UC_REQUIRE(e == cudaSuccess, UC_ERR_CUDA, "uc_gemm: cudaFuncSetAttribute(gemm2) failed: %s", cudaGetErrorString(e));
     configured = true;
   }
-  cudaError_t le = launch_pdl(gemm2_kernel<MASK, F32>, dim3(grid), dim3(GEMM_THREADS), G2_SMEM, stream, tmA, tmB, tmC, tmAux, g);
+  cudaError_t le = launch_pdl(gemm2_kernel<MASK, F32, BN>, dim3(grid), dim3(GEMM_THREADS), Cfg2<BN>::SMEM, stream, tmA, tmB, tmC, tmAux, g);
   UC_REQUIRE(le == cudaSuccess, UC_ERR_CUDA, "uc_gemm(cta_pair): launch failed: %s", cudaGetErrorString(le));
   return check_launch("uc_gemm(cta_pair)");
 }
 
+template <int BN>
 int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux, const GemmArgs& g,
             int grid, cudaStream_t stream) {
   constexpr int kGeneric = UC_EPI_BIAS | UC_EPI_ROPE | UC_EPI_RESIDUAL | UC_EPI_RELU | UC_EPI_RELU_BWD;
   const int e = g.epilogue;
   if (g.c_f32) {
-    if (e == UC_EPI_ATOMIC) return launch2_inst<UC_EPI_ATOMIC, true>(tmA, tmB, tmC, tmAux, g, grid, stream);
-    if ((e & ~kGeneric) == 0) return launch2_inst<kGeneric, true>(tmA, tmB, tmC, tmAux, g, grid, stream);
-    return launch2_inst<-1, true>(tmA, tmB, tmC, tmAux, g, grid, stream);
+    if (e == UC_EPI_ATOMIC) return launch2_inst<UC_EPI_ATOMIC, true, BN>(tmA, tmB, tmC, tmAux, g, grid, stream);
+    if ((e & ~kGeneric) == 0) return launch2_inst<kGeneric, true, BN>(tmA, tmB, tmC, tmAux, g, grid, stream);
+    return launch2_inst<-1, true, BN>(tmA, tmB, tmC, tmAux, g, grid, stream);
   }
   if ((e & ~(UC_EPI_BIAS | UC_EPI_GELU)) == 0 && (e & UC_EPI_GELU))
-    return launch2_inst<UC_EPI_BIAS | UC_EPI_GELU, false>(tmA, tmB, tmC, tmAux, g, grid, stream);
-  if (e == UC_EPI_GELU_BWD) return launch2_inst<UC_EPI_GELU_BWD, false>(tmA, tmB, tmC, tmAux, g, grid, stream);
-  if ((e & ~kGeneric) == 0) return launch2_inst<kGeneric, false>(tmA, tmB, tmC, tmAux, g, grid, stream);
-  return launch2_inst<-1, false>(tmA, tmB, tmC, tmAux, g, grid, stream);
+    return launch2_inst<UC_EPI_BIAS | UC_EPI_GELU, false, BN>(tmA, tmB, tmC, tmAux, g, grid, stream);
+  if (e == UC_EPI_GELU_BWD) return launch2_inst<UC_EPI_GELU_BWD, false, BN>(tmA, tmB, tmC, tmAux, g, grid, stream);
+  if ((e & ~kGeneric) == 0) return launch2_inst<kGeneric, false, BN>(tmA, tmB, tmC, tmAux, g, grid, stream);
+  return launch2_inst<-1, false, BN>(tmA, tmB, tmC, tmAux, g, grid, stream);
 }
 
 template <int BN>
@@ -780,13 +787,15 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
   bool pair = false;
   {
     double best = -1.0;
-    // measured on B200 (profiles/): the pair kernel reaches 1.35 PFLOP/s at K=4096 but needs a long K loop to
-    // amortise its 256x256 tile prologue / epilogue; at K=768 it only ties the single-CTA kernel
+    // measured on B200 (profiles/r01h_gemm_pair_vs_single.log): with its staged, specialised epilogue and PDL the pair
+    // kernel wins or ties on every shape of the path, including K = 768 (8192x3072x768: 33 us vs 48 us single-CTA;
+    // 8192x768x768: 16.3 vs 17.1), so it is preferred unless its wave quantisation is much worse
     const double kf = num_kb <= 8 ? 0.0 : (num_kb >= 40 ? 1.0 : double(num_kb - 8) / 32.0);
-    const int cand[4] = {256, 128, 64, 256};
-    const double rate[4] = {1.0, 0.9, 0.6, 0.95 + 0.4 * kf};
-    for (int i = 0; i < 4; ++i) {
-      const bool is_pair = (i == 3);
+    static const double p128_rate = [] { const char* e = getenv("UC_GEMM_P128_RATE"); return e ? atof(e) : 1.15; }();
+    const int cand[5] = {256, 128, 64, 256, 128};
+    const double rate[5] = {1.0, 0.9, 0.6, 1.3 + 0.1 * kf, p128_rate};
+    for (int i = 0; i < 5; ++i) {
+      const bool is_pair = (i >= 3);
       if (is_pair && pair_env == 0) continue;
       if (p->n % cand[i] != 0) continue;
       const int bm = is_pair ? 256 : BM;
@@ -796,9 +805,9 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
       // split-K (wgrad) fills the machine by itself, so only the per-tile efficiency matters there
       double eff = (atomic ? 1.0 : double(tiles) / double(waves * slots)) * rate[i];
       // the GELU / GELU' epilogues are issue-bound: only the pair kernel's staged, software-pipelined, specialised
-      // epilogue keeps up with the MMA pipe (decoder fc1 at K=768: 86 us single-CTA vs the pair kernel)
+      // epilogue keeps up with the MMA pipe (decoder fc1 at K=768: 86 us single-CTA vs 51 us)
       if (is_pair && (epi & (UC_EPI_GELU | UC_EPI_GELU_BWD))) eff *= 1.5;
-      if (is_pair && pair_env == 1) eff = 10.0;
+      if (is_pair && pair_env == 1) eff = 10.0 + rate[i];
       if (eff > best) { best = eff; bn = cand[i]; pair = is_pair; }
     }
   }
@@ -811,10 +820,18 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
   if (split_k <= 0) {
     split_k = 1;
     if (atomic) {
+      // wgrad: pick the split that fills whole waves (768x768: 9 tiles x 8 splits = 72 of 74 cluster slots in ONE wave;
+      // rounding up to 9 splits made it 81 items = two half-empty waves)
       const long long tiles = (long long)num_m * num_n;
-      split_k = (int)((slots + tiles - 1) / tiles);
-      if (split_k > num_kb / 4) split_k = num_kb / 4;
-      if (split_k < 1) split_k = 1;
+      const int max_split = num_kb / 4 < 1 ? 1 : num_kb / 4;
+      double best_u = -1.0;
+      for (int sk = 1; sk <= max_split && sk <= 64; ++sk) {
+        const long long items = tiles * sk;
+        const long long waves = (items + slots - 1) / slots;
+        const double u = double(items) / double(waves * slots) - 0.002 * sk;  // ties -> fewer splits (less reduction traffic)
+        if (u > best_u) { best_u = u; split_k = sk; }
+        if (items >= 4LL * slots) break;
+      }
     }
   }
   UC_REQUIRE(split_k == 1 || ((epi & UC_EPI_ATOMIC) && epi == UC_EPI_ATOMIC), UC_ERR_BAD_SHAPE,
@@ -832,7 +849,7 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
     strides[0] = (uint64_t)p->lda * 2;
     int r = make_tensor_map(&tmA, p->a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (r) return r;
-    if (!p->b_layout) { dims[0] = p->k; dims[1] = p->n; box[0] = BK; box[1] = pair ? 128 : bn; }
+    if (!p->b_layout) { dims[0] = p->k; dims[1] = p->n; box[0] = BK; box[1] = pair ? bn / 2 : bn; }
     else { dims[0] = p->n; dims[1] = p->k; box[0] = 64; box[1] = BK; }
     strides[0] = (uint64_t)p->ldb * 2;
     r = make_tensor_map(&tmB, p->b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -874,7 +891,7 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
       if (r) return r;
     }
     const int clusters = (int)(total < slots ? total : slots);
-    return launch2(tmA, tmB, tmC, tmAux, g, 2 * clusters, stream);
+    return bn == 256 ? launch2<256>(tmA, tmB, tmC, tmAux, g, 2 * clusters, stream) : launch2<128>(tmA, tmB, tmC, tmAux, g, 2 * clusters, stream);
   }
   const int grid = (int)(total < sms ? total : sms);
   int r = bn == 256 ? launch<256>(tmA, tmB, g, grid, stream) : bn == 128 ? launch<128>(tmA, tmB, g, grid, stream)

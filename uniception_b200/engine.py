@@ -188,6 +188,10 @@ def encoder_fwd(pk: ParamPack, p: str, img: torch.Tensor, depth: int, heads: int
     rope = Rope(B, h, w, rope_base, rope_f0, img.device) if rope_base is not None else None
     cols = ops.patchify(img, patch)
     wpe = pk.w16(p + "patch_embed.proj.weight")
+    if wpe.shape[1] != cols.shape[1]:  # patch sizes whose 3*p*p is not a multiple of 8 (p = 14): zero-padded operand copy
+        wpad = torch.zeros(wpe.shape[0], cols.shape[1], dtype=wpe.dtype, device=wpe.device)
+        wpad[:, :wpe.shape[1]] = wpe
+        wpe = wpad
     x = _empty(cols.shape[0], wpe.shape[0], cols)
     ops.gemm(cols, wpe, x, bias=pk.w32(p + "patch_embed.proj.bias"))
     saved = {"cols": cols, "blocks": [], "B": B, "N": N, "rope": rope, "inter": []}
@@ -246,7 +250,14 @@ def encoder_bwd(pk: ParamPack, p: str, saved, d_out: Optional[torch.Tensor], dep
         done = nxt is not None
         pk.notify_done(bp)  # this block's gradients are final -> its all-reduce bucket may start
     if dx is not None and pk.requires_grad(p + "patch_embed.proj.weight"):
-        ops.gemm(dx, saved["cols"], pk.grad(p + "patch_embed.proj.weight"), a_layout=1, b_layout=1, atomic=True)
+        gw = pk.grad(p + "patch_embed.proj.weight")
+        cols = saved["cols"]
+        if gw.shape[1] == cols.shape[1]:
+            ops.gemm(dx, cols, gw, a_layout=1, b_layout=1, atomic=True)
+        else:  # padded pitch (p = 14): accumulate into a padded fp32 scratch, then add the valid columns
+            gpad = torch.zeros(gw.shape[0], cols.shape[1], dtype=torch.float32, device=gw.device)
+            ops.gemm(dx, cols, gpad, a_layout=1, b_layout=1, atomic=True)
+            gw.add_(gpad[:, :gw.shape[1]])
         if not (done and depth > 0):
             ops.colsum_(dx, pk.grad(p + "patch_embed.proj.bias"))
     return None

@@ -181,7 +181,9 @@ def patchify(img: torch.Tensor, patch: int) -> torch.Tensor:
     B, Cc, H, W = img.shape
     assert H % patch == 0, f"Input image height ({H}) is not a multiple of patch size ({patch})."
     assert W % patch == 0, f"Input image width ({W}) is not a multiple of patch size ({patch})."
-    cols = torch.empty(B * (H // patch) * (W // patch), Cc * patch * patch, dtype=torch.bfloat16, device=img.device)
+    k = Cc * patch * patch
+    kp = k if patch % 8 == 0 else (k + 63) // 64 * 64  # odd patch sizes: row pitch padded to the GEMM granularity (zeros)
+    cols = torch.empty(B * (H // patch) * (W // patch), kp, dtype=torch.bfloat16, device=img.device)
     L.check(L.lib.uc_patchify(_ptr(img), _ptr(cols), B, Cc, H, W, patch, _stream()))
     return cols
 
