@@ -43,6 +43,16 @@ def _peaks():
         return 1400.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
+def _gemm_traffic():
+    """DRAM bytes per uc_gemm launch (read + write, averaged over the launches of one step) from the committed ncu pass
+    profiles/r01i_dram_traffic_per_kernel.json (dram__bytes_read.sum + dram__bytes_write.sum); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01i_dram_traffic_per_kernel.json")) as f:
+            return float(json.load(f)["gemm_dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -256,8 +266,11 @@ def run_b200(args):
             "gpu_launches": int(launches * world),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
-                         "frac": achieved / sustained if sustained else None, "traffic": None,
-                         "kernel": "uc::gemm_kernel<BN> (tcgen05.mma kind::f16, TMA, TMEM double-buffered epilogue)",
+                         "frac": achieved / sustained if sustained else None, "traffic": _gemm_traffic(),
+                         "traffic_note": "avg DRAM bytes per uc_gemm launch (ncu, profiles/r01i_dram_traffic_per_kernel.json); "
+                                         "algorithmic FLOPs per launch = 2*m*n*k, avg %.3e" % (gemm_flop / max(n_gemm, 1)),
+                         "kernel": "uc::gemm2_kernel<EPI,F32,BN> (CTA-pair tcgen05.mma cta_group::2 kind::f16, TMA, TMEM double-buffered "
+                                   "epilogue) + uc::gemm_kernel<BN> for narrow n",
                          "how": f"sum of 2*m*n*k over {n_gemm} uc_gemm launches of 2 instrumented steps / sum of CUDA-event durations on the launching stream",
                          "peak_source": peak_src, "frac_of_burst_peak": achieved / burst if burst else None,
                          "step_tflops": (pairs_per_s / world) * flop_pair / 1e12 if flop_pair else None,

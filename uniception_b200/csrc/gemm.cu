@@ -363,7 +363,7 @@ constexpr uint32_t G2_A_BYTES = 128 * BK * 2;
 constexpr uint32_t G2_STG_WARP = 2 * 4096;  // per epilogue warp: two 32-row x 128-byte staging tiles (see the epilogue)
 constexpr uint32_t G2_STG_BYTES = NUM_EPI_WARPS * G2_STG_WARP;
 template <int BN>
-struct Cfg2 {  // BN = 256: 256 x 256 tiles; BN = 128: 256 x 128 tiles (n = 768 shapes: 3 waves of half tiles instead of 2 full ones)
+struct Cfg2 {  // BN = 256: 256 x 256 tiles (the only instantiation); BN = 128 compiles and is correct but slower per FLOP
   static constexpr int STAGES = BN == 256 ? 5 : 6;
   static constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;
   static constexpr uint32_t STAGE_BYTES = G2_A_BYTES + B_BYTES;
@@ -791,11 +791,12 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
     // kernel wins or ties on every shape of the path, including K = 768 (8192x3072x768: 33 us vs 48 us single-CTA;
     // 8192x768x768: 16.3 vs 17.1), so it is preferred unless its wave quantisation is much worse
     const double kf = num_kb <= 8 ? 0.0 : (num_kb >= 40 ? 1.0 : double(num_kb - 8) / 32.0);
-    static const double p128_rate = [] { const char* e = getenv("UC_GEMM_P128_RATE"); return e ? atof(e) : 1.15; }();
-    const int cand[5] = {256, 128, 64, 256, 128};
-    const double rate[5] = {1.0, 0.9, 0.6, 1.3 + 0.1 * kf, p128_rate};
-    for (int i = 0; i < 5; ++i) {
-      const bool is_pair = (i >= 3);
+    // (256 x 128 pair tiles were tried for the n = 768 shapes -- 3 waves of half tiles instead of 2 full ones -- and lost:
+    // 102.6 vs 114.0 pairs/s when preferred; the kernel template still takes BN, only BN = 256 is instantiated.)
+    const int cand[4] = {256, 128, 64, 256};
+    const double rate[4] = {1.0, 0.9, 0.6, 1.3 + 0.1 * kf};
+    for (int i = 0; i < 4; ++i) {
+      const bool is_pair = (i == 3);
       if (is_pair && pair_env == 0) continue;
       if (p->n % cand[i] != 0) continue;
       const int bm = is_pair ? 256 : BM;
@@ -807,7 +808,7 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
       // the GELU / GELU' epilogues are issue-bound: only the pair kernel's staged, software-pipelined, specialised
       // epilogue keeps up with the MMA pipe (decoder fc1 at K=768: 86 us single-CTA vs 51 us)
       if (is_pair && (epi & (UC_EPI_GELU | UC_EPI_GELU_BWD))) eff *= 1.5;
-      if (is_pair && pair_env == 1) eff = 10.0 + rate[i];
+      if (is_pair && pair_env == 1) eff = 10.0;
       if (eff > best) { best = eff; bn = cand[i]; pair = is_pair; }
     }
   }
@@ -891,7 +892,7 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
       if (r) return r;
     }
     const int clusters = (int)(total < slots ? total : slots);
-    return bn == 256 ? launch2<256>(tmA, tmB, tmC, tmAux, g, 2 * clusters, stream) : launch2<128>(tmA, tmB, tmC, tmAux, g, 2 * clusters, stream);
+    return launch2<256>(tmA, tmB, tmC, tmAux, g, 2 * clusters, stream);
   }
   const int grid = (int)(total < sms ? total : sms);
   int r = bn == 256 ? launch<256>(tmA, tmB, g, grid, stream) : bn == 128 ? launch<128>(tmA, tmB, g, grid, stream)
