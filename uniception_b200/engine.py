@@ -16,6 +16,8 @@ fp32 LayerNorm statistics, fp32 softmax, fp32 RoPE angle math, fp32 head output 
 """
 from __future__ import annotations
 
+import contextlib
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -264,6 +266,56 @@ def encoder_bwd(pk: ParamPack, p: str, saved, d_out: Optional[torch.Tensor], dep
 
 
 # ------------------------------------------------------------------------------------------------
+# per-view CUDA streams (two-view decoder)
+# ------------------------------------------------------------------------------------------------
+class ViewStreams:
+    """At one decoder depth the two views' blocks only read the PREVIOUS depth's tokens, so their kernel chains are
+    independent.  Each chain is ~20 launches of small (m = 8192, n = 768 ...) kernels whose tiles do not fill whole
+    waves of the 148 SMs; on two streams the second chain's CTAs take the SMs the first chain's partial waves leave
+    idle.  Discipline: `fork()` (view streams wait for the caller's stream) -> per-view work under `on(v)` -> `join()`
+    (caller's stream waits for both) once per depth.  Every tensor that crosses streams is either saved for backward
+    (long-lived) or consumed before the next fork, so the caching allocator's per-stream pools never recycle a block
+    that another stream still reads.  UC_VIEW_STREAMS=0 runs everything on the caller's stream."""
+
+    _cache: Dict[str, List[torch.cuda.Stream]] = {}
+    enabled = os.environ.get("UC_VIEW_STREAMS", "1") != "0"
+
+    def __init__(self, nv: int, device):
+        self.active = bool(self.enabled and nv == 2 and torch.device(device).type == "cuda")
+        self.main = torch.cuda.current_stream(device) if self.active else None
+        if self.active:
+            key = str(device)
+            if key not in self._cache:
+                self._cache[key] = [torch.cuda.Stream(device) for _ in range(2)]
+            self.streams = self._cache[key]
+
+    def fork(self) -> None:
+        if self.active:
+            for st in self.streams:
+                st.wait_stream(self.main)
+
+    def join(self) -> None:
+        if self.active:
+            for st in self.streams:
+                self.main.wait_stream(st)
+
+    def on(self, v: int):
+        return torch.cuda.stream(self.streams[v]) if self.active else contextlib.nullcontext()
+
+    def event(self, v: int):
+        """Event recorded on view v's stream (None when inactive)."""
+        if not self.active:
+            return None
+        e = torch.cuda.Event()
+        e.record(self.streams[v])
+        return e
+
+    def wait(self, v: int, event) -> None:
+        if self.active and event is not None:
+            self.streams[v].wait_event(event)
+
+
+# ------------------------------------------------------------------------------------------------
 # two-view (N-view) cross-attention decoder (info_sharing/cross_attention_transformer.py:191-275)
 # ------------------------------------------------------------------------------------------------
 def _cross_fwd(pk, p, x, y, B, Nq, Nk, H, rope_q: Optional[Rope], rope_k: Optional[Rope], saved: list, has_norm_y: bool):
@@ -314,22 +366,31 @@ def decoder_fwd(pk: ParamPack, p: str, toks: List[torch.Tensor], B: int, h: int,
     rope = Rope(B, h, w, rope_base, rope_f0, dev) if rope_base is not None else None
     rope_o = Rope(B * (nv - 1), h, w, rope_base, rope_f0, dev) if (rope_base is not None and nv > 2) else rope
     saved = {"in": toks, "blocks": [], "B": B, "N": N, "nv": nv, "rope": rope, "rope_o": rope_o, "inter": [], "final": []}
-    xs = [linear_fwd(pk, p + "proj_embed", t) for t in toks] if has_proj_embed else list(toks)
+    vs = ViewStreams(nv, dev)
+    vs.fork()
+    xs = []
+    for v, t in enumerate(toks):
+        with vs.on(v):
+            xs.append(linear_fwd(pk, p + "proj_embed", t) if has_proj_embed else t)
+    vs.join()
     inter = []
     for k in range(depth):
         new, lvl = [], []
+        vs.fork()
         for v in range(nv):
             bp = f"{p}multi_view_branches.{v}.{k}."
             bs: list = []
-            if nv == 2:
-                y = xs[1 - v]
-            else:  # other views concatenated along tokens, per batch element
-                y = torch.cat([xs[i].view(B, N, -1) for i in range(nv) if i != v], dim=1).reshape(B * N * (nv - 1), -1)
-            x = self_attn_fwd(pk, bp, xs[v], B, N, heads, rope, "norm1", bs)
-            x = _cross_fwd(pk, bp, x, y, B, N, N * (nv - 1), heads, rope, rope_o, bs, has_norm_y)
-            x = mlp_fwd(pk, bp, x, "norm3", bs)
+            with vs.on(v):
+                if nv == 2:
+                    y = xs[1 - v]
+                else:  # other views concatenated along tokens, per batch element
+                    y = torch.cat([xs[i].view(B, N, -1) for i in range(nv) if i != v], dim=1).reshape(B * N * (nv - 1), -1)
+                x = self_attn_fwd(pk, bp, xs[v], B, N, heads, rope, "norm1", bs)
+                x = _cross_fwd(pk, bp, x, y, B, N, N * (nv - 1), heads, rope, rope_o, bs, has_norm_y)
+                x = mlp_fwd(pk, bp, x, "norm3", bs)
             new.append(x)
             lvl.append(bs)
+        vs.join()
         xs = new
         saved["blocks"].append(lvl)
         if k in take:
@@ -357,6 +418,7 @@ def decoder_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[torch.Te
                 need_input_grad: bool = True):
     B, N, nv, rope, rope_o = saved["B"], saved["N"], saved["nv"], saved["rope"], saved["rope_o"]
     inter_levels = sorted({k for (k, _, _, _, _) in saved["inter"]})
+    vs = ViewStreams(nv, saved["in"][0].device)
 
     def stream_sink(v: int, k: int):
         """Bias buffer fed by the FINAL gradient of view v's token stream entering level k from above (k = -1: the
@@ -392,40 +454,46 @@ def decoder_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[torch.Te
         d_yn: List[Optional[torch.Tensor]] = [None] * nv
         own_done = [False] * nv
         fold_ln = nv == 2 and has_norm_y  # the norm_y backward of the OTHER view produces the final stream gradient
+        vs.fork()
+        ready = [None] * nv  # event: view v's chain of this depth (d_own[v], d_yn[v]) has been issued
         for v in range(nv):
             if dxs[v] is None:
                 continue
             bp = f"{p}multi_view_branches.{v}.{k}."
             bs = lvl[v]
-            s_cross = bias_sink(pk, bp + "cross_attn.proj")
-            dx = mlp_bwd(pk, bp, dxs[v], "norm3", bs[2], bias_done=done[v], out_sink=s_cross)
-            s_attn = bias_sink(pk, bp + "attn.proj")
-            dx, d_yn[v] = _cross_bwd(pk, bp, dx, B, N, N * (nv - 1), heads, rope, rope_o, bs[1], has_norm_y,
-                                     bias_done=s_cross is not None, out_sink=s_attn)
-            # if no fold follows for this view (the other view carries no gradient), norm1's backward is final
-            s_own = stream_sink(v, k - 1) if (nv == 2 and dxs[1 - v] is None) else None
-            d_own[v] = self_attn_bwd(pk, bp, dx, B, N, heads, rope, "norm1", bs[0], bias_done=s_attn is not None, out_sink=s_own)
+            with vs.on(v):
+                s_cross = bias_sink(pk, bp + "cross_attn.proj")
+                dx = mlp_bwd(pk, bp, dxs[v], "norm3", bs[2], bias_done=done[v], out_sink=s_cross)
+                s_attn = bias_sink(pk, bp + "attn.proj")
+                dx, d_yn[v] = _cross_bwd(pk, bp, dx, B, N, N * (nv - 1), heads, rope, rope_o, bs[1], has_norm_y,
+                                         bias_done=s_cross is not None, out_sink=s_attn)
+                # if no fold follows for this view (the other view carries no gradient), norm1's backward is final
+                s_own = stream_sink(v, k - 1) if (nv == 2 and dxs[1 - v] is None) else None
+                d_own[v] = self_attn_bwd(pk, bp, dx, B, N, heads, rope, "norm1", bs[0], bias_done=s_attn is not None, out_sink=s_own)
             own_done[v] = s_own is not None
-            if not has_norm_y:
-                pk.notify_done(bp)
+            ready[v] = vs.event(v)
         # fold the cross-view gradients: d tokens_v(k-1) = d_own[v] + sum_{u != v} norm_y_u'(d_yn[u])|_v
         new: List[Optional[torch.Tensor]] = list(d_own)
         new_done = list(own_done)
+        finished: List[str] = []
         for u in range(nv):
-            if d_yn[u] is None:
-                continue
             bp = f"{p}multi_view_branches.{u}.{k}."
+            if d_yn[u] is None:
+                if dxs[u] is not None:
+                    finished.append(bp)
+                continue
             y, yn, ymean, yrstd = lvl[u][1][8], lvl[u][1][9], lvl[u][1][10], lvl[u][1][11]
             if nv == 2:
                 v = 1 - u
-                if has_norm_y:
-                    sink = stream_sink(v, k - 1) if fold_ln else None
-                    new[v] = ln_bwd(pk, bp + "norm_y", d_yn[u], y, ymean, yrstd, dres=new[v], colsum=sink)
-                    new_done[v] = sink is not None
-                    pk.notify_done(bp)
-                else:
-                    new[v] = d_yn[u] if new[v] is None else new[v] + d_yn[u]
-                    new_done[v] = False
+                vs.wait(v, ready[u])  # d_yn[u] comes from the other view's stream
+                with vs.on(v):
+                    if has_norm_y:
+                        sink = stream_sink(v, k - 1) if fold_ln else None
+                        new[v] = ln_bwd(pk, bp + "norm_y", d_yn[u], y, ymean, yrstd, dres=new[v], colsum=sink)
+                        new_done[v] = sink is not None
+                    else:
+                        new[v] = d_yn[u] if new[v] is None else new[v] + d_yn[u]
+                        new_done[v] = False
             else:
                 dy = ln_bwd(pk, bp + "norm_y", d_yn[u], y, ymean, yrstd) if has_norm_y else d_yn[u]
                 parts = dy.view(B, nv - 1, N, -1)
@@ -434,6 +502,10 @@ def decoder_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[torch.Te
                     g = parts[:, j].reshape(B * N, -1)
                     new[v] = g.contiguous() if new[v] is None else new[v] + g
                     new_done[v] = False
+            finished.append(bp)
+        vs.join()
+        for bp in finished:
+            pk.notify_done(bp)  # this block's gradients (incl. its norm_y, written from the other view's stream) are final
         dxs, done = new, new_done
     d_in: List[Optional[torch.Tensor]] = [None] * nv
     for v in range(nv):
