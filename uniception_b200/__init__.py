@@ -10,6 +10,7 @@ All compute goes through `libuc_b200.so` (C ABI in include/uc_b200.h); importing
 the built library raises ImportError -- there is no CPU or library fallback.
 """
 from . import _lib  # noqa: F401  (fails loudly when the CUDA extension is missing)
+from . import checkpoints  # noqa: F401  (original DUSt3R / CroCo checkpoint -> UniCeption-format state dicts)
 from .dust3r import DUSt3R, interleave, is_symmetrized  # noqa: F401
 from .encoders import (  # noqa: F401
     ENCODER_CONFIGS, CroCoEncoder, CroCoIntermediateFeatureReturner, ViTEncoderInput, ViTEncoderOutput,
