@@ -188,26 +188,46 @@ def decoder_block(sd: SD, p: str, x: Tensor, y: Tensor, xpos, ypos, heads: int, 
     return x
 
 
-def patch_embed(sd: SD, p: str, img: Tensor, patch: int) -> Tuple[Tensor, Tensor]:
+def patch_embed(sd: SD, p: str, img: Tensor, patch: int, true_shape: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     """Conv2d(3,C,k=s=patch)+bias, flatten(2).transpose(1,2) (libs/croco/patch_embed.py:68-82),
-    restated as unfold + matmul (kernel == stride so patches do not overlap)."""
+    restated as unfold + matmul (kernel == stride so patches do not overlap).
+    true_shape [B,2] (height, width): `ManyAR_PatchEmbed` (patch_embed.py:85-127) -- samples whose true width < height
+    were stored transposed (landscape); their patches are taken from the image with the last two axes swapped and their
+    positions come from the (W/p, H/p) grid."""
     B, Cin, H, W = img.shape
     assert H % patch == 0 and W % patch == 0
     h, w = H // patch, W // patch
-    cols = img.view(B, Cin, h, patch, w, patch).permute(0, 2, 4, 1, 3, 5).reshape(B, h * w, Cin * patch * patch)
     wgt = sd[p + "proj.weight"]
-    x = cols @ wgt.reshape(wgt.shape[0], -1).t() + sd[p + "proj.bias"]
-    return x, patch_positions(B, h, w, img.device)
+    wmat = wgt.reshape(wgt.shape[0], -1).t()
+
+    def embed(im, hh, ww):
+        cols = im.reshape(im.shape[0], Cin, hh, patch, ww, patch).permute(0, 2, 4, 1, 3, 5).reshape(im.shape[0], hh * ww, Cin * patch * patch)
+        return cols @ wmat + sd[p + "proj.bias"]
+
+    if true_shape is None:
+        return embed(img, h, w), patch_positions(B, h, w, img.device)
+    assert W >= H, f"img should be in landscape mode, but got W={W} H={H}"
+    assert tuple(true_shape.shape) == (B, 2)
+    portrait = (true_shape[:, 1] < true_shape[:, 0]).tolist()
+    xs, pos = [], []
+    for b_, is_p in enumerate(portrait):
+        if is_p:
+            xs.append(embed(img[b_:b_ + 1].swapaxes(-1, -2), w, h))
+            pos.append(patch_positions(1, w, h, img.device))
+        else:
+            xs.append(embed(img[b_:b_ + 1], h, w))
+            pos.append(patch_positions(1, h, w, img.device))
+    return torch.cat(xs, 0), torch.cat(pos, 0)
 
 
 def croco_encoder(
     sd: SD, p: str, img: Tensor, depth: int, heads: int, patch: int = 16, base: float = 100.0,
-    indices=None, norm_intermediate: bool = True,
+    indices=None, norm_intermediate: bool = True, true_shape: Optional[Tensor] = None,
 ):
     """encoders/croco.py:147-182 (and the IFR variant :260-327 when `indices` is given).
-    Returns BCHW features (and a list of intermediate BCHW features)."""
+    Returns BCHW features (and a list of intermediate BCHW features).  `true_shape`: ManyAR patch-embed (croco.py:160-168)."""
     B, _, H, W = img.shape
-    x, pos = patch_embed(sd, p + "patch_embed.", img, patch)
+    x, pos = patch_embed(sd, p + "patch_embed.", img, patch, true_shape)
     take = feature_take_indices(depth, indices)[0] if indices is not None else []
     inter = []
     for i in range(depth):

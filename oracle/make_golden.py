@@ -287,6 +287,33 @@ def golden_depth_c5(name, seed, B=2, hw=(42, 56), patch=14, C=128, depth=4, head
                grad_patch=params["encoder.patch_embed.proj.weight"].grad))
 
 
+def golden_encoder_manyar(name, seed, C=128, depth=2, heads=2, hw=(32, 48), B=3):
+    """Mixed aspect-ratio batch through the reference's `ManyAR_PatchEmbed` encoder (patch_embed.py:85-127, croco.py:160-168):
+    samples 0 and 2 landscape, sample 1 portrait (stored transposed, true_shape = (W, H))."""
+    from uniception.models.encoders.base import ViTEncoderInput
+    from uniception.models.encoders.croco import CroCoEncoder
+
+    enc = CroCoEncoder(name="enc", data_norm_type="dust3r", patch_embed_cls="ManyAR_PatchEmbed", img_size=hw, enc_embed_dim=C,
+                       enc_depth=depth, enc_num_heads=heads)
+    sd, shapes = _load_seeded(enc, seed)
+    img = _img((B, 3, *hw), seed + 1)
+    true_shape = torch.tensor([[hw[0], hw[1]], [hw[1], hw[0]], [hw[0], hw[1]]][:B])
+    inp = ViTEncoderInput(image=img, data_norm_type="dust3r")
+    inp.true_shape = true_shape
+    feat = enc(inp).features
+    feat.sum().backward()
+    params = dict(enc.named_parameters())
+    sdp = {"encoder." + k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    of = O.croco_encoder(sdp, "encoder.", img, depth, heads, true_shape=true_shape)
+    _check(name, of, feat)
+    of.sum().backward()
+    _check(name + " grad patch", sdp["encoder.patch_embed.proj.weight"].grad, params["patch_embed.proj.weight"].grad, 1e-4)
+    _check(name + " grad qkv0", sdp["encoder.enc_blocks.0.attn.qkv.weight"].grad, params["enc_blocks.0.attn.qkv.weight"].grad, 1e-4)
+    _save(name, dict(C=C, depth=depth, heads=heads, hw=list(hw), B=B, seed=seed, shapes={k: list(v) for k, v in shapes.items()}),
+          dict(img=img, true_shape=true_shape, features=feat, grad_patch=params["patch_embed.proj.weight"].grad,
+               grad_qkv0=params["enc_blocks.0.attn.qkv.weight"].grad))
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -301,6 +328,7 @@ def main():
     golden_dust3r("dust3r_tiny_linear_sym", "linear", seed=22, B=4, symmetrized=True)
     golden_dust3r("dust3r_tiny_dpt", "dpt", seed=23, hw=(32, 32))
     golden_depth_c5("depth_c5_tiny_patch14", seed=31)
+    golden_encoder_manyar("encoder_tiny_manyar", seed=41)
 
 
 if __name__ == "__main__":

@@ -325,3 +325,29 @@ def test_c5_depth_patch14_vs_reference_golden():
     assert cos >= 0.995
     gp = m.encoder.patch_embed.proj.weight.grad
     assert gp is not None and O.parity(gp, sd["encoder.patch_embed.proj.weight"].grad)[1] <= 5e-2
+
+
+def test_encoder_manyar_mixed_aspect_ratio_vs_reference_golden():
+    """`CroCoEncoder(patch_embed_cls="ManyAR_PatchEmbed")` on a batch that mixes landscape and portrait samples
+    (`true_shape`), forward vs the reference's golden, patch-embed / first-block gradients vs the reference's."""
+    cfg, a = load("encoder_tiny_manyar")
+    enc = U.CroCoEncoder(name="enc", data_norm_type="dust3r", patch_embed_cls="ManyAR_PatchEmbed", img_size=tuple(cfg["hw"]),
+                         enc_embed_dim=cfg["C"], enc_depth=cfg["depth"], enc_num_heads=cfg["heads"])
+    enc.load_state_dict(weights(cfg))
+    enc = enc.to(DEV)
+    img = a["img"].to(DEV)
+    inp = U.ViTEncoderInput(image=img, data_norm_type="dust3r")
+    inp.true_shape = a["true_shape"]
+    feat = enc(inp).features
+    sd = {k: v.to(DEV) for k, v in weights(cfg, "encoder.").items()}
+    ref_err = _autocast_err(lambda: [O.croco_encoder(sd, "encoder.", img, cfg["depth"], cfg["heads"], true_shape=a["true_shape"])])[0]
+    err = O.parity(feat, a["features"].to(DEV))[1]
+    print(f"manyar encoder: ours vs reference golden rel {err:.3e} (autocast-bf16 oracle: {ref_err:.3e})")
+    assert err <= 1.5 * ref_err + 2e-3, (err, ref_err)
+    # the portrait sample really went through the transposed path: plain patch-embedding of the same batch differs
+    plain = U.ViTEncoderInput(image=img, data_norm_type="dust3r")
+    assert O.parity(enc(plain).features[1], a["features"][1].to(DEV))[1] > 0.1
+    feat.sum().backward()
+    gp = enc.patch_embed.proj.weight.grad
+    assert O.parity(gp, a["grad_patch"].to(DEV))[1] <= 5e-2
+    assert O.parity(enc.enc_blocks[0].attn.qkv.weight.grad, a["grad_qkv0"].to(DEV))[1] <= 5e-2

@@ -151,3 +151,18 @@ def test_depth_c5_patch14_golden():
     out.sum().backward()
     _close(sd["encoder.enc_blocks.0.attn.qkv.weight"].grad, a["grad_qkv0"], 1e-4)
     _close(sd["encoder.patch_embed.proj.weight"].grad, a["grad_patch"], 1e-4)
+
+
+def test_encoder_manyar_golden():
+    """Mixed aspect-ratio batch: `ManyAR_PatchEmbed` semantics of the oracle == the reference's golden."""
+    cfg, a = load("encoder_tiny_manyar")
+    sd = {k: v.requires_grad_(True) for k, v in weights(cfg, "encoder.").items()}
+    f = O.croco_encoder(sd, "encoder.", a["img"], cfg["depth"], cfg["heads"], true_shape=a["true_shape"])
+    _close(f, a["features"])
+    f.sum().backward()
+    _close(sd["encoder.patch_embed.proj.weight"].grad, a["grad_patch"], 1e-4)
+    _close(sd["encoder.enc_blocks.0.attn.qkv.weight"].grad, a["grad_qkv0"], 1e-4)
+    # all-landscape true_shape == plain patch embedding
+    ts = torch.tensor([[cfg["hw"][0], cfg["hw"][1]]] * cfg["B"])
+    _close(O.croco_encoder(sd, "encoder.", a["img"], cfg["depth"], cfg["heads"], true_shape=ts),
+           O.croco_encoder(sd, "encoder.", a["img"], cfg["depth"], cfg["heads"]), 2e-6)  # per-sample vs batched matmul rounding

@@ -13,7 +13,7 @@ from . import _lib  # noqa: F401  (fails loudly when the CUDA extension is missi
 from . import checkpoints  # noqa: F401  (original DUSt3R / CroCo checkpoint -> UniCeption-format state dicts)
 from .dust3r import DUSt3R, interleave, is_symmetrized  # noqa: F401
 from .encoders import (  # noqa: F401
-    ENCODER_CONFIGS, CroCoEncoder, CroCoIntermediateFeatureReturner, ViTEncoderInput, ViTEncoderOutput,
+    ENCODER_CONFIGS, CroCoEncoder, CroCoIntermediateFeatureReturner, ManyAR_PatchEmbed, ViTEncoderInput, ViTEncoderOutput,
     encoder_factory, feature_returner_encoder_factory, feature_take_indices,
 )
 from .info_sharing import (  # noqa: F401

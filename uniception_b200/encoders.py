@@ -34,6 +34,8 @@ class EncoderOutput:
 @dataclass
 class ViTEncoderInput(EncoderInput):
     image: torch.Tensor  # [B, C, H, W]
+    # optional attribute `true_shape` [B, 2] (height, width), attached by the caller as in the reference
+    # (croco.py:160-165 reads it with hasattr): used by the ManyAR patch-embed
 
 
 @dataclass
@@ -122,6 +124,22 @@ class UniCeptionViTEncoderBase(nn.Module):
         ), f"Input normalization type {data_norm_type} does not match the encoder's normalization type {self.data_norm_type}."
 
 
+class ManyAR_PatchEmbed(PatchEmbedDust3R):
+    """Parameter container of libs/croco/patch_embed.py:85-127 (same `proj.*` keys): all images of a batch are stored in
+    landscape orientation; `true_shape` says which samples are really portrait (their patches / positions are taken from
+    the transposed image).  The arithmetic lives in engine.encoder_fwd(portrait=...)."""
+
+    @staticmethod
+    def portrait_flags(image: torch.Tensor, true_shape: Optional[torch.Tensor]):
+        B, _, H, W = image.shape
+        assert W >= H, f"img should be in landscape mode, but got W={W} H={H}"
+        if true_shape is None:
+            return None
+        assert tuple(true_shape.shape) == (B, 2), f"true_shape has the wrong shape={tuple(true_shape.shape)}"
+        height, width = true_shape.T
+        return (width < height).tolist()
+
+
 class CroCoEncoder(UniCeptionViTEncoderBase):
     "UniCeption CroCov2 Encoder on the B200 engine"
 
@@ -154,9 +172,8 @@ class CroCoEncoder(UniCeptionViTEncoderBase):
         self.pretrained_checkpoint_path = pretrained_checkpoint_path
         self.override_checkpoint_attributes = override_checkpoint_attributes
         check_norm_layer(norm_layer)
-        if patch_embed_cls not in ("PatchEmbedDust3R", "PatchEmbedCroCo"):
-            raise NotImplementedError(
-                f"uniception_b200: patch_embed_cls {patch_embed_cls!r} (mixed aspect-ratio path) is SURVEY.md 8(f3), not built yet")
+        if patch_embed_cls not in ("PatchEmbedDust3R", "PatchEmbedCroCo", "ManyAR_PatchEmbed"):
+            raise NotImplementedError(f"uniception_b200: unknown patch_embed_cls {patch_embed_cls!r}")
 
         self.pos_embed = pos_embed
         if pos_embed.startswith("RoPE"):  # eg RoPE100 (croco.py:79-85)
@@ -167,7 +184,8 @@ class CroCoEncoder(UniCeptionViTEncoderBase):
         else:
             raise NotImplementedError("Unknown pos_embed " + pos_embed)
 
-        self.patch_embed = PatchEmbedDust3R(img_size, patch_size, 3, enc_embed_dim)
+        pe_cls = ManyAR_PatchEmbed if patch_embed_cls == "ManyAR_PatchEmbed" else PatchEmbedDust3R
+        self.patch_embed = pe_cls(img_size, patch_size, 3, enc_embed_dim)
         self.enc_blocks = nn.ModuleList(
             [Block(enc_embed_dim, enc_num_heads, mlp_ratio, qkv_bias=True, norm_layer=norm_layer, rope=self.rope)
              for _ in range(enc_depth)]
@@ -202,20 +220,26 @@ class CroCoEncoder(UniCeptionViTEncoderBase):
             nn.init.constant_(m.weight, 1.0)
 
     # ---- engine entry: tokens in / tokens out (used by the fused DUSt3R model) ----
-    def _cfg(self, take=(), norm_intermediate=True):
+    def _cfg(self, take=(), norm_intermediate=True, portrait=None):
         fr = fusable_rope(self.rope)
         return dict(depth=self.enc_depth, heads=self.enc_num_heads, patch=self.patch_size,
                     rope_base=fr[0] if fr else None, rope_f0=fr[1] if fr else 1.0, take=tuple(take),
-                    norm_intermediate=norm_intermediate)
+                    norm_intermediate=norm_intermediate, portrait=portrait)
 
-    def forward_tokens(self, image: torch.Tensor, pk: ParamPack, prefix: str, take=(), norm_intermediate=True):
+    def _portrait(self, encoder_input) -> Optional[list]:
+        """ManyAR patch-embed: per-sample portrait flags from `encoder_input.true_shape` (croco.py:160-168)."""
+        if not isinstance(self.patch_embed, ManyAR_PatchEmbed):
+            return None
+        return ManyAR_PatchEmbed.portrait_flags(encoder_input.image, getattr(encoder_input, "true_shape", None))
+
+    def forward_tokens(self, image: torch.Tensor, pk: ParamPack, prefix: str, take=(), norm_intermediate=True, portrait=None):
         """image [B,3,H,W] -> (normalised tokens bf16 [B*N, C], [intermediate tokens...])."""
         B, Cin, H, W = image.shape
         assert H % self.patch_size == 0, f"Input image height ({H}) is not a multiple of patch size ({self.patch_size})."
         assert W % self.patch_size == 0, f"Input image width ({W}) is not a multiple of patch size ({self.patch_size})."
         if not image.is_cuda:
             raise RuntimeError("uniception_b200.CroCoEncoder runs on CUDA only (no CPU fallback)")
-        outs = fused.EncoderFn.apply(image, pk, prefix, self._cfg(take, norm_intermediate), *pk.params.values())
+        outs = fused.EncoderFn.apply(image, pk, prefix, self._cfg(take, norm_intermediate, portrait), *pk.params.values())
         return outs[0], list(outs[1:])
 
     def _pack(self) -> ParamPack:
@@ -226,7 +250,7 @@ class CroCoEncoder(UniCeptionViTEncoderBase):
     def forward(self, encoder_input: ViTEncoderInput) -> ViTEncoderOutput:
         self._check_data_normalization_type(encoder_input.data_norm_type)
         B, _, H, W = encoder_input.image.shape
-        tok, _ = self.forward_tokens(encoder_input.image, self._pack(), "")
+        tok, _ = self.forward_tokens(encoder_input.image, self._pack(), "", portrait=self._portrait(encoder_input))
         feats = fused.NlcToNchwFn.apply(tok, B, H // self.patch_size, W // self.patch_size)
         return ViTEncoderOutput(features=feats)
 
@@ -252,7 +276,8 @@ class CroCoIntermediateFeatureReturner(CroCoEncoder, IntermediateFeatureReturner
         B, _, H, W = encoder_input.image.shape
         h, w = H // self.patch_size, W // self.patch_size
         take, _ = feature_take_indices(len(self.enc_blocks), self.indices)
-        tok, inter = self.forward_tokens(encoder_input.image, self._pack(), "", take, self.norm_intermediate)
+        tok, inter = self.forward_tokens(encoder_input.image, self._pack(), "", take, self.norm_intermediate,
+                                         portrait=self._portrait(encoder_input))
         inter = [ViTEncoderOutput(features=fused.NlcToNchwFn.apply(t, B, h, w)) for t in inter]
         if self.intermediates_only:
             return inter

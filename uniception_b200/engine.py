@@ -56,10 +56,15 @@ def rope_table(num_pos: int, base: float, f0: float, device) -> torch.Tensor:
 
 
 class Rope:
-    """Fused-RoPE context for a token grid: int32 positions [rows,2] + (cos,sin) table."""
+    """Fused-RoPE context for a token grid: int32 positions [rows,2] + (cos,sin) table.
+    `portrait` (per-sample flags, ManyAR patch-embed): those samples use the (w, h) grid (patch_embed.py:120-121)."""
 
-    def __init__(self, b: int, h: int, w: int, base: float, f0: float, device):
-        self.pos = grid_positions(b, h, w, device)
+    def __init__(self, b: int, h: int, w: int, base: float, f0: float, device, portrait: Optional[Sequence[bool]] = None):
+        if portrait is None or not any(portrait):
+            self.pos = grid_positions(b, h, w, device)
+        else:
+            land, port = grid_positions(1, h, w, device), grid_positions(1, w, h, device)
+            self.pos = torch.cat([port if f else land for f in portrait], dim=0).contiguous()
         self.table = rope_table(max(h, w), base, f0, device)
 
 
@@ -182,13 +187,28 @@ def mlp_bwd(pk, p, dx2, norm: str, saved, bias_done=False, out_sink=None):
 # encoder (encoders/croco.py:147-182)
 # ------------------------------------------------------------------------------------------------
 def encoder_fwd(pk: ParamPack, p: str, img: torch.Tensor, depth: int, heads: int, patch: int, rope_base: Optional[float],
-                rope_f0: float = 1.0, take: Sequence[int] = (), norm_intermediate: bool = True):
-    """img fp32 [B,3,H,W] -> (normalised tokens bf16 [B*N, C], intermediates, saved-for-backward)."""
+                rope_f0: float = 1.0, take: Sequence[int] = (), norm_intermediate: bool = True,
+                portrait: Optional[Sequence[bool]] = None):
+    """img fp32 [B,3,H,W] -> (normalised tokens bf16 [B*N, C], intermediates, saved-for-backward).
+    portrait: per-sample flags of `ManyAR_PatchEmbed` (libs/croco/patch_embed.py:85-127): flagged samples are patchified
+    from the image with its last two axes swapped and take their positions from the (w, h) grid."""
     B, _, Hh, Ww = img.shape
     h, w = Hh // patch, Ww // patch
     N = h * w
-    rope = Rope(B, h, w, rope_base, rope_f0, img.device) if rope_base is not None else None
-    cols = ops.patchify(img, patch)
+    if portrait is not None and not any(portrait):
+        portrait = None
+    rope = Rope(B, h, w, rope_base, rope_f0, img.device, portrait) if rope_base is not None else None
+    if portrait is None:
+        cols = ops.patchify(img, patch)
+    else:  # mixed batch: gather each orientation group separately, then restore the sample order (index ops, bit-exact)
+        pidx = [i for i, f in enumerate(portrait) if f]
+        lidx = [i for i, f in enumerate(portrait) if not f]
+        cp = ops.patchify(img[pidx].swapaxes(-1, -2).contiguous(), patch)
+        cols = torch.empty(B, N, cp.shape[1], dtype=cp.dtype, device=cp.device)
+        cols[pidx] = cp.view(len(pidx), N, -1)
+        if lidx:
+            cols[lidx] = ops.patchify(img[lidx].contiguous(), patch).view(len(lidx), N, -1)
+        cols = cols.view(B * N, -1)
     wpe = pk.w16(p + "patch_embed.proj.weight")
     if wpe.shape[1] != cols.shape[1]:  # patch sizes whose 3*p*p is not a multiple of 8 (p = 14): zero-padded operand copy
         wpad = torch.zeros(wpe.shape[0], cols.shape[1], dtype=wpe.dtype, device=wpe.device)

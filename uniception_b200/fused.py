@@ -29,7 +29,8 @@ class EncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img, pk: ParamPack, prefix: str, cfg: dict, *params):
         y, inter, saved = E.encoder_fwd(pk, prefix, img.contiguous().float(), cfg["depth"], cfg["heads"], cfg["patch"],
-                                        cfg["rope_base"], cfg["rope_f0"], cfg.get("take", ()), cfg.get("norm_intermediate", True))
+                                        cfg["rope_base"], cfg["rope_f0"], cfg.get("take", ()), cfg.get("norm_intermediate", True),
+                                        cfg.get("portrait"))
         ctx.pk, ctx.prefix, ctx.cfg, ctx.saved = pk, prefix, cfg, saved
         ctx.n_inter = len(inter)
         return (y, *inter)
