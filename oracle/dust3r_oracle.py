@@ -324,6 +324,54 @@ def depth_adaptor(x: Tensor, mode: str = "exp", vmin=-math.inf, vmax=math.inf) -
     return y
 
 
+def view_sinusoid_table(n_position: int, d_hid: int, base: float = 10000.0) -> Tensor:
+    """info_sharing/global_attention_transformer.py:198-208 (`_get_sinusoid_encoding_table`), computed in float64 like the
+    reference's numpy code, returned as fp32."""
+    import numpy as np
+
+    pos = np.arange(n_position, dtype=np.float64)[:, None]
+    j = np.arange(d_hid)
+    ang = pos / np.power(base, 2 * (j // 2) / d_hid)
+    ang[:, 0::2] = np.sin(ang[:, 0::2])
+    ang[:, 1::2] = np.cos(ang[:, 1::2])
+    return torch.from_numpy(ang).float()
+
+
+def self_attention_info_sharing(sd: SD, p: str, feats: List[Tensor], depth: int, heads: int, *, alternating: bool = False,
+                                base: Optional[float] = None, distinguish_ref: bool = True, pe_for_non_ref: bool = True,
+                                max_num_views_for_pe: int = 1000) -> List[Tensor]:
+    """`MultiViewGlobalAttentionTransformer.forward` (global_attention_transformer.py:224-462) and, with
+    `alternating=True`, `MultiViewAlternatingAttentionTransformer.forward` (alternating_attention_transformer.py:397-442:
+    even depths attend over all V*N tokens, odd depths inside each view), for `use_rand_idx_pe_for_non_reference_views=False`
+    and no additional tokens.  Blocks are `SelfAttentionBlock`s (utils/transformer_blocks.py:415-514): without LayerScale /
+    DropPath that is `encoder_block`'s arithmetic.  base: RoPE frequency base when `custom_positional_encoding="rope"`, else None."""
+    V = len(feats)
+    B, C_in, h, w = feats[0].shape
+    N = h * w
+    x = torch.stack(feats, dim=1).permute(0, 1, 3, 4, 2).reshape(B, V * N, C_in)
+    if p + "proj_embed.weight" in sd:
+        x = linear(x, sd[p + "proj_embed.weight"], sd[p + "proj_embed.bias"])
+    dim = x.shape[-1]
+    if distinguish_ref:
+        tab = view_sinusoid_table(max_num_views_for_pe if pe_for_non_ref else 1, dim).to(x.device)
+        pe = torch.zeros(V, dim, device=x.device)
+        pe[0] = tab[0]
+        if pe_for_non_ref:
+            pe[1:] = tab[1:V]
+        x = x + pe.repeat_interleave(N, dim=0)[None]
+    pos = patch_positions(B, h, w, x.device).repeat(1, V, 1) if base is not None else None
+    for i in range(depth):
+        bp = f"{p}self_attention_blocks.{i}."
+        if alternating and i % 2 == 1:
+            xf = x.reshape(B * V, N, dim)
+            pf = pos.reshape(B * V, N, 2) if pos is not None else None
+            x = encoder_block(sd, bp, xf, pf, heads, base).reshape(B, V * N, dim)
+        else:
+            x = encoder_block(sd, bp, x, pos, heads, base)
+    x = layer_norm(x, sd[p + "norm.weight"], sd[p + "norm.bias"])
+    x = x.reshape(B, V, h, w, dim).permute(0, 1, 4, 2, 3)
+    return [x[:, v].contiguous() for v in range(V)]
+
 # --------------------------------------------------------------------------------------
 # DPT head (prediction_heads/dpt.py:94-232, :271-311; libs/croco/dpt_block.py:114-255)
 # --------------------------------------------------------------------------------------

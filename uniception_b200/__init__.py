@@ -17,8 +17,8 @@ from .encoders import (  # noqa: F401
     encoder_factory, feature_returner_encoder_factory, feature_take_indices,
 )
 from .info_sharing import (  # noqa: F401
-    INFO_SHARING_CLASSES, MultiViewCrossAttentionTransformer, MultiViewCrossAttentionTransformerIFR,
-    MultiViewTransformerInput, MultiViewTransformerOutput,
+    INFO_SHARING_CLASSES, MultiViewAlternatingAttentionTransformer, MultiViewCrossAttentionTransformer,
+    MultiViewCrossAttentionTransformerIFR, MultiViewGlobalAttentionTransformer, MultiViewTransformerInput, MultiViewTransformerOutput,
 )
 from .prediction_heads import (  # noqa: F401
     AdaptorInput, ConfidenceAdaptor, DepthAdaptor, LinearFeature, PixelTaskOutput, PointMapAdaptor,

@@ -539,6 +539,74 @@ def decoder_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[torch.Te
 
 
 # ------------------------------------------------------------------------------------------------
+# global / alternating self-attention over all views (info_sharing/global_attention_transformer.py:224-462,
+# alternating_attention_transformer.py:397-442): the encoder block arithmetic on the concatenated token set
+# ------------------------------------------------------------------------------------------------
+def mv_self_attn_fwd(pk: ParamPack, p: str, toks: List[torch.Tensor], B: int, h: int, w: int, depth: int, heads: int,
+                     rope_base: Optional[float], rope_f0: float, alternating: bool, view_pe: Optional[torch.Tensor],
+                     has_proj_embed: bool):
+    """toks: per-view bf16 [B*N, C_in]; view_pe: fp32 [V, dim] view-index encodings added after proj_embed (or None).
+    Rows are ordered (batch, view, token), so the SAME buffer is a [B, V*N] sequence set for the global layers and a
+    [B*V, N] one for the frame-level layers of the alternating variant: no data movement between the two."""
+    nv, N, dev = len(toks), h * w, toks[0].device
+    x_in = torch.cat([t.view(B, N, -1) for t in toks], dim=1).reshape(B * nv * N, -1)
+    rope = Rope(B * nv, h, w, rope_base, rope_f0, dev) if rope_base is not None else None
+    pe = None
+    if view_pe is not None:  # [V, dim] -> one row per token, bf16 like the residual stream it is added to
+        pe = view_pe.to(torch.bfloat16).repeat_interleave(N, dim=0).repeat(B, 1).contiguous()
+    if has_proj_embed:
+        x = linear_fwd(pk, p + "proj_embed", x_in, residual=pe)  # the view encoding rides the GEMM's residual epilogue
+    else:
+        x = x_in if pe is None else ops.elementwise(0, x_in.contiguous(), pe)
+    saved = {"x_in": x_in, "blocks": [], "B": B, "N": N, "nv": nv, "rope": rope}
+    for i in range(depth):
+        frame = alternating and i % 2 == 1
+        Bb, Nn = (B * nv, N) if frame else (B, nv * N)
+        bs: list = []
+        bp = f"{p}self_attention_blocks.{i}."
+        x = self_attn_fwd(pk, bp, x, Bb, Nn, heads, rope, "norm1", bs)
+        x = mlp_fwd(pk, bp, x, "norm2", bs)
+        saved["blocks"].append(bs)
+    y, mean, rstd = ln_fwd(pk, p + "norm", x)
+    saved["final"] = (x, mean, rstd)
+    outs = [t.reshape(B * N, -1) for t in y.view(B, nv, N, -1).unbind(1)]
+    return [t.contiguous() for t in outs], saved
+
+
+def mv_self_attn_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[torch.Tensor]], depth: int, heads: int,
+                     alternating: bool, has_proj_embed: bool, need_input_grad: bool = True):
+    B, N, nv, rope = saved["B"], saved["N"], saved["nv"], saved["rope"]
+    x, mean, rstd = saved["final"]
+    parts = [(d if d is not None else torch.zeros(B * N, x.shape[1], dtype=torch.bfloat16, device=x.device)).view(B, N, -1)
+             for d in d_outs]
+    dy = torch.stack(parts, dim=1).reshape(B * nv * N, -1).contiguous()
+    sink = bias_sink(pk, f"{p}self_attention_blocks.{depth - 1}.mlp.fc2") if depth > 0 else None
+    dx = ln_bwd(pk, p + "norm", dy, x, mean, rstd, colsum=sink)
+    done = sink is not None
+    for i in reversed(range(depth)):
+        frame = alternating and i % 2 == 1
+        Bb, Nn = (B * nv, N) if frame else (B, nv * N)
+        bs = saved["blocks"][i]
+        bp = f"{p}self_attention_blocks.{i}."
+        sink = bias_sink(pk, bp + "attn.proj")
+        dx = mlp_bwd(pk, bp, dx, "norm2", bs[1], bias_done=done, out_sink=sink)
+        if i > 0:
+            nxt = bias_sink(pk, f"{p}self_attention_blocks.{i - 1}.mlp.fc2")
+        else:
+            nxt = bias_sink(pk, p + "proj_embed") if has_proj_embed else None
+        dx = self_attn_bwd(pk, bp, dx, Bb, Nn, heads, rope, "norm1", bs[0], bias_done=sink is not None, out_sink=nxt)
+        done = nxt is not None
+        pk.notify_done(bp)
+    if has_proj_embed:  # the view encoding is a constant: its gradient is dropped
+        d_in = linear_bwd(pk, p + "proj_embed", dx, saved["x_in"], need_dx=need_input_grad, bias_done=done and depth > 0)
+    else:
+        d_in = dx
+    if d_in is None:
+        return [None] * nv
+    return [t.reshape(B * N, -1).contiguous() for t in d_in.view(B, nv, N, -1).unbind(1)]
+
+
+# ------------------------------------------------------------------------------------------------
 # linear head + pixel-shuffle + pointmap/confidence adaptor
 # ------------------------------------------------------------------------------------------------
 def linear_head_fwd(pk: ParamPack, p: str, tok: torch.Tensor, B: int, h: int, w: int, patch: int, conf_min: float, conf_max: float):

@@ -16,10 +16,10 @@ import torch
 import torch.nn as nn
 
 from . import fused
-from .blocks import CrossAttentionBlock, Mlp, _require, check_norm_layer
+from .blocks import Block, CrossAttentionBlock, Mlp, _require, check_norm_layer
 from .encoders import IntermediateFeatureReturner, PositionGetter, feature_take_indices
 from .params import ParamPack, get_pack
-from .rope import fusable_rope
+from .rope import RoPE2D, fusable_rope
 
 
 # ---- dataclasses: info_sharing/base.py:14-97 ----
@@ -233,7 +233,128 @@ class MultiViewCrossAttentionTransformerIFR(MultiViewCrossAttentionTransformer, 
         return MultiViewTransformerOutput(features=[fused.NlcToNchwFn.apply(t, B, h, w) for t in finals]), inter_out
 
 
-# registry surface: info_sharing/__init__.py:23-37 (in-scope entries)
+def _sinusoid_table(n_position: int, d_hid: int, base: float = 10000.0) -> torch.Tensor:
+    """global_attention_transformer.py:198-208 (`_get_sinusoid_encoding_table`): float64 numpy math, fp32 result."""
+    import numpy as np
+
+    pos = np.arange(n_position, dtype=np.float64)[:, None]
+    j = np.arange(d_hid)
+    ang = pos / np.power(base, 2 * (j // 2) / d_hid)
+    ang[:, 0::2] = np.sin(ang[:, 0::2])
+    ang[:, 1::2] = np.cos(ang[:, 1::2])
+    return torch.from_numpy(ang).float()
+
+
+class MultiViewGlobalAttentionTransformer(UniCeptionInfoSharingBase):
+    """UniCeption Multi-View Global-Attention Transformer on the B200 engine (global_attention_transformer.py:25-462):
+    all views' tokens form one sequence of V*N tokens per batch element, `depth` SelfAttentionBlocks, final norm.
+    Same constructor, state-dict keys (incl. the `view_pos_table` buffer) and I/O dataclasses as the reference.
+    Not built: additional input tokens, qk_norm / LayerScale / softmax-scaling flags (NotImplementedError)."""
+
+    ALTERNATING = False
+    _PE_NON_REF_DEFAULT = True
+
+    def __init__(self, name: str, input_embed_dim: int, distinguish_ref_and_non_ref_views: bool = True,
+                 use_pe_for_non_reference_views: Optional[bool] = None, max_num_views_for_pe: int = 1000,
+                 use_rand_idx_pe_for_non_reference_views: bool = True, size: Optional[str] = None, depth: int = 12,
+                 dim: int = 768, num_heads: int = 12, mlp_ratio: float = 4.0, qkv_bias: bool = True, qk_norm: bool = False,
+                 proj_drop: float = 0.0, attn_drop: float = 0.0, init_values: Optional[float] = None, drop_path: float = 0.0,
+                 act_layer=nn.GELU, norm_layer=partial(nn.LayerNorm, eps=1e-6), mlp_layer=Mlp,
+                 custom_positional_encoding=None, use_scalable_softmax: bool = False, use_entropy_scaling: bool = False,
+                 base_token_count_for_entropy_scaling: int = 444, entropy_scaling_growth_factor: float = 1.4,
+                 pretrained_checkpoint_path: Optional[str] = None, gradient_checkpointing: bool = False, *args, **kwargs):
+        super().__init__(name=name, size=size, *args, **kwargs)
+        if use_pe_for_non_reference_views is None:
+            use_pe_for_non_reference_views = self._PE_NON_REF_DEFAULT
+        check_norm_layer(norm_layer)
+        if qk_norm or init_values or drop_path or proj_drop or attn_drop or use_scalable_softmax or use_entropy_scaling:
+            raise NotImplementedError("uniception_b200: qk_norm / LayerScale / dropout / softmax-scaling block options (SURVEY.md 8f4)")
+        if gradient_checkpointing:
+            raise NotImplementedError("uniception_b200: gradient checkpointing is not needed (activations fit 180 GB) and not built")
+        self.input_embed_dim = input_embed_dim
+        self.distinguish_ref_and_non_ref_views = distinguish_ref_and_non_ref_views
+        self.use_pe_for_non_reference_views = use_pe_for_non_reference_views
+        self.max_num_views_for_pe = max_num_views_for_pe
+        self.use_rand_idx_pe_for_non_reference_views = use_rand_idx_pe_for_non_reference_views
+        self.depth, self.dim, self.num_heads, self.mlp_ratio, self.qkv_bias = depth, dim, num_heads, mlp_ratio, qkv_bias
+        self.norm_layer = norm_layer
+        self.pretrained_checkpoint_path = pretrained_checkpoint_path
+        self.proj_embed = nn.Linear(input_embed_dim, dim, bias=True) if input_embed_dim != dim else nn.Identity()
+        if isinstance(custom_positional_encoding, str):
+            if custom_positional_encoding != "rope":
+                raise ValueError(f"Unknown custom positional encoding: {custom_positional_encoding}")
+            self.rope = RoPE2D(freq=100.0, F0=1.0)
+            custom_positional_encoding = self.rope
+        self.custom_positional_encoding = custom_positional_encoding
+        if custom_positional_encoding is not None and fusable_rope(custom_positional_encoding) is None:
+            raise NotImplementedError("uniception_b200: only RoPE2D positional encodings are fused")
+        self.self_attention_blocks = nn.ModuleList(
+            [Block(dim, num_heads, mlp_ratio, qkv_bias=qkv_bias, norm_layer=norm_layer, rope=custom_positional_encoding)
+             for _ in range(depth)])
+        self.norm = norm_layer(dim)
+        if distinguish_ref_and_non_ref_views:
+            self.register_buffer("view_pos_table", _sinusoid_table(max_num_views_for_pe if use_pe_for_non_reference_views else 1, dim))
+        self.apply(self._init_weights)
+        if pretrained_checkpoint_path is not None:
+            print(f"Loading pretrained multi-view attention transformer weights from {pretrained_checkpoint_path} ...")
+            ckpt = torch.load(pretrained_checkpoint_path, weights_only=False)
+            print(self.load_state_dict(ckpt["model"]))
+
+    _init_weights = MultiViewCrossAttentionTransformer._init_weights
+
+    def _pack(self) -> ParamPack:
+        pk = get_pack(self)
+        pk.refresh_bf16()
+        return pk
+
+    def _view_pe(self, nv: int) -> Optional[torch.Tensor]:
+        """[V, dim] rows added to each view's tokens (global_attention_transformer.py:365-393)."""
+        if not self.distinguish_ref_and_non_ref_views:
+            return None
+        pe = torch.zeros(nv, self.dim, device=self.view_pos_table.device)
+        pe[0] = self.view_pos_table[0]
+        if self.use_pe_for_non_reference_views and nv > 1:
+            if self.use_rand_idx_pe_for_non_reference_views:
+                idx = torch.randint(low=1, high=self.max_num_views_for_pe, size=(nv - 1,))
+            else:
+                idx = torch.arange(1, nv)
+            pe[1:] = self.view_pos_table[idx.to(self.view_pos_table.device)]
+        return pe
+
+    def forward_tokens(self, toks: List[torch.Tensor], B: int, h: int, w: int, pk: ParamPack, prefix: str):
+        fr = fusable_rope(self.custom_positional_encoding)
+        cfg = dict(B=B, h=h, w=w, depth=self.depth, heads=self.num_heads, rope_base=fr[0] if fr else None,
+                   rope_f0=fr[1] if fr else 1.0, alternating=self.ALTERNATING, view_pe=self._view_pe(len(toks)),
+                   has_proj_embed=isinstance(self.proj_embed, nn.Linear))
+        return list(fused.MultiViewSelfAttnFn.apply(pk, prefix, cfg, len(toks), *toks, *pk.params.values()))
+
+    def forward(self, model_input: MultiViewTransformerInput) -> MultiViewTransformerOutput:
+        feats = model_input.features
+        assert len(feats) <= self.max_num_views_for_pe, f"Expected less than {self.max_num_views_for_pe} views, got {len(feats)}"
+        assert all(f.shape[1] == self.input_embed_dim for f in feats), f"All views must have input dimension {self.input_embed_dim}"
+        assert all(f.ndim == 4 for f in feats), "All views must have 4 dimensions (N, C, H, W)"
+        if model_input.additional_input_tokens is not None or model_input.additional_input_tokens_per_view is not None:
+            raise NotImplementedError("uniception_b200: additional input tokens are not built (SURVEY.md 8f2)")
+        if not feats[0].is_cuda:
+            raise RuntimeError(f"uniception_b200.{type(self).__name__} runs on CUDA only (no CPU fallback)")
+        B, _, h, w = feats[0].shape
+        toks = [fused.NchwToNlcFn.apply(f) for f in feats]
+        outs = self.forward_tokens(toks, B, h, w, self._pack(), "")
+        return MultiViewTransformerOutput(features=[fused.NlcToNchwFn.apply(t, B, h, w) for t in outs])
+
+
+class MultiViewAlternatingAttentionTransformer(MultiViewGlobalAttentionTransformer):
+    """alternating_attention_transformer.py:22-500: even depths attend over all views' tokens, odd depths inside each view.
+    (Only the reference view gets a view encoding by default: `use_pe_for_non_reference_views=False`, :30.)"""
+
+    ALTERNATING = True
+    _PE_NON_REF_DEFAULT = False
+
+
+# registry surface: info_sharing/__init__.py:23-37 (in-scope entries; the IFR variants of the self-attention transformers
+# are not built)
 INFO_SHARING_CLASSES = {
     "cross_attention": (MultiViewCrossAttentionTransformer, MultiViewCrossAttentionTransformerIFR),
+    "global_attention": (MultiViewGlobalAttentionTransformer, None),
+    "alternating_attention": (MultiViewAlternatingAttentionTransformer, None),
 }
