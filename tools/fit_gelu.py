@@ -26,3 +26,11 @@ t = np.exp2(np.float32(p * ax + np.float32(-1.0)).astype(np.float64)).astype(np.
 g = np.maximum(x, 0) - ax * t
 ref = x.astype(np.float64) * 0.5 * erfc(-x.astype(np.float64) / np.sqrt(2))
 print("max |gelu - exact| in fp32:", float(np.abs(g - ref).max()))
+
+# derivative used by the GELU' epilogue (csrc/common.cuh gelu_erf_grad): Phi(x) + x * phi(x) from the same polynomial
+half_minus = np.float32(0.5) - t
+cdf = np.float32(0.5) + np.copysign(half_minus, x)
+gauss = np.exp2(x.astype(np.float64) ** 2 * (-0.7213475204444817) - 1.3257480647361595).astype(np.float32)
+X = x.astype(np.float64)
+ref_d = 0.5 * erfc(-X / np.sqrt(2)) + X * np.exp(-X * X / 2) / np.sqrt(2 * np.pi)
+print("max |gelu' - exact| in fp32:", float(np.abs(cdf + x * gauss - ref_d).max()))

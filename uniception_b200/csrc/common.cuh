@@ -330,22 +330,6 @@ __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v 
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-// erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7) on the fast MUFU paths: one rcp + one ex2 + 7 FMA.
-// The same exp(-x^2/2) serves the Gaussian term of GELU', so GELU' costs no second transcendental.
-// (CUDA's erff() is ~3x the instructions; the GELU epilogues of fc1 / fc2-dgrad were math-bound with it.)
-__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& gauss) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170f));  // exp(-x^2/2)
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  const float erf_abs = fmaf(-poly * t, e, 1.0f);          // erf(|x|/sqrt2)
-  cdf = fmaf(copysignf(0.5f, x), erf_abs, 0.5f);            // Phi(x) = 0.5 (1 + erf(x/sqrt2))
-  gauss = e * 0.3989422804014327f;                          // phi(x)
-}
 // Forward GELU with ONE transcendental: the upper tail of the normal CDF is 2^-r(a) with r a degree-5 polynomial in
 // a = |x| (fitted to -log2 erfc(a/sqrt2) on [0,7], monotone beyond; max |gelu error| 8e-7 in fp32, checked against
 // scipy erfc in tools/fit_gelu.py).  gelu(x) = relu(x) - |x| * 0.5 * 2^-r(|x|): 5 FMA + ex2 + max + FMA.
@@ -360,9 +344,18 @@ __device__ __forceinline__ float gelu_erf(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(a, p, -1.0f)));  // 0.5 * (1 - Phi(|x|))
   return fmaf(-a, t, fmaxf(x, 0.f));
 }
+// d/dx gelu(x) = Phi(x) + x * phi(x): Phi from the same tail polynomial (|error| 2.2e-6), phi(x) = 2^(-x^2/(2 ln2) - log2(sqrt(2 pi))).
+// Two ex2, no rcp; max |error| 2.3e-6 in fp32 (checked against scipy in tools/fit_gelu.py).
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  float cdf, g;
-  gelu_parts(x, cdf, g);
+  const float a = fabsf(x);
+  float p = fmaf(a, -0.0004921853717271429f, 0.007223218305366688f);
+  p = fmaf(a, p, -0.05219716762260339f);
+  p = fmaf(a, p, -0.4595537883744506f);
+  p = fmaf(a, p, -1.1510123524537288f);
+  float t, g;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(a, p, -1.0f)));                            // 1 - Phi(|x|)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(fmaf(x * x, -0.72134752044448170f, -1.3257480647361595f)));  // phi(x)
+  const float cdf = 0.5f + copysignf(0.5f - t, x);
   return fmaf(x, g, cdf);
 }
 
