@@ -228,22 +228,32 @@ def run_b200(args):
             dist.barrier()
         return float(ms.item())
 
+    n0 = _lib.launch_count()
     for _ in range(max(3, args.warmup)):
         step_resident()
+    launches_per_step = (_lib.launch_count() - n0) // max(3, args.warmup)  # host-side count of libuc_b200 kernel launches
+    graph_note = "eager launches (2 decoder view streams, PDL)"
     if args.graph and world == 1:
         # One CUDA graph of the whole step (zero grads, forward, loss, backward; both decoder view streams and every
-        # programmatic-dependent-launch edge are captured): ~1550 launches replayed without host work.
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            static_loss = step(a_dev, b_dev)
-        for _ in range(2):
-            step_resident()
-        torch.cuda.synchronize()
+        # programmatic-dependent-launch edge are captured): ~1550 launches replayed without host work.  Falls back to
+        # eager launches if capture is refused.
+        try:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                loss_g = step(a_dev, b_dev)
+            graph, static_loss = g, loss_g
+            for _ in range(2):
+                step_resident()
+            torch.cuda.synchronize()
+            graph_note = "one CUDA graph per step (same kernels, 2 decoder view streams and PDL edges captured)"
+        except Exception as exc:  # pragma: no cover
+            graph, static_loss = None, None
+            torch.cuda.synchronize()
+            graph_note = f"eager launches (CUDA graph capture refused: {type(exc).__name__})"
     sampler = ClockSampler(local) if rank == 0 else None
-    n0 = _lib.launch_count()
     ms = timed(step_resident, args.steps)
-    launches = _lib.launch_count() - n0
+    launches = launches_per_step * args.steps  # the graph replays exactly the launches counted above
     clocks = sampler.stop() if sampler else {}
     for _ in range(2):
         step_e2e()
@@ -284,7 +294,7 @@ def run_b200(args):
                        "l2": ("activations per step (>10 GB) far exceed the 126 MB L2; no flush needed" if S >= 512 else
                               "activations per step (~3 GB at 224^2) exceed the 126 MB L2; no flush needed"),
                        "grad_allreduce": "flat fp32 buffer, per-block buckets overlapped with backward" if world > 1 else "none",
-                       "launch": "one CUDA graph per step" if graph is not None else "eager launches (2 decoder view streams, PDL)"},
+                       "launch": graph_note},
             "e2e": {"value": e2e_pairs, "unit": "pairs/s", "h2d_bytes_per_step": int(a_host.numel() * 4 * 2),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches * world),
@@ -318,7 +328,7 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--pairs-per-gpu", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", type=int, default=0, help="1: replay the step from one captured CUDA graph (single GPU)")
+    ap.add_argument("--graph", type=int, default=1, help="1 (default): replay the step from one captured CUDA graph (single GPU); 0: eager")
     ap.add_argument("--gemm-breakdown", action="store_true", help="print per-shape GEMM timings of the instrumented steps to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
