@@ -144,19 +144,33 @@ def mlp(sd: SD, p: str, x: Tensor) -> Tensor:
     return linear(gelu_erf(linear(x, sd[p + "fc1.weight"], sd[p + "fc1.bias"])), sd[p + "fc2.weight"], sd[p + "fc2.bias"])
 
 
-def self_attention(sd: SD, p: str, x: Tensor, pos: Optional[Tensor], heads: int, base: float) -> Tensor:
-    """libs/croco/blocks.py:105-130 == utils/transformer_blocks.py:208-257 (DUSt3R flags)."""
+def softmax_q_multiplier(n_tokens: int, softmax_scaling=None) -> float:
+    """Query multipliers of `use_scalable_softmax` (log N) and `use_entropy_scaling` (sqrt(growth log N / log base)),
+    utils/transformer_blocks.py:231-241, :360-370.  softmax_scaling = (use_ss, use_es, base_token_count, growth) or None."""
+    m = 1.0
+    if softmax_scaling:
+        use_ss, use_es, base_cnt, growth = softmax_scaling
+        if use_ss:
+            m *= math.log(n_tokens)
+        if use_es:
+            m *= math.sqrt(growth * math.log(n_tokens) / math.log(base_cnt))
+    return m
+
+
+def self_attention(sd: SD, p: str, x: Tensor, pos: Optional[Tensor], heads: int, base: float, softmax_scaling=None) -> Tensor:
+    """libs/croco/blocks.py:105-130 == utils/transformer_blocks.py:208-257 (DUSt3R flags; optional softmax scaling)."""
     B, N, C = x.shape
     d = C // heads
     qkv = linear(x, sd[p + "qkv.weight"], sd.get(p + "qkv.bias")).view(B, N, 3, heads, d).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0], qkv[1], qkv[2]
     if pos is not None:
         q, k = rope2d(q, pos, base), rope2d(k, pos, base)
+    q = q * softmax_q_multiplier(N, softmax_scaling)
     o = sdpa(q, k, v).transpose(1, 2).reshape(B, N, C)
     return linear(o, sd[p + "proj.weight"], sd[p + "proj.bias"])
 
 
-def cross_attention(sd: SD, p: str, xq: Tensor, y: Tensor, qpos, kpos, heads: int, base: float) -> Tensor:
+def cross_attention(sd: SD, p: str, xq: Tensor, y: Tensor, qpos, kpos, heads: int, base: float, softmax_scaling=None) -> Tensor:
     """utils/transformer_blocks.py:320-386."""
     B, Nq, C = xq.shape
     Nk = y.shape[1]
@@ -166,23 +180,27 @@ def cross_attention(sd: SD, p: str, xq: Tensor, y: Tensor, qpos, kpos, heads: in
     v = linear(y, sd[p + "projv.weight"], sd.get(p + "projv.bias")).view(B, Nk, heads, d).permute(0, 2, 1, 3)
     if qpos is not None:
         q, k = rope2d(q, qpos, base), rope2d(k, kpos, base)
+    q = q * softmax_q_multiplier(Nq, softmax_scaling)
     o = sdpa(q, k, v).transpose(1, 2).reshape(B, Nq, C)
     return linear(o, sd[p + "proj.weight"], sd[p + "proj.bias"])
 
 
-def encoder_block(sd: SD, p: str, x: Tensor, pos: Tensor, heads: int, base: float) -> Tensor:
-    """libs/croco/blocks.py:158-161."""
-    x = x + self_attention(sd, p + "attn.", layer_norm(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"]), pos, heads, base)
+def encoder_block(sd: SD, p: str, x: Tensor, pos: Tensor, heads: int, base: float, softmax_scaling=None) -> Tensor:
+    """libs/croco/blocks.py:158-161 (== SelfAttentionBlock, utils/transformer_blocks.py:497-499, without LayerScale)."""
+    x = x + self_attention(sd, p + "attn.", layer_norm(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"]), pos, heads, base,
+                           softmax_scaling)
     x = x + mlp(sd, p + "mlp.", layer_norm(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"]))
     return x
 
 
-def decoder_block(sd: SD, p: str, x: Tensor, y: Tensor, xpos, ypos, heads: int, base: float) -> Tensor:
+def decoder_block(sd: SD, p: str, x: Tensor, y: Tensor, xpos, ypos, heads: int, base: float, softmax_scaling=None) -> Tensor:
     """utils/transformer_blocks.py:643-646 (LayerScale/DropPath are Identity for DUSt3R)."""
-    x = x + self_attention(sd, p + "attn.", layer_norm(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"]), xpos, heads, base)
+    x = x + self_attention(sd, p + "attn.", layer_norm(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"]), xpos, heads, base,
+                           softmax_scaling)
     y_ = layer_norm(y, sd[p + "norm_y.weight"], sd[p + "norm_y.bias"])
     x = x + cross_attention(
-        sd, p + "cross_attn.", layer_norm(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"]), y_, xpos, ypos, heads, base
+        sd, p + "cross_attn.", layer_norm(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"]), y_, xpos, ypos, heads, base,
+        softmax_scaling,
     )
     x = x + mlp(sd, p + "mlp.", layer_norm(x, sd[p + "norm3.weight"], sd[p + "norm3.bias"]))
     return x
@@ -247,7 +265,7 @@ def croco_encoder(
 
 def info_sharing(
     sd: SD, p: str, feats: List[Tensor], depth: int, heads: int, base: float = 100.0,
-    indices=None, norm_intermediate: bool = True,
+    indices=None, norm_intermediate: bool = True, softmax_scaling=None,
 ):
     """info_sharing/cross_attention_transformer.py:191-275 (IFR: :390-505).  Each view's block
     at depth k reads the *other* views' tokens from depth k-1."""
@@ -265,7 +283,8 @@ def info_sharing(
         for v in range(nv):
             others = torch.cat([toks[i] for i in range(nv) if i != v], dim=1)
             opos = torch.cat([pos[i] for i in range(nv) if i != v], dim=1)
-            new.append(decoder_block(sd, f"{p}multi_view_branches.{v}.{k}.", toks[v], others, pos[v], opos, heads, base))
+            new.append(decoder_block(sd, f"{p}multi_view_branches.{v}.{k}.", toks[v], others, pos[v], opos, heads, base,
+                                     softmax_scaling))
         toks = new
         if k in take:
             inter.append([layer_norm(t, nw, nb) if norm_intermediate else t for t in toks])
@@ -339,7 +358,7 @@ def view_sinusoid_table(n_position: int, d_hid: int, base: float = 10000.0) -> T
 
 def self_attention_info_sharing(sd: SD, p: str, feats: List[Tensor], depth: int, heads: int, *, alternating: bool = False,
                                 base: Optional[float] = None, distinguish_ref: bool = True, pe_for_non_ref: bool = True,
-                                max_num_views_for_pe: int = 1000) -> List[Tensor]:
+                                max_num_views_for_pe: int = 1000, softmax_scaling=None) -> List[Tensor]:
     """`MultiViewGlobalAttentionTransformer.forward` (global_attention_transformer.py:224-462) and, with
     `alternating=True`, `MultiViewAlternatingAttentionTransformer.forward` (alternating_attention_transformer.py:397-442:
     even depths attend over all V*N tokens, odd depths inside each view), for `use_rand_idx_pe_for_non_reference_views=False`
@@ -365,9 +384,9 @@ def self_attention_info_sharing(sd: SD, p: str, feats: List[Tensor], depth: int,
         if alternating and i % 2 == 1:
             xf = x.reshape(B * V, N, dim)
             pf = pos.reshape(B * V, N, 2) if pos is not None else None
-            x = encoder_block(sd, bp, xf, pf, heads, base).reshape(B, V * N, dim)
+            x = encoder_block(sd, bp, xf, pf, heads, base, softmax_scaling).reshape(B, V * N, dim)
         else:
-            x = encoder_block(sd, bp, x, pos, heads, base)
+            x = encoder_block(sd, bp, x, pos, heads, base, softmax_scaling)
     x = layer_norm(x, sd[p + "norm.weight"], sd[p + "norm.bias"])
     x = x.reshape(B, V, h, w, dim).permute(0, 1, 4, 2, 3)
     return [x[:, v].contiguous() for v in range(V)]

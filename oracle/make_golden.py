@@ -314,7 +314,8 @@ def golden_encoder_manyar(name, seed, C=128, depth=2, heads=2, hw=(32, 48), B=3)
                grad_qkv0=params["enc_blocks.0.attn.qkv.weight"].grad))
 
 
-def golden_self_attention_info_sharing(name, cls_name, seed, rope, V=2, B=2, hw=(3, 4), C_in=192, dim=128, depth=4, heads=2):
+def golden_self_attention_info_sharing(name, cls_name, seed, rope, V=2, B=2, hw=(3, 4), C_in=192, dim=128, depth=4, heads=2,
+                                       scaling=False):
     """`MultiViewGlobalAttentionTransformer` / `MultiViewAlternatingAttentionTransformer` on V views, with
     sequential view-index positional encodings (the default draws them at random) and optional RoPE."""
     from uniception.models.info_sharing import alternating_attention_transformer as AT, global_attention_transformer as GT
@@ -325,7 +326,9 @@ def golden_self_attention_info_sharing(name, cls_name, seed, rope, V=2, B=2, hw=
     cls = getattr(GT, cls_name, None) or getattr(AT, cls_name)
     # a callable, not the string "rope": the alternating transformer does not resolve the string (it would call a str)
     m = cls(name="mv", input_embed_dim=C_in, depth=depth, dim=dim, num_heads=heads, use_rand_idx_pe_for_non_reference_views=False,
-            custom_positional_encoding=RoPE2D(freq=100.0) if rope else None)
+            custom_positional_encoding=RoPE2D(freq=100.0) if rope else None,
+            use_scalable_softmax=scaling, use_entropy_scaling=scaling)
+    sm = (True, True, m.base_token_count_for_entropy_scaling, m.entropy_scaling_growth_factor) if scaling else None
     # seeded parameters only: `view_pos_table` is a persistent BUFFER (the sinusoid table), not a weight
     shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if k != "view_pos_table"}
     m.load_state_dict(O.seeded_state_dict(shapes, seed), strict=False)
@@ -338,7 +341,8 @@ def golden_self_attention_info_sharing(name, cls_name, seed, rope, V=2, B=2, hw=
     osd = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "view_pos_table"}
     of = [f.detach().clone().requires_grad_(True) for f in feats]
     oo = O.self_attention_info_sharing(osd, "", of, depth, heads, alternating="Alternating" in cls_name, base=100.0 if rope else None,
-                                       distinguish_ref=m.distinguish_ref_and_non_ref_views, pe_for_non_ref=m.use_pe_for_non_reference_views)
+                                       distinguish_ref=m.distinguish_ref_and_non_ref_views, pe_for_non_ref=m.use_pe_for_non_reference_views,
+                                       softmax_scaling=sm)
     for v in range(V):
         _check(f"{name} view{v}", oo[v], out[v])
     sum(o.sum() for o in oo).backward()
@@ -349,7 +353,39 @@ def golden_self_attention_info_sharing(name, cls_name, seed, rope, V=2, B=2, hw=
     arrays.update({f"out{v}": out[v] for v in range(V)})
     arrays.update(grad_qkv1=params[k0].grad, grad_proj_embed=params["proj_embed.weight"].grad, grad_in0=feats[0].grad)
     _save(name, dict(cls=cls_name, seed=seed, rope=bool(rope), V=V, B=B, hw=list(hw), C_in=C_in, dim=dim, depth=depth, heads=heads,
-                     pe_for_non_ref=bool(m.use_pe_for_non_reference_views),
+                     pe_for_non_ref=bool(m.use_pe_for_non_reference_views), scaling=bool(scaling),
+                     shapes={k: list(v) for k, v in shapes.items()}), arrays)
+
+
+def golden_cross_attention_scaled(name, seed, B=2, hw=(3, 4), C_in=192, dim=128, depth=2, heads=2):
+    """`MultiViewCrossAttentionTransformer(use_scalable_softmax=True, use_entropy_scaling=True)` (the two
+    token-count-dependent query multipliers, utils/transformer_blocks.py:231-241, :360-370)."""
+    from uniception.models.info_sharing.base import MultiViewTransformerInput
+    from uniception.models.info_sharing.cross_attention_transformer import MultiViewCrossAttentionTransformer
+    from uniception.models.libs.croco.pos_embed import RoPE2D
+
+    m = MultiViewCrossAttentionTransformer(name="mv", input_embed_dim=C_in, num_views=2, depth=depth, dim=dim, num_heads=heads,
+                                           custom_positional_encoding=RoPE2D(freq=100.0), use_scalable_softmax=True,
+                                           use_entropy_scaling=True)
+    sd, shapes = _load_seeded(m, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    feats = [torch.randn(B, C_in, *hw, generator=g).requires_grad_(True) for _ in range(2)]
+    out = m(MultiViewTransformerInput(features=feats)).features
+    sum(o.sum() for o in out).backward()
+    params = dict(m.named_parameters())
+    sm = (True, True, m.base_token_count_for_entropy_scaling, m.entropy_scaling_growth_factor)
+    osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    of = [f.detach().clone().requires_grad_(True) for f in feats]
+    oo = O.info_sharing(osd, "", of, depth, heads, softmax_scaling=sm)
+    for v in range(2):
+        _check(f"{name} view{v}", oo[v], out[v])
+    sum(o.sum() for o in oo).backward()
+    k0 = "multi_view_branches.1.0.cross_attn.projq.weight"
+    _check(f"{name} grad {k0}", osd[k0].grad, params[k0].grad, 1e-4)
+    arrays = {f"feat{v}": feats[v].detach() for v in range(2)}
+    arrays.update({f"out{v}": out[v] for v in range(2)})
+    arrays.update(grad_projq=params[k0].grad, grad_qkv=params["multi_view_branches.0.1.attn.qkv.weight"].grad, grad_in0=feats[0].grad)
+    _save(name, dict(seed=seed, B=B, hw=list(hw), C_in=C_in, dim=dim, depth=depth, heads=heads, softmax_scaling=list(sm),
                      shapes={k: list(v) for k, v in shapes.items()}), arrays)
 
 
@@ -371,6 +407,8 @@ def main():
     golden_self_attention_info_sharing("global_attn_tiny", "MultiViewGlobalAttentionTransformer", seed=51, rope=False)
     golden_self_attention_info_sharing("global_attn_tiny_rope", "MultiViewGlobalAttentionTransformer", seed=52, rope=True, V=3)
     golden_self_attention_info_sharing("alternating_attn_tiny", "MultiViewAlternatingAttentionTransformer", seed=53, rope=True)
+    golden_self_attention_info_sharing("global_attn_tiny_scaled", "MultiViewGlobalAttentionTransformer", seed=54, rope=True, scaling=True)
+    golden_cross_attention_scaled("cross_attn_tiny_scaled", seed=55)
 
 
 if __name__ == "__main__":

@@ -353,14 +353,16 @@ def test_encoder_manyar_mixed_aspect_ratio_vs_reference_golden():
     assert O.parity(enc.enc_blocks[0].attn.qkv.weight.grad, a["grad_qkv0"].to(DEV))[1] <= 5e-2
 
 
-@pytest.mark.parametrize("name", ["global_attn_tiny", "global_attn_tiny_rope", "alternating_attn_tiny"])
+@pytest.mark.parametrize("name", ["global_attn_tiny", "global_attn_tiny_rope", "alternating_attn_tiny", "global_attn_tiny_scaled"])
 def test_self_attention_info_sharing_vs_reference_golden(name):
     """`MultiViewGlobalAttentionTransformer` / `MultiViewAlternatingAttentionTransformer` on the B200 engine vs
     the reference's golden outputs and gradients (2 and 3 views, with and without RoPE)."""
     cfg, a = load(name)
     m = getattr(U, cfg["cls"])(name="mv", input_embed_dim=cfg["C_in"], depth=cfg["depth"], dim=cfg["dim"], num_heads=cfg["heads"],
                                use_rand_idx_pe_for_non_reference_views=False,
-                               custom_positional_encoding=U.RoPE2D(freq=100.0) if cfg["rope"] else None)
+                               custom_positional_encoding=U.RoPE2D(freq=100.0) if cfg["rope"] else None,
+                               use_scalable_softmax=cfg.get("scaling", False), use_entropy_scaling=cfg.get("scaling", False))
+    sm = (True, True, 444, 1.4) if cfg.get("scaling") else None
     m.load_state_dict(weights(cfg), strict=False)  # view_pos_table is a buffer (the sinusoid table), not a weight
     m = m.to(DEV)
     feats = [a[f"feat{v}"].to(DEV).requires_grad_(True) for v in range(cfg["V"])]
@@ -370,7 +372,7 @@ def test_self_attention_info_sharing_vs_reference_golden(name):
     ref_err = max(_autocast_err(lambda: O.self_attention_info_sharing(sd, "", fin, cfg["depth"], cfg["heads"],
                                                                       alternating="Alternating" in cfg["cls"],
                                                                       base=100.0 if cfg["rope"] else None,
-                                                                      pe_for_non_ref=cfg["pe_for_non_ref"])))
+                                                                      pe_for_non_ref=cfg["pe_for_non_ref"], softmax_scaling=sm)))
     err = max(O.parity(out[v], a[f"out{v}"].to(DEV))[1] for v in range(cfg["V"]))
     print(f"{name}: ours vs reference golden rel {err:.3e} (autocast-bf16 oracle: {ref_err:.3e})")
     assert err <= 1.5 * ref_err + 2e-3, (err, ref_err)
@@ -378,4 +380,28 @@ def test_self_attention_info_sharing_vs_reference_golden(name):
     g = m.self_attention_blocks[1].attn.qkv.weight.grad
     assert O.parity(g, a["grad_qkv1"].to(DEV))[1] <= 5e-2
     assert O.parity(m.proj_embed.weight.grad, a["grad_proj_embed"].to(DEV))[1] <= 5e-2
+    assert O.parity(feats[0].grad, a["grad_in0"].to(DEV))[1] <= 5e-2
+
+
+def test_cross_attention_softmax_scaling_vs_reference_golden():
+    """`MultiViewCrossAttentionTransformer(use_scalable_softmax=True, use_entropy_scaling=True)`: the
+    token-count query multipliers fold into the attention kernels' scale (forward, dq, dk)."""
+    cfg, a = load("cross_attn_tiny_scaled")
+    m = U.MultiViewCrossAttentionTransformer(name="mv", input_embed_dim=cfg["C_in"], num_views=2, depth=cfg["depth"], dim=cfg["dim"],
+                                             num_heads=cfg["heads"], custom_positional_encoding=U.RoPE2D(freq=100.0),
+                                             use_scalable_softmax=True, use_entropy_scaling=True)
+    m.load_state_dict(weights(cfg))
+    m = m.to(DEV)
+    feats = [a["feat0"].to(DEV).requires_grad_(True), a["feat1"].to(DEV).requires_grad_(True)]
+    out = m(U.MultiViewTransformerInput(features=feats)).features
+    sd = {k: v.to(DEV) for k, v in weights(cfg).items()}
+    fin = [f.detach() for f in feats]
+    sm = tuple(cfg["softmax_scaling"])
+    ref_err = max(_autocast_err(lambda: O.info_sharing(sd, "", fin, cfg["depth"], cfg["heads"], softmax_scaling=sm)))
+    err = max(O.parity(out[v], a[f"out{v}"].to(DEV))[1] for v in range(2))
+    print(f"cross-attn + softmax scaling: ours vs reference golden rel {err:.3e} (autocast-bf16 oracle: {ref_err:.3e})")
+    assert err <= 1.5 * ref_err + 2e-3, (err, ref_err)
+    sum(o.sum() for o in out).backward()
+    assert O.parity(m.multi_view_branches[1][0].cross_attn.projq.weight.grad, a["grad_projq"].to(DEV))[1] <= 5e-2
+    assert O.parity(m.multi_view_branches[0][1].attn.qkv.weight.grad, a["grad_qkv"].to(DEV))[1] <= 5e-2
     assert O.parity(feats[0].grad, a["grad_in0"].to(DEV))[1] <= 5e-2

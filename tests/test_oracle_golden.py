@@ -168,7 +168,7 @@ def test_encoder_manyar_golden():
            O.croco_encoder(sd, "encoder.", a["img"], cfg["depth"], cfg["heads"]), 2e-6)  # per-sample vs batched matmul rounding
 
 
-@pytest.mark.parametrize("name", ["global_attn_tiny", "global_attn_tiny_rope", "alternating_attn_tiny"])
+@pytest.mark.parametrize("name", ["global_attn_tiny", "global_attn_tiny_rope", "alternating_attn_tiny", "global_attn_tiny_scaled"])
 def test_self_attention_info_sharing_golden(name):
     """global / alternating attention transformers -- oracle == the reference's golden (fwd + bwd), and our
     parameter containers expose the reference's state-dict keys (incl. the `view_pos_table` buffer, first)."""
@@ -177,16 +177,35 @@ def test_self_attention_info_sharing_golden(name):
     cfg, a = load(name)
     m = getattr(U, cfg["cls"])(name="mv", input_embed_dim=cfg["C_in"], depth=cfg["depth"], dim=cfg["dim"], num_heads=cfg["heads"],
                                use_rand_idx_pe_for_non_reference_views=False,
-                               custom_positional_encoding=U.RoPE2D(freq=100.0) if cfg["rope"] else None)
+                               custom_positional_encoding=U.RoPE2D(freq=100.0) if cfg["rope"] else None,
+                               use_scalable_softmax=cfg.get("scaling", False), use_entropy_scaling=cfg.get("scaling", False))
+    sm = (True, True, 444, 1.4) if cfg.get("scaling") else None
     assert list(m.state_dict().keys()) == ["view_pos_table"] + list(cfg["shapes"].keys())
     assert m.use_pe_for_non_reference_views == cfg["pe_for_non_ref"]
     sd = {k: v.requires_grad_(True) for k, v in weights(cfg).items()}
     feats = [a[f"feat{v}"].clone().requires_grad_(True) for v in range(cfg["V"])]
     out = O.self_attention_info_sharing(sd, "", feats, cfg["depth"], cfg["heads"], alternating="Alternating" in cfg["cls"],
-                                        base=100.0 if cfg["rope"] else None, pe_for_non_ref=cfg["pe_for_non_ref"])
+                                        base=100.0 if cfg["rope"] else None, pe_for_non_ref=cfg["pe_for_non_ref"],
+                                        softmax_scaling=sm)
     for v in range(cfg["V"]):
         _close(out[v], a[f"out{v}"])
     sum(o.sum() for o in out).backward()
     _close(sd["self_attention_blocks.1.attn.qkv.weight"].grad, a["grad_qkv1"], 1e-4)
     _close(sd["proj_embed.weight"].grad, a["grad_proj_embed"], 1e-4)
     _close(feats[0].grad, a["grad_in0"], 1e-4)
+
+
+def test_cross_attention_softmax_scaling_golden():
+    """`use_scalable_softmax` + `use_entropy_scaling` in the cross-attention transformer."""
+    cfg, a = load("cross_attn_tiny_scaled")
+    sd = {k: v.requires_grad_(True) for k, v in weights(cfg).items()}
+    feats = [a["feat0"].clone().requires_grad_(True), a["feat1"].clone()]
+    out = O.info_sharing(sd, "", feats, cfg["depth"], cfg["heads"], softmax_scaling=tuple(cfg["softmax_scaling"]))
+    _close(out[0], a["out0"])
+    _close(out[1], a["out1"])
+    sum(o.sum() for o in out).backward()
+    _close(sd["multi_view_branches.1.0.cross_attn.projq.weight"].grad, a["grad_projq"], 1e-4)
+    _close(sd["multi_view_branches.0.1.attn.qkv.weight"].grad, a["grad_qkv"], 1e-4)
+    # the flags matter: without them the output differs
+    plain = O.info_sharing(sd, "", [f.detach() for f in feats], cfg["depth"], cfg["heads"])
+    assert O.parity(plain[0], a["out0"])[1] > 1e-3

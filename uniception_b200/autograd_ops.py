@@ -138,7 +138,7 @@ class AttentionFn(torch.autograd.Function):
     forward, inverse rotation fused into the backward kernels)."""
 
     @staticmethod
-    def forward(ctx, q_src, kv_src, B, Nq, Nk, H, q_off, k_off, v_off, qpos32, kpos32, table):
+    def forward(ctx, q_src, kv_src, B, Nq, Nk, H, q_off, k_off, v_off, qpos32, kpos32, table, scale=0.125):
         C = H * 64
         q2, kv2 = _act2d(q_src), _act2d(kv_src)
         q = q2[:, q_off:q_off + C]
@@ -150,7 +150,8 @@ class AttentionFn(torch.autograd.Function):
             base, f0, _ = table
             ops.rope2d_(q.view(B, Nq, H, 64), qpos32.view(B, Nq, 2).long(), base, f0)
             ops.rope2d_(k.view(B, Nk, H, 64), kpos32.view(B, Nk, 2).long(), base, f0)
-        o, lse = ops.attn_fwd(q, k, v, B, H, Nq, Nk, 0.125)
+        o, lse = ops.attn_fwd(q, k, v, B, H, Nq, Nk, scale)
+        ctx.scale = scale
         ctx.save_for_backward(q, k, v, o, lse, qpos32, kpos32, table[2] if table is not None else None)
         ctx.dims = (B, Nq, Nk, H, q_off, k_off, v_off, q2.shape, kv2.shape, q_src.shape, kv_src.shape, q_src is kv_src)
         return o.view(*q_src.shape[:-1], C)
@@ -163,10 +164,10 @@ class AttentionFn(torch.autograd.Function):
         d2 = _act2d(d_o)
         dq_src = torch.zeros(q2s, dtype=torch.bfloat16, device=d2.device)
         dkv_src = dq_src if same else torch.zeros(kv2s, dtype=torch.bfloat16, device=d2.device)
-        ops.attn_bwd(q, k, v, o, d2, lse, B, H, Nq, Nk, 0.125, dq_src[:, q_off:q_off + C], dkv_src[:, k_off:k_off + C],
+        ops.attn_bwd(q, k, v, o, d2, lse, B, H, Nq, Nk, ctx.scale, dq_src[:, q_off:q_off + C], dkv_src[:, k_off:k_off + C],
                      dkv_src[:, v_off:v_off + C], q_positions=qpos32 if tab is not None else None,
                      k_positions=kpos32 if tab is not None else None, rope_table=tab)
-        return (dq_src.view(qs), None if same else dkv_src.view(kvs)) + (None,) * 10
+        return (dq_src.view(qs), None if same else dkv_src.view(kvs)) + (None,) * 11
 
 
 # ------------------------------------------------------------------------------------------------
@@ -185,7 +186,8 @@ def layer_norm(x, norm: nn.LayerNorm):
     return LayerNormFn.apply(x, norm.weight, norm.bias, norm.eps)
 
 
-def attention(q_src, kv_src, B, Nq, Nk, H, q_off, k_off, v_off, qpos=None, kpos=None, rope=None):
+def attention(q_src, kv_src, B, Nq, Nk, H, q_off, k_off, v_off, qpos=None, kpos=None, rope=None, scale=0.125):
+    """scale: softmax scale (head_dim^-0.5, times the scalable-softmax / entropy-scaling query multipliers)."""
     fr = fusable_rope(rope)
     if rope is not None and fr is None:
         # arbitrary positional-encoding plugin: call it on [B,H,N,d] tensors under autograd, as the
@@ -196,13 +198,13 @@ def attention(q_src, kv_src, B, Nq, Nk, H, q_off, k_off, v_off, qpos=None, kpos=
         q4, k4 = rope(q4, qpos), rope(k4, kpos)
         q_r = q4.transpose(1, 2).reshape(B, Nq, C)
         kv_r = torch.cat((k4.transpose(1, 2).reshape(B, Nk, C), kv_src[..., v_off:v_off + C].reshape(B, Nk, C)), dim=-1)
-        return AttentionFn.apply(q_r, kv_r, B, Nq, Nk, H, 0, 0, C, None, None, None)
+        return AttentionFn.apply(q_r, kv_r, B, Nq, Nk, H, 0, 0, C, None, None, None, scale)
     if fr is None:
-        return AttentionFn.apply(q_src, kv_src, B, Nq, Nk, H, q_off, k_off, v_off, None, None, None)
+        return AttentionFn.apply(q_src, kv_src, B, Nq, Nk, H, q_off, k_off, v_off, None, None, None, scale)
     assert qpos is not None and kpos is not None
     base, f0 = fr
     num_pos = int(max(int(qpos.max()), int(kpos.max()))) + 1  # host sync: granular API only
     table = E.rope_table(num_pos, base, f0, q_src.device)
     q32 = qpos.reshape(-1, 2).to(torch.int32).contiguous()
     k32 = kpos.reshape(-1, 2).to(torch.int32).contiguous()
-    return AttentionFn.apply(q_src, kv_src, B, Nq, Nk, H, q_off, k_off, v_off, q32, k32, (base, f0, table))
+    return AttentionFn.apply(q_src, kv_src, B, Nq, Nk, H, q_off, k_off, v_off, q32, k32, (base, f0, table), scale)

@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import autograd_ops as A
+from .engine import attn_scale
 from .rope import fusable_rope
 
 
@@ -51,12 +52,15 @@ class Attention(nn.Module):
 
     def __init__(self, dim, rope=None, num_heads=8, qkv_bias=False, attn_drop=0.0, proj_drop=0.0, qk_norm=False,
                  custom_positional_encoding: Optional[Callable] = None, use_scalable_softmax=False, use_entropy_scaling=False,
-                 **_ignored):
+                 base_token_count_for_entropy_scaling=444, entropy_scaling_growth_factor=1.4, **_ignored):
         super().__init__()
         assert dim % num_heads == 0, "dim should be divisible by num_heads"
         _require(dim // num_heads == 64, f"head_dim {dim // num_heads} (only 64)")
-        _require(not qk_norm and not use_scalable_softmax and not use_entropy_scaling, "qk_norm / softmax scaling options")
+        _require(not qk_norm, "qk_norm")
         _require(attn_drop == 0.0 and proj_drop == 0.0, "attention dropout")
+        # softmax scaling by the token count (utils/transformer_blocks.py:231-241) folds into the kernels' scale
+        self.softmax_scaling = (use_scalable_softmax, use_entropy_scaling, base_token_count_for_entropy_scaling,
+                                entropy_scaling_growth_factor) if (use_scalable_softmax or use_entropy_scaling) else None
         self.num_heads = num_heads
         self.head_dim = dim // num_heads
         self.scale = self.head_dim ** -0.5
@@ -70,7 +74,8 @@ class Attention(nn.Module):
         if self.rope is not None:
             assert xpos is not None, "Positions of tokens (xpos) are a required input when using custom positional encoding"
         qkv = A.linear(x, self.qkv.weight, self.qkv.bias)
-        o = A.attention(qkv, qkv, B, N, N, self.num_heads, q_off=0, k_off=C, v_off=2 * C, qpos=xpos, kpos=xpos, rope=self.rope)
+        o = A.attention(qkv, qkv, B, N, N, self.num_heads, q_off=0, k_off=C, v_off=2 * C, qpos=xpos, kpos=xpos, rope=self.rope,
+                        scale=attn_scale(self.softmax_scaling, N))
         return A.linear(o, self.proj.weight, self.proj.bias, residual=residual)
 
 
@@ -98,12 +103,14 @@ class CrossAttention(nn.Module):
 
     def __init__(self, dim, num_heads=8, qkv_bias=False, qk_norm=False, attn_drop=0.0, proj_drop=0.0,
                  norm_layer=nn.LayerNorm, custom_positional_encoding=None, use_scalable_softmax=False,
-                 use_entropy_scaling=False, **_ignored):
+                 use_entropy_scaling=False, base_token_count_for_entropy_scaling=444, entropy_scaling_growth_factor=1.4, **_ignored):
         super().__init__()
         assert dim % num_heads == 0, "dim should be divisible by num_heads"
         _require(dim // num_heads == 64, f"head_dim {dim // num_heads} (only 64)")
-        _require(not qk_norm and not use_scalable_softmax and not use_entropy_scaling, "qk_norm / softmax scaling options")
+        _require(not qk_norm, "qk_norm")
         _require(attn_drop == 0.0 and proj_drop == 0.0, "attention dropout")
+        self.softmax_scaling = (use_scalable_softmax, use_entropy_scaling, base_token_count_for_entropy_scaling,
+                                entropy_scaling_growth_factor) if (use_scalable_softmax or use_entropy_scaling) else None
         self.num_heads = num_heads
         self.head_dim = dim // num_heads
         self.scale = self.head_dim ** -0.5
@@ -121,7 +128,7 @@ class CrossAttention(nn.Module):
         v = A.linear(value, self.projv.weight, self.projv.bias)
         kv = torch.cat((k, v), dim=-1)
         o = A.attention(q, kv, B, Nq, Nk, self.num_heads, q_off=0, k_off=0, v_off=C, qpos=qpos, kpos=kpos,
-                        rope=self.custom_positional_encoding)
+                        rope=self.custom_positional_encoding, scale=attn_scale(self.softmax_scaling, Nq))
         return A.linear(o, self.proj.weight, self.proj.bias, residual=residual)
 
 
@@ -138,7 +145,9 @@ class CrossAttentionBlock(nn.Module):
         _require(mlp_layer is Mlp, "a custom mlp_layer")
         common = dict(num_heads=num_heads, qkv_bias=qkv_bias, qk_norm=qk_norm, attn_drop=attn_drop, proj_drop=proj_drop,
                       custom_positional_encoding=custom_positional_encoding, use_scalable_softmax=use_scalable_softmax,
-                      use_entropy_scaling=use_entropy_scaling)
+                      use_entropy_scaling=use_entropy_scaling,
+                      base_token_count_for_entropy_scaling=base_token_count_for_entropy_scaling,
+                      entropy_scaling_growth_factor=entropy_scaling_growth_factor)
         self.norm1 = norm_layer(dim)
         self.attn = Attention(dim, **common)
         self.ls1 = nn.Identity()

@@ -17,6 +17,7 @@ fp32 LayerNorm statistics, fp32 softmax, fp32 RoPE angle math, fp32 head output 
 from __future__ import annotations
 
 import contextlib
+import math
 import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -141,25 +142,41 @@ def bias_sink(pk: ParamPack, linear_name: Optional[str], like: Optional[torch.Te
 # ------------------------------------------------------------------------------------------------
 # self-attention + MLP sub-blocks (shared by encoder and decoder blocks)
 # ------------------------------------------------------------------------------------------------
-def self_attn_fwd(pk, p, x, B, N, H, rope: Optional[Rope], norm: str, saved: list):
+def attn_scale(softmax_scaling, n_queries: int, head_dim: int = 64) -> float:
+    """head_dim^-0.5 times the query multipliers of `use_scalable_softmax` (log N, utils/transformer_blocks.py:231-233,
+    :360-362) and `use_entropy_scaling` (sqrt(growth * log N / log base), :235-241, :364-370).  Both only multiply q by a
+    scalar that depends on the token count, so they fold into the attention kernels' `scale` (forward, dq and dk alike).
+    softmax_scaling: None or (use_scalable_softmax, use_entropy_scaling, base_token_count, growth_factor)."""
+    s = head_dim ** -0.5
+    if softmax_scaling:
+        use_ss, use_es, base, growth = softmax_scaling
+        if use_ss:
+            s *= math.log(n_queries)
+        if use_es:
+            s *= math.sqrt(growth * math.log(n_queries) / math.log(base))
+    return s
+
+
+
+def self_attn_fwd(pk, p, x, B, N, H, rope: Optional[Rope], norm: str, saved: list, scale: float = 0.125):
     """x += proj(attn(rope(qkv(LN(x)))))  -- returns the new residual stream."""
     C = H * 64
     h1, mean, rstd = ln_fwd(pk, p + norm, x)
     qkv = linear_fwd(pk, p + "attn.qkv", h1, rope=rope, rope_cols=2 * C)
-    o, lse = ops.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, H, N, N, 0.125)
+    o, lse = ops.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, H, N, N, scale)
     x2 = linear_fwd(pk, p + "attn.proj", o, residual=x)
-    saved.append((x, mean, rstd, h1, qkv, o, lse))
+    saved.append((x, mean, rstd, h1, qkv, o, lse, scale))
     return x2
 
 
 def self_attn_bwd(pk, p, dx2, B, N, H, rope: Optional[Rope], norm: str, saved, bias_done=False, out_sink=None):
     """dx2: gradient w.r.t. the sub-block output (bf16).  Returns gradient w.r.t. its input.
     bias_done: colsum(dx2) already sits in attn.proj.bias.grad; out_sink: bias-gradient buffer fed by the returned dx."""
-    x, mean, rstd, h1, qkv, o, lse = saved
+    x, mean, rstd, h1, qkv, o, lse, scale = saved
     C = H * 64
     d_o = linear_bwd(pk, p + "attn.proj", dx2, o, bias_done=bias_done)
     dqkv = torch.empty_like(qkv)
-    ops.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, d_o, lse, B, H, N, N, 0.125,
+    ops.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, d_o, lse, B, H, N, N, scale,
                  dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:],
                  q_positions=rope.pos if rope is not None else None, k_positions=rope.pos if rope is not None else None,
                  rope_table=rope.table if rope is not None else None)
@@ -338,7 +355,8 @@ class ViewStreams:
 # ------------------------------------------------------------------------------------------------
 # two-view (N-view) cross-attention decoder (info_sharing/cross_attention_transformer.py:191-275)
 # ------------------------------------------------------------------------------------------------
-def _cross_fwd(pk, p, x, y, B, Nq, Nk, H, rope_q: Optional[Rope], rope_k: Optional[Rope], saved: list, has_norm_y: bool):
+def _cross_fwd(pk, p, x, y, B, Nq, Nk, H, rope_q: Optional[Rope], rope_k: Optional[Rope], saved: list, has_norm_y: bool,
+               scale: float = 0.125):
     C = H * 64
     if has_norm_y:
         yn, ymean, yrstd = ln_fwd(pk, p + "norm_y", y)
@@ -350,20 +368,20 @@ def _cross_fwd(pk, p, x, y, B, Nq, Nk, H, rope_q: Optional[Rope], rope_k: Option
     wkv = pk.w16_rows(p + "cross_attn.projk.weight", p + "cross_attn.projv.weight")
     bkv = pk.w32_span(p + "cross_attn.projk.bias", p + "cross_attn.projv.bias")
     kv = linear_fwd(pk, "", yn, rope=rope_k, rope_cols=C, w16=wkv, bias=bkv)
-    o, lse = ops.attn_fwd(q, kv[:, :C], kv[:, C:], B, H, Nq, Nk, 0.125)
+    o, lse = ops.attn_fwd(q, kv[:, :C], kv[:, C:], B, H, Nq, Nk, scale)
     x2 = linear_fwd(pk, p + "cross_attn.proj", o, residual=x)
-    saved.append((x, mean, rstd, h2, q, kv, o, lse, y, yn, ymean, yrstd))
+    saved.append((x, mean, rstd, h2, q, kv, o, lse, y, yn, ymean, yrstd, scale))
     return x2
 
 
 def _cross_bwd(pk, p, dx2, B, Nq, Nk, H, rope_q, rope_k, saved, has_norm_y: bool, bias_done=False, out_sink=None):
     """Returns (dx, d_yn): gradient w.r.t. the block's own stream and w.r.t. norm_y(y) (bf16)."""
-    x, mean, rstd, h2, q, kv, o, lse, y, yn, ymean, yrstd = saved
+    x, mean, rstd, h2, q, kv, o, lse, y, yn, ymean, yrstd, scale = saved
     C = H * 64
     d_o = linear_bwd(pk, p + "cross_attn.proj", dx2, o, bias_done=bias_done)
     dq = torch.empty_like(q)
     dkv = torch.empty_like(kv)
-    ops.attn_bwd(q, kv[:, :C], kv[:, C:], o, d_o, lse, B, H, Nq, Nk, 0.125, dq, dkv[:, :C], dkv[:, C:],
+    ops.attn_bwd(q, kv[:, :C], kv[:, C:], o, d_o, lse, B, H, Nq, Nk, scale, dq, dkv[:, :C], dkv[:, C:],
                  q_positions=rope_q.pos if rope_q is not None else None,
                  k_positions=rope_k.pos if rope_k is not None else None,
                  rope_table=rope_q.table if rope_q is not None else None)
@@ -378,8 +396,9 @@ def _cross_bwd(pk, p, dx2, B, Nq, Nk, H, rope_q, rope_k, saved, has_norm_y: bool
 
 def decoder_fwd(pk: ParamPack, p: str, toks: List[torch.Tensor], B: int, h: int, w: int, depth: int, heads: int,
                 rope_base: Optional[float], rope_f0: float = 1.0, take: Sequence[int] = (), norm_intermediate: bool = True,
-                has_proj_embed: bool = True, has_norm_y: bool = True):
-    """toks: per-view bf16 [B*N, C_in].  Returns (per-view normalised bf16 [B*N, dim], intermediates, saved)."""
+                has_proj_embed: bool = True, has_norm_y: bool = True, softmax_scaling=None):
+    """toks: per-view bf16 [B*N, C_in].  Returns (per-view normalised bf16 [B*N, dim], intermediates, saved).
+    softmax_scaling: see `attn_scale` (the token count is the number of QUERY tokens, N, for self- and cross-attention)."""
     nv = len(toks)
     N = h * w
     dev = toks[0].device
@@ -405,8 +424,9 @@ def decoder_fwd(pk: ParamPack, p: str, toks: List[torch.Tensor], B: int, h: int,
                     y = xs[1 - v]
                 else:  # other views concatenated along tokens, per batch element
                     y = torch.cat([xs[i].view(B, N, -1) for i in range(nv) if i != v], dim=1).reshape(B * N * (nv - 1), -1)
-                x = self_attn_fwd(pk, bp, xs[v], B, N, heads, rope, "norm1", bs)
-                x = _cross_fwd(pk, bp, x, y, B, N, N * (nv - 1), heads, rope, rope_o, bs, has_norm_y)
+                sc = attn_scale(softmax_scaling, N)
+                x = self_attn_fwd(pk, bp, xs[v], B, N, heads, rope, "norm1", bs, sc)
+                x = _cross_fwd(pk, bp, x, y, B, N, N * (nv - 1), heads, rope, rope_o, bs, has_norm_y, sc)
                 x = mlp_fwd(pk, bp, x, "norm3", bs)
             new.append(x)
             lvl.append(bs)
@@ -544,7 +564,7 @@ def decoder_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[torch.Te
 # ------------------------------------------------------------------------------------------------
 def mv_self_attn_fwd(pk: ParamPack, p: str, toks: List[torch.Tensor], B: int, h: int, w: int, depth: int, heads: int,
                      rope_base: Optional[float], rope_f0: float, alternating: bool, view_pe: Optional[torch.Tensor],
-                     has_proj_embed: bool):
+                     has_proj_embed: bool, softmax_scaling=None):
     """toks: per-view bf16 [B*N, C_in]; view_pe: fp32 [V, dim] view-index encodings added after proj_embed (or None).
     Rows are ordered (batch, view, token), so the SAME buffer is a [B, V*N] sequence set for the global layers and a
     [B*V, N] one for the frame-level layers of the alternating variant: no data movement between the two."""
@@ -564,7 +584,7 @@ def mv_self_attn_fwd(pk: ParamPack, p: str, toks: List[torch.Tensor], B: int, h:
         Bb, Nn = (B * nv, N) if frame else (B, nv * N)
         bs: list = []
         bp = f"{p}self_attention_blocks.{i}."
-        x = self_attn_fwd(pk, bp, x, Bb, Nn, heads, rope, "norm1", bs)
+        x = self_attn_fwd(pk, bp, x, Bb, Nn, heads, rope, "norm1", bs, attn_scale(softmax_scaling, Nn))
         x = mlp_fwd(pk, bp, x, "norm2", bs)
         saved["blocks"].append(bs)
     y, mean, rstd = ln_fwd(pk, p + "norm", x)

@@ -53,7 +53,7 @@ class DecoderFn(torch.autograd.Function):
         toks = [t.contiguous() if t.dtype == torch.bfloat16 else t.to(torch.bfloat16).contiguous() for t in tensors[:nv]]
         outs, inter, saved = E.decoder_fwd(pk, prefix, toks, cfg["B"], cfg["h"], cfg["w"], cfg["depth"], cfg["heads"],
                                            cfg["rope_base"], cfg["rope_f0"], cfg.get("take", ()), cfg.get("norm_intermediate", True),
-                                           cfg["has_proj_embed"], cfg["has_norm_y"])
+                                           cfg["has_proj_embed"], cfg["has_norm_y"], cfg.get("softmax_scaling"))
         ctx.pk, ctx.prefix, ctx.cfg, ctx.saved, ctx.nv = pk, prefix, cfg, saved, nv
         ctx.n_levels = len(inter)
         ctx.in_dtypes = [t.dtype for t in tensors[:nv]]
@@ -81,7 +81,8 @@ class MultiViewSelfAttnFn(torch.autograd.Function):
     def forward(ctx, pk: ParamPack, prefix: str, cfg: dict, nv: int, *tensors):
         toks = [t.contiguous() if t.dtype == torch.bfloat16 else t.to(torch.bfloat16).contiguous() for t in tensors[:nv]]
         outs, saved = E.mv_self_attn_fwd(pk, prefix, toks, cfg["B"], cfg["h"], cfg["w"], cfg["depth"], cfg["heads"], cfg["rope_base"],
-                                         cfg["rope_f0"], cfg["alternating"], cfg["view_pe"], cfg["has_proj_embed"])
+                                         cfg["rope_f0"], cfg["alternating"], cfg["view_pe"], cfg["has_proj_embed"],
+                                         cfg.get("softmax_scaling"))
         ctx.pk, ctx.prefix, ctx.cfg, ctx.saved, ctx.nv = pk, prefix, cfg, saved, nv
         ctx.in_dtypes = [t.dtype for t in tensors[:nv]]
         return tuple(outs)

@@ -128,7 +128,9 @@ class MultiViewCrossAttentionTransformer(UniCeptionInfoSharingBase):
                                  proj_drop=proj_drop, attn_drop=attn_drop, init_values=init_values, drop_path=drop_path,
                                  act_layer=act_layer, norm_layer=norm_layer, mlp_layer=mlp_layer,
                                  custom_positional_encoding=custom_positional_encoding, norm_cross_tokens=norm_cross_tokens,
-                                 use_scalable_softmax=use_scalable_softmax, use_entropy_scaling=use_entropy_scaling)
+                                 use_scalable_softmax=use_scalable_softmax, use_entropy_scaling=use_entropy_scaling,
+                                 base_token_count_for_entropy_scaling=base_token_count_for_entropy_scaling,
+                                 entropy_scaling_growth_factor=entropy_scaling_growth_factor)
              for _ in range(depth)]
         )
         self.multi_view_branches = nn.ModuleList([blocks])
@@ -159,9 +161,12 @@ class MultiViewCrossAttentionTransformer(UniCeptionInfoSharingBase):
     # ---- engine entry ----
     def _cfg(self, B, h, w, take=(), norm_intermediate=True):
         fr = fusable_rope(self.custom_positional_encoding)
+        sm = (self.use_scalable_softmax, self.use_entropy_scaling, self.base_token_count_for_entropy_scaling,
+              self.entropy_scaling_growth_factor) if (self.use_scalable_softmax or self.use_entropy_scaling) else None
         return dict(B=B, h=h, w=w, depth=self.depth, heads=self.num_heads, rope_base=fr[0] if fr else None,
                     rope_f0=fr[1] if fr else 1.0, take=tuple(take), norm_intermediate=norm_intermediate,
-                    has_proj_embed=isinstance(self.proj_embed, nn.Linear), has_norm_y=self.norm_cross_tokens)
+                    has_proj_embed=isinstance(self.proj_embed, nn.Linear), has_norm_y=self.norm_cross_tokens,
+                    softmax_scaling=sm)
 
     def forward_tokens(self, toks: List[torch.Tensor], B: int, h: int, w: int, pk: ParamPack, prefix: str, take=(),
                        norm_intermediate=True):
@@ -267,8 +272,10 @@ class MultiViewGlobalAttentionTransformer(UniCeptionInfoSharingBase):
         if use_pe_for_non_reference_views is None:
             use_pe_for_non_reference_views = self._PE_NON_REF_DEFAULT
         check_norm_layer(norm_layer)
-        if qk_norm or init_values or drop_path or proj_drop or attn_drop or use_scalable_softmax or use_entropy_scaling:
-            raise NotImplementedError("uniception_b200: qk_norm / LayerScale / dropout / softmax-scaling block options (SURVEY.md 8f4)")
+        if qk_norm or init_values or drop_path or proj_drop or attn_drop:
+            raise NotImplementedError("uniception_b200: qk_norm / LayerScale / dropout block options (SURVEY.md 8f4)")
+        self.softmax_scaling = (use_scalable_softmax, use_entropy_scaling, base_token_count_for_entropy_scaling,
+                                entropy_scaling_growth_factor) if (use_scalable_softmax or use_entropy_scaling) else None
         if gradient_checkpointing:
             raise NotImplementedError("uniception_b200: gradient checkpointing is not needed (activations fit 180 GB) and not built")
         self.input_embed_dim = input_embed_dim
@@ -325,7 +332,7 @@ class MultiViewGlobalAttentionTransformer(UniCeptionInfoSharingBase):
         fr = fusable_rope(self.custom_positional_encoding)
         cfg = dict(B=B, h=h, w=w, depth=self.depth, heads=self.num_heads, rope_base=fr[0] if fr else None,
                    rope_f0=fr[1] if fr else 1.0, alternating=self.ALTERNATING, view_pe=self._view_pe(len(toks)),
-                   has_proj_embed=isinstance(self.proj_embed, nn.Linear))
+                   has_proj_embed=isinstance(self.proj_embed, nn.Linear), softmax_scaling=self.softmax_scaling)
         return list(fused.MultiViewSelfAttnFn.apply(pk, prefix, cfg, len(toks), *toks, *pk.params.values()))
 
     def forward(self, model_input: MultiViewTransformerInput) -> MultiViewTransformerOutput:
