@@ -358,12 +358,15 @@ def view_sinusoid_table(n_position: int, d_hid: int, base: float = 10000.0) -> T
 
 def self_attention_info_sharing(sd: SD, p: str, feats: List[Tensor], depth: int, heads: int, *, alternating: bool = False,
                                 base: Optional[float] = None, distinguish_ref: bool = True, pe_for_non_ref: bool = True,
-                                max_num_views_for_pe: int = 1000, softmax_scaling=None) -> List[Tensor]:
+                                max_num_views_for_pe: int = 1000, softmax_scaling=None, indices: Optional[Sequence[int]] = None,
+                                norm_intermediate: bool = True):
     """`MultiViewGlobalAttentionTransformer.forward` (global_attention_transformer.py:224-462) and, with
     `alternating=True`, `MultiViewAlternatingAttentionTransformer.forward` (alternating_attention_transformer.py:397-442:
     even depths attend over all V*N tokens, odd depths inside each view), for `use_rand_idx_pe_for_non_reference_views=False`
     and no additional tokens.  Blocks are `SelfAttentionBlock`s (utils/transformer_blocks.py:415-514): without LayerScale /
-    DropPath that is `encoder_block`'s arithmetic.  base: RoPE frequency base when `custom_positional_encoding="rope"`, else None."""
+    DropPath that is `encoder_block`'s arithmetic.  base: RoPE frequency base when `custom_positional_encoding="rope"`, else None.
+    indices: the IFR variants (global_attention_transformer.py:766-774, :880-897): also collect `norm(x)` (or x) after those
+    depths and return (final per-view maps, [per-view maps per taken depth])."""
     V = len(feats)
     B, C_in, h, w = feats[0].shape
     N = h * w
@@ -379,6 +382,7 @@ def self_attention_info_sharing(sd: SD, p: str, feats: List[Tensor], depth: int,
             pe[1:] = tab[1:V]
         x = x + pe.repeat_interleave(N, dim=0)[None]
     pos = patch_positions(B, h, w, x.device).repeat(1, V, 1) if base is not None else None
+    inter = []
     for i in range(depth):
         bp = f"{p}self_attention_blocks.{i}."
         if alternating and i % 2 == 1:
@@ -387,9 +391,17 @@ def self_attention_info_sharing(sd: SD, p: str, feats: List[Tensor], depth: int,
             x = encoder_block(sd, bp, xf, pf, heads, base, softmax_scaling).reshape(B, V * N, dim)
         else:
             x = encoder_block(sd, bp, x, pos, heads, base, softmax_scaling)
+        if indices is not None and i in indices:
+            inter.append(layer_norm(x, sd[p + "norm.weight"], sd[p + "norm.bias"]) if norm_intermediate else x)
     x = layer_norm(x, sd[p + "norm.weight"], sd[p + "norm.bias"])
-    x = x.reshape(B, V, h, w, dim).permute(0, 1, 4, 2, 3)
-    return [x[:, v].contiguous() for v in range(V)]
+
+    def views(t):
+        t = t.reshape(B, V, h, w, dim).permute(0, 1, 4, 2, 3)
+        return [t[:, v].contiguous() for v in range(V)]
+
+    if indices is None:
+        return views(x)
+    return views(x), [views(t) for t in inter]
 
 # --------------------------------------------------------------------------------------
 # DPT head (prediction_heads/dpt.py:94-232, :271-311; libs/croco/dpt_block.py:114-255)

@@ -315,9 +315,10 @@ def golden_encoder_manyar(name, seed, C=128, depth=2, heads=2, hw=(32, 48), B=3)
 
 
 def golden_self_attention_info_sharing(name, cls_name, seed, rope, V=2, B=2, hw=(3, 4), C_in=192, dim=128, depth=4, heads=2,
-                                       scaling=False):
+                                       scaling=False, indices=None, norm_intermediate=True):
     """`MultiViewGlobalAttentionTransformer` / `MultiViewAlternatingAttentionTransformer` on V views, with
-    sequential view-index positional encodings (the default draws them at random) and optional RoPE."""
+    sequential view-index positional encodings (the default draws them at random) and optional RoPE.  With `indices` the
+    class is the `...IFR` variant and the loss weights intermediate level k by (0.5 + k)."""
     from uniception.models.info_sharing import alternating_attention_transformer as AT, global_attention_transformer as GT
     from uniception.models.info_sharing.base import MultiViewTransformerInput
 
@@ -327,7 +328,8 @@ def golden_self_attention_info_sharing(name, cls_name, seed, rope, V=2, B=2, hw=
     # a callable, not the string "rope": the alternating transformer does not resolve the string (it would call a str)
     m = cls(name="mv", input_embed_dim=C_in, depth=depth, dim=dim, num_heads=heads, use_rand_idx_pe_for_non_reference_views=False,
             custom_positional_encoding=RoPE2D(freq=100.0) if rope else None,
-            use_scalable_softmax=scaling, use_entropy_scaling=scaling)
+            use_scalable_softmax=scaling, use_entropy_scaling=scaling,
+            **(dict(indices=list(indices), norm_intermediate=norm_intermediate) if indices is not None else {}))
     sm = (True, True, m.base_token_count_for_entropy_scaling, m.entropy_scaling_growth_factor) if scaling else None
     # seeded parameters only: `view_pos_table` is a persistent BUFFER (the sinusoid table), not a weight
     shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if k != "view_pos_table"}
@@ -335,25 +337,39 @@ def golden_self_attention_info_sharing(name, cls_name, seed, rope, V=2, B=2, hw=
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     g = torch.Generator().manual_seed(seed + 1)
     feats = [torch.randn(B, C_in, *hw, generator=g).requires_grad_(True) for _ in range(V)]
-    out = m(MultiViewTransformerInput(features=feats)).features
-    sum(o.sum() for o in out).backward()
+    res = m(MultiViewTransformerInput(features=feats))
+    inter = []
+    if indices is not None:
+        res, inter = res
+        inter = [lvl.features for lvl in inter]
+    out = res.features
+    (sum(o.sum() for o in out) + sum((0.5 + k) * sum(t.sum() for t in lvl) for k, lvl in enumerate(inter))).backward()
     params = dict(m.named_parameters())
     osd = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "view_pos_table"}
     of = [f.detach().clone().requires_grad_(True) for f in feats]
     oo = O.self_attention_info_sharing(osd, "", of, depth, heads, alternating="Alternating" in cls_name, base=100.0 if rope else None,
                                        distinguish_ref=m.distinguish_ref_and_non_ref_views, pe_for_non_ref=m.use_pe_for_non_reference_views,
-                                       softmax_scaling=sm)
+                                       softmax_scaling=sm, indices=indices, norm_intermediate=norm_intermediate)
+    oi = []
+    if indices is not None:
+        oo, oi = oo
     for v in range(V):
         _check(f"{name} view{v}", oo[v], out[v])
-    sum(o.sum() for o in oo).backward()
+    for k, lvl in enumerate(oi):
+        for v in range(V):
+            _check(f"{name} inter{k} view{v}", lvl[v], inter[k][v])
+    (sum(o.sum() for o in oo) + sum((0.5 + k) * sum(t.sum() for t in lvl) for k, lvl in enumerate(oi))).backward()
     k0 = "self_attention_blocks.1.attn.qkv.weight"
     _check(f"{name} grad {k0}", osd[k0].grad, params[k0].grad, 1e-4)
     _check(f"{name} grad input0", of[0].grad, feats[0].grad, 1e-4)
     arrays = {f"feat{v}": feats[v].detach() for v in range(V)}
     arrays.update({f"out{v}": out[v] for v in range(V)})
-    arrays.update(grad_qkv1=params[k0].grad, grad_proj_embed=params["proj_embed.weight"].grad, grad_in0=feats[0].grad)
+    arrays.update({f"inter{k}_{v}": inter[k][v] for k in range(len(inter)) for v in range(V)})
+    arrays.update(grad_qkv1=params[k0].grad, grad_proj_embed=params["proj_embed.weight"].grad, grad_in0=feats[0].grad,
+                  grad_norm_w=params["norm.weight"].grad, grad_fc2_b1=params["self_attention_blocks.1.mlp.fc2.bias"].grad)
     _save(name, dict(cls=cls_name, seed=seed, rope=bool(rope), V=V, B=B, hw=list(hw), C_in=C_in, dim=dim, depth=depth, heads=heads,
                      pe_for_non_ref=bool(m.use_pe_for_non_reference_views), scaling=bool(scaling),
+                     indices=list(indices) if indices is not None else None, norm_intermediate=bool(norm_intermediate),
                      shapes={k: list(v) for k, v in shapes.items()}), arrays)
 
 
@@ -409,6 +425,10 @@ def main():
     golden_self_attention_info_sharing("alternating_attn_tiny", "MultiViewAlternatingAttentionTransformer", seed=53, rope=True)
     golden_self_attention_info_sharing("global_attn_tiny_scaled", "MultiViewGlobalAttentionTransformer", seed=54, rope=True, scaling=True)
     golden_cross_attention_scaled("cross_attn_tiny_scaled", seed=55)
+    golden_self_attention_info_sharing("global_attn_tiny_ifr", "MultiViewGlobalAttentionTransformerIFR", seed=56, rope=True,
+                                       indices=[1, 3])
+    golden_self_attention_info_sharing("alternating_attn_tiny_ifr", "MultiViewAlternatingAttentionTransformerIFR", seed=57, rope=True,
+                                       V=3, indices=[0, 2], norm_intermediate=False)
 
 
 if __name__ == "__main__":

@@ -383,6 +383,48 @@ def test_self_attention_info_sharing_vs_reference_golden(name):
     assert O.parity(feats[0].grad, a["grad_in0"].to(DEV))[1] <= 5e-2
 
 
+@pytest.mark.parametrize("name", ["global_attn_tiny_ifr", "alternating_attn_tiny_ifr"])
+def test_self_attention_info_sharing_ifr_vs_reference_golden(name):
+    """`MultiView{Global,Alternating}AttentionTransformerIFR` on the B200 engine vs the reference's golden final
+    maps, tapped intermediates (final-normed / raw) and gradients (tapped depths take the un-fused bias-gradient path)."""
+    cfg, a = load(name)
+    m = getattr(U, cfg["cls"])(name="mv", input_embed_dim=cfg["C_in"], depth=cfg["depth"], dim=cfg["dim"], num_heads=cfg["heads"],
+                               use_rand_idx_pe_for_non_reference_views=False, custom_positional_encoding=U.RoPE2D(freq=100.0),
+                               indices=cfg["indices"], norm_intermediate=cfg["norm_intermediate"])
+    m.load_state_dict(weights(cfg), strict=False)
+    m = m.to(DEV)
+    V = cfg["V"]
+    feats = [a[f"feat{v}"].to(DEV).requires_grad_(True) for v in range(V)]
+    final, inter = m(U.MultiViewTransformerInput(features=feats))
+    assert len(inter) == len(cfg["indices"])
+    sd = {k: v.to(DEV) for k, v in weights(cfg).items()}
+    fin = [f.detach() for f in feats]
+
+    def oracle_all():
+        o, it = O.self_attention_info_sharing(sd, "", fin, cfg["depth"], cfg["heads"], alternating="Alternating" in cfg["cls"],
+                                              base=100.0, pe_for_non_ref=cfg["pe_for_non_ref"], indices=cfg["indices"],
+                                              norm_intermediate=cfg["norm_intermediate"])
+        return o + [t for lvl in it for t in lvl]
+
+    ref_err = max(_autocast_err(oracle_all))
+    ours = list(final.features) + [t for lvl in inter for t in lvl.features]
+    gold = [a[f"out{v}"] for v in range(V)] + [a[f"inter{k}_{v}"] for k in range(len(inter)) for v in range(V)]
+    err = max(O.parity(x, g.to(DEV))[1] for x, g in zip(ours, gold))
+    print(f"{name}: ours vs reference golden rel {err:.3e} (autocast-bf16 oracle: {ref_err:.3e})")
+    assert err <= 1.5 * ref_err + 2e-3, (err, ref_err)
+    (sum(o.sum() for o in final.features)
+     + sum((0.5 + k) * sum(t.sum() for t in lvl.features) for k, lvl in enumerate(inter))).backward()
+    assert O.parity(m.self_attention_blocks[1].attn.qkv.weight.grad, a["grad_qkv1"].to(DEV))[1] <= 5e-2
+    assert O.parity(m.norm.weight.grad, a["grad_norm_w"].to(DEV))[1] <= 5e-2
+    assert O.parity(m.self_attention_blocks[1].mlp.fc2.bias.grad, a["grad_fc2_b1"].to(DEV))[1] <= 5e-2
+    assert O.parity(m.proj_embed.weight.grad, a["grad_proj_embed"].to(DEV))[1] <= 5e-2
+    assert O.parity(feats[0].grad, a["grad_in0"].to(DEV))[1] <= 5e-2
+    # intermediates_only returns just the list
+    m.intermediates_only = True
+    only = m(U.MultiViewTransformerInput(features=[f.detach() for f in feats]))
+    assert isinstance(only, list) and len(only) == len(cfg["indices"])
+
+
 def test_cross_attention_softmax_scaling_vs_reference_golden():
     """`MultiViewCrossAttentionTransformer(use_scalable_softmax=True, use_entropy_scaling=True)`: the
     token-count query multipliers fold into the attention kernels' scale (forward, dq, dk)."""

@@ -195,6 +195,36 @@ def test_self_attention_info_sharing_golden(name):
     _close(feats[0].grad, a["grad_in0"], 1e-4)
 
 
+@pytest.mark.parametrize("name", ["global_attn_tiny_ifr", "alternating_attn_tiny_ifr"])
+def test_self_attention_info_sharing_ifr_golden(name):
+    """the intermediate-feature-returner variants -- oracle == reference golden for the final maps, the tapped
+    intermediates (normed and raw) and the gradients of a loss that weights every output."""
+    import uniception_b200 as U
+
+    cfg, a = load(name)
+    m = getattr(U, cfg["cls"])(name="mv", input_embed_dim=cfg["C_in"], depth=cfg["depth"], dim=cfg["dim"], num_heads=cfg["heads"],
+                               use_rand_idx_pe_for_non_reference_views=False, custom_positional_encoding=U.RoPE2D(freq=100.0),
+                               indices=cfg["indices"], norm_intermediate=cfg["norm_intermediate"])
+    assert list(m.state_dict().keys()) == ["view_pos_table"] + list(cfg["shapes"].keys())
+    assert isinstance(m, U.IntermediateFeatureReturner) and m.use_pe_for_non_reference_views == cfg["pe_for_non_ref"]
+    assert U.INFO_SHARING_CLASSES["alternating_attention" if "Alternating" in cfg["cls"] else "global_attention"][1] is type(m)
+    sd = {k: v.requires_grad_(True) for k, v in weights(cfg).items()}
+    feats = [a[f"feat{v}"].clone().requires_grad_(True) for v in range(cfg["V"])]
+    out, inter = O.self_attention_info_sharing(sd, "", feats, cfg["depth"], cfg["heads"], alternating="Alternating" in cfg["cls"],
+                                               base=100.0, pe_for_non_ref=cfg["pe_for_non_ref"], indices=cfg["indices"],
+                                               norm_intermediate=cfg["norm_intermediate"])
+    assert len(inter) == len(cfg["indices"])
+    for v in range(cfg["V"]):
+        _close(out[v], a[f"out{v}"])
+        for k in range(len(inter)):
+            _close(inter[k][v], a[f"inter{k}_{v}"])
+    (sum(o.sum() for o in out) + sum((0.5 + k) * sum(t.sum() for t in lvl) for k, lvl in enumerate(inter))).backward()
+    _close(sd["self_attention_blocks.1.attn.qkv.weight"].grad, a["grad_qkv1"], 1e-4)
+    _close(sd["norm.weight"].grad, a["grad_norm_w"], 1e-4)
+    _close(sd["self_attention_blocks.1.mlp.fc2.bias"].grad, a["grad_fc2_b1"], 1e-4)
+    _close(feats[0].grad, a["grad_in0"], 1e-4)
+
+
 def test_cross_attention_softmax_scaling_golden():
     """`use_scalable_softmax` + `use_entropy_scaling` in the cross-attention transformer."""
     cfg, a = load("cross_attn_tiny_scaled")

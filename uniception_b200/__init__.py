@@ -13,12 +13,13 @@ from . import _lib  # noqa: F401  (fails loudly when the CUDA extension is missi
 from . import checkpoints  # noqa: F401  (original DUSt3R / CroCo checkpoint -> UniCeption-format state dicts)
 from .dust3r import DUSt3R, interleave, is_symmetrized  # noqa: F401
 from .encoders import (  # noqa: F401
-    ENCODER_CONFIGS, CroCoEncoder, CroCoIntermediateFeatureReturner, ManyAR_PatchEmbed, ViTEncoderInput, ViTEncoderOutput,
+    ENCODER_CONFIGS, CroCoEncoder, CroCoIntermediateFeatureReturner, IntermediateFeatureReturner, ManyAR_PatchEmbed, ViTEncoderInput, ViTEncoderOutput,
     encoder_factory, feature_returner_encoder_factory, feature_take_indices,
 )
 from .info_sharing import (  # noqa: F401
-    INFO_SHARING_CLASSES, MultiViewAlternatingAttentionTransformer, MultiViewCrossAttentionTransformer,
-    MultiViewCrossAttentionTransformerIFR, MultiViewGlobalAttentionTransformer, MultiViewTransformerInput, MultiViewTransformerOutput,
+    INFO_SHARING_CLASSES, MultiViewAlternatingAttentionTransformer, MultiViewAlternatingAttentionTransformerIFR,
+    MultiViewCrossAttentionTransformer, MultiViewCrossAttentionTransformerIFR, MultiViewGlobalAttentionTransformer,
+    MultiViewGlobalAttentionTransformerIFR, MultiViewTransformerInput, MultiViewTransformerOutput,
 )
 from .prediction_heads import (  # noqa: F401
     AdaptorInput, ConfidenceAdaptor, DepthAdaptor, LinearFeature, PixelTaskOutput, PointMapAdaptor,

@@ -564,10 +564,12 @@ def decoder_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[torch.Te
 # ------------------------------------------------------------------------------------------------
 def mv_self_attn_fwd(pk: ParamPack, p: str, toks: List[torch.Tensor], B: int, h: int, w: int, depth: int, heads: int,
                      rope_base: Optional[float], rope_f0: float, alternating: bool, view_pe: Optional[torch.Tensor],
-                     has_proj_embed: bool, softmax_scaling=None):
+                     has_proj_embed: bool, softmax_scaling=None, take: Sequence[int] = (), norm_intermediate: bool = True):
     """toks: per-view bf16 [B*N, C_in]; view_pe: fp32 [V, dim] view-index encodings added after proj_embed (or None).
     Rows are ordered (batch, view, token), so the SAME buffer is a [B, V*N] sequence set for the global layers and a
-    [B*V, N] one for the frame-level layers of the alternating variant: no data movement between the two."""
+    [B*V, N] one for the frame-level layers of the alternating variant: no data movement between the two.
+    take / norm_intermediate: intermediate-feature-returner variants (global_attention_transformer.py:766-774).
+    Returns (per-view final tokens, [per-view intermediate tokens per taken depth], saved)."""
     nv, N, dev = len(toks), h * w, toks[0].device
     x_in = torch.cat([t.view(B, N, -1) for t in toks], dim=1).reshape(B * nv * N, -1)
     rope = Rope(B * nv, h, w, rope_base, rope_f0, dev) if rope_base is not None else None
@@ -578,7 +580,12 @@ def mv_self_attn_fwd(pk: ParamPack, p: str, toks: List[torch.Tensor], B: int, h:
         x = linear_fwd(pk, p + "proj_embed", x_in, residual=pe)  # the view encoding rides the GEMM's residual epilogue
     else:
         x = x_in if pe is None else ops.elementwise(0, x_in.contiguous(), pe)
-    saved = {"x_in": x_in, "blocks": [], "B": B, "N": N, "nv": nv, "rope": rope}
+    saved = {"x_in": x_in, "blocks": [], "B": B, "N": N, "nv": nv, "rope": rope, "inter": []}
+
+    def split(t):
+        return [u.reshape(B * N, -1).contiguous() for u in t.view(B, nv, N, -1).unbind(1)]
+
+    inter = []
     for i in range(depth):
         frame = alternating and i % 2 == 1
         Bb, Nn = (B * nv, N) if frame else (B, nv * N)
@@ -587,23 +594,49 @@ def mv_self_attn_fwd(pk: ParamPack, p: str, toks: List[torch.Tensor], B: int, h:
         x = self_attn_fwd(pk, bp, x, Bb, Nn, heads, rope, "norm1", bs, attn_scale(softmax_scaling, Nn))
         x = mlp_fwd(pk, bp, x, "norm2", bs)
         saved["blocks"].append(bs)
+        if i in take:
+            if norm_intermediate:
+                yi, m, r = ln_fwd(pk, p + "norm", x)
+                saved["inter"].append((i, x, m, r))
+                inter.append(split(yi))
+            else:
+                saved["inter"].append((i, None, None, None))
+                inter.append(split(x))
     y, mean, rstd = ln_fwd(pk, p + "norm", x)
     saved["final"] = (x, mean, rstd)
-    outs = [t.reshape(B * N, -1) for t in y.view(B, nv, N, -1).unbind(1)]
-    return [t.contiguous() for t in outs], saved
+    return split(y), inter, saved
 
 
 def mv_self_attn_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[torch.Tensor]], depth: int, heads: int,
-                     alternating: bool, has_proj_embed: bool, need_input_grad: bool = True):
+                     alternating: bool, has_proj_embed: bool, need_input_grad: bool = True,
+                     d_inter: Sequence[Sequence[Optional[torch.Tensor]]] = ()):
     B, N, nv, rope = saved["B"], saved["N"], saved["nv"], saved["rope"]
     x, mean, rstd = saved["final"]
-    parts = [(d if d is not None else torch.zeros(B * N, x.shape[1], dtype=torch.bfloat16, device=x.device)).view(B, N, -1)
-             for d in d_outs]
-    dy = torch.stack(parts, dim=1).reshape(B * nv * N, -1).contiguous()
-    sink = bias_sink(pk, f"{p}self_attention_blocks.{depth - 1}.mlp.fc2") if depth > 0 else None
-    dx = ln_bwd(pk, p + "norm", dy, x, mean, rstd, colsum=sink)
-    done = sink is not None
+    C = x.shape[1]
+
+    def join(parts):
+        """per-view gradients ([B*N, C] or None) -> [(b, v, n) rows, C], or None when every view is None."""
+        if all(d is None for d in parts):
+            return None
+        ps = [(d if d is not None else torch.zeros(B * N, C, dtype=torch.bfloat16, device=x.device)).view(B, N, -1) for d in parts]
+        return torch.stack(ps, dim=1).reshape(B * nv * N, -1).contiguous()
+
+    inter_at = {i: (k, xi, m, r) for k, (i, xi, m, r) in enumerate(saved["inter"])}
+    dy = join(d_outs)
+    sink = bias_sink(pk, f"{p}self_attention_blocks.{depth - 1}.mlp.fc2") if (depth > 0 and (depth - 1) not in inter_at) else None
+    dx = ln_bwd(pk, p + "norm", dy, x, mean, rstd, colsum=sink) if dy is not None else None
+    done = dx is not None and sink is not None
     for i in reversed(range(depth)):
+        if i in inter_at:
+            k, xi, m, r = inter_at[i]
+            g = join(d_inter[k]) if k < len(d_inter) and d_inter[k] is not None else None
+            if g is not None:
+                if xi is not None:  # normalised intermediate: through the shared final norm
+                    dx = ln_bwd(pk, p + "norm", g, xi, m, r, dres=dx)
+                else:
+                    dx = g.to(torch.bfloat16) if dx is None else ops.elementwise(0, dx, g.to(torch.bfloat16))
+        if dx is None:
+            continue
         frame = alternating and i % 2 == 1
         Bb, Nn = (B * nv, N) if frame else (B, nv * N)
         bs = saved["blocks"][i]
@@ -611,12 +644,14 @@ def mv_self_attn_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[tor
         sink = bias_sink(pk, bp + "attn.proj")
         dx = mlp_bwd(pk, bp, dx, "norm2", bs[1], bias_done=done, out_sink=sink)
         if i > 0:
-            nxt = bias_sink(pk, f"{p}self_attention_blocks.{i - 1}.mlp.fc2")
+            nxt = bias_sink(pk, f"{p}self_attention_blocks.{i - 1}.mlp.fc2") if (i - 1) not in inter_at else None
         else:
             nxt = bias_sink(pk, p + "proj_embed") if has_proj_embed else None
         dx = self_attn_bwd(pk, bp, dx, Bb, Nn, heads, rope, "norm1", bs[0], bias_done=sink is not None, out_sink=nxt)
         done = nxt is not None
         pk.notify_done(bp)
+    if dx is None:
+        return [None] * nv
     if has_proj_embed:  # the view encoding is a constant: its gradient is dropped
         d_in = linear_bwd(pk, p + "proj_embed", dx, saved["x_in"], need_dx=need_input_grad, bias_done=done and depth > 0)
     else:

@@ -75,25 +75,29 @@ class DecoderFn(torch.autograd.Function):
 
 
 class MultiViewSelfAttnFn(torch.autograd.Function):
-    """Global / alternating self-attention info sharing: per-view token tensors in, per-view normalised tokens out."""
+    """Global / alternating self-attention info sharing: per-view token tensors in; per-view normalised tokens, then the
+    flattened intermediates (depth-major), out."""
 
     @staticmethod
     def forward(ctx, pk: ParamPack, prefix: str, cfg: dict, nv: int, *tensors):
         toks = [t.contiguous() if t.dtype == torch.bfloat16 else t.to(torch.bfloat16).contiguous() for t in tensors[:nv]]
-        outs, saved = E.mv_self_attn_fwd(pk, prefix, toks, cfg["B"], cfg["h"], cfg["w"], cfg["depth"], cfg["heads"], cfg["rope_base"],
-                                         cfg["rope_f0"], cfg["alternating"], cfg["view_pe"], cfg["has_proj_embed"],
-                                         cfg.get("softmax_scaling"))
+        outs, inter, saved = E.mv_self_attn_fwd(pk, prefix, toks, cfg["B"], cfg["h"], cfg["w"], cfg["depth"], cfg["heads"],
+                                                cfg["rope_base"], cfg["rope_f0"], cfg["alternating"], cfg["view_pe"],
+                                                cfg["has_proj_embed"], cfg.get("softmax_scaling"), cfg.get("take", ()),
+                                                cfg.get("norm_intermediate", True))
         ctx.pk, ctx.prefix, ctx.cfg, ctx.saved, ctx.nv = pk, prefix, cfg, saved, nv
+        ctx.n_levels = len(inter)
         ctx.in_dtypes = [t.dtype for t in tensors[:nv]]
-        return tuple(outs)
+        return (*outs, *[t for lvl in inter for t in lvl])
 
     @staticmethod
     def backward(ctx, *grads):
         pk, nv, cfg = ctx.pk, ctx.nv, ctx.cfg
         _prep_grads(pk)
         need_in = any(ctx.needs_input_grad[4:4 + nv])
+        d_inter = [list(grads[nv + l * nv: nv + (l + 1) * nv]) for l in range(ctx.n_levels)]
         d_in = E.mv_self_attn_bwd(pk, ctx.prefix, ctx.saved, list(grads[:nv]), cfg["depth"], cfg["heads"], cfg["alternating"],
-                                  cfg["has_proj_embed"], need_input_grad=need_in)
+                                  cfg["has_proj_embed"], need_input_grad=need_in, d_inter=d_inter)
         ctx.saved = None
         d_in = [g if (g is None or g.dtype == dt) else g.to(dt) for g, dt in zip(d_in, ctx.in_dtypes)]
         return (None, None, None, None, *d_in) + (None,) * (len(ctx.needs_input_grad) - 4 - nv)

@@ -328,14 +328,20 @@ class MultiViewGlobalAttentionTransformer(UniCeptionInfoSharingBase):
             pe[1:] = self.view_pos_table[idx.to(self.view_pos_table.device)]
         return pe
 
-    def forward_tokens(self, toks: List[torch.Tensor], B: int, h: int, w: int, pk: ParamPack, prefix: str):
+    def forward_tokens(self, toks: List[torch.Tensor], B: int, h: int, w: int, pk: ParamPack, prefix: str, take=(),
+                       norm_intermediate=True):
+        """per-view tokens -> (per-view final tokens, [[per-view intermediate tokens] per taken depth])."""
+        nv = len(toks)
         fr = fusable_rope(self.custom_positional_encoding)
         cfg = dict(B=B, h=h, w=w, depth=self.depth, heads=self.num_heads, rope_base=fr[0] if fr else None,
-                   rope_f0=fr[1] if fr else 1.0, alternating=self.ALTERNATING, view_pe=self._view_pe(len(toks)),
-                   has_proj_embed=isinstance(self.proj_embed, nn.Linear), softmax_scaling=self.softmax_scaling)
-        return list(fused.MultiViewSelfAttnFn.apply(pk, prefix, cfg, len(toks), *toks, *pk.params.values()))
+                   rope_f0=fr[1] if fr else 1.0, alternating=self.ALTERNATING, view_pe=self._view_pe(nv),
+                   has_proj_embed=isinstance(self.proj_embed, nn.Linear), softmax_scaling=self.softmax_scaling,
+                   take=tuple(take), norm_intermediate=norm_intermediate)
+        outs = fused.MultiViewSelfAttnFn.apply(pk, prefix, cfg, nv, *toks, *pk.params.values())
+        rest = outs[nv:]
+        return list(outs[:nv]), [list(rest[l * nv:(l + 1) * nv]) for l in range(len(rest) // nv)]
 
-    def forward(self, model_input: MultiViewTransformerInput) -> MultiViewTransformerOutput:
+    def _check_input(self, model_input):
         feats = model_input.features
         assert len(feats) <= self.max_num_views_for_pe, f"Expected less than {self.max_num_views_for_pe} views, got {len(feats)}"
         assert all(f.shape[1] == self.input_embed_dim for f in feats), f"All views must have input dimension {self.input_embed_dim}"
@@ -344,10 +350,35 @@ class MultiViewGlobalAttentionTransformer(UniCeptionInfoSharingBase):
             raise NotImplementedError("uniception_b200: additional input tokens are not built (SURVEY.md 8f2)")
         if not feats[0].is_cuda:
             raise RuntimeError(f"uniception_b200.{type(self).__name__} runs on CUDA only (no CPU fallback)")
-        B, _, h, w = feats[0].shape
-        toks = [fused.NchwToNlcFn.apply(f) for f in feats]
-        outs = self.forward_tokens(toks, B, h, w, self._pack(), "")
+
+    def forward(self, model_input: MultiViewTransformerInput) -> MultiViewTransformerOutput:
+        self._check_input(model_input)
+        B, _, h, w = model_input.features[0].shape
+        toks = [fused.NchwToNlcFn.apply(f) for f in model_input.features]
+        outs, _ = self.forward_tokens(toks, B, h, w, self._pack(), "")
         return MultiViewTransformerOutput(features=[fused.NlcToNchwFn.apply(t, B, h, w) for t in outs])
+
+
+class MultiViewGlobalAttentionTransformerIFR(MultiViewGlobalAttentionTransformer, IntermediateFeatureReturner):
+    """Intermediate-feature-returner variant (global_attention_transformer.py:463-897): additionally returns the (optionally
+    final-normed) token maps after the depths in `indices`."""
+
+    def __init__(self, *args, indices: Optional[Union[int, List[int]]] = None, norm_intermediate: bool = True,
+                 intermediates_only: bool = False, **kwargs):
+        MultiViewGlobalAttentionTransformer.__init__(self, *args, **kwargs)
+        IntermediateFeatureReturner.__init__(self, indices=indices, norm_intermediate=norm_intermediate,
+                                             intermediates_only=intermediates_only)
+
+    def forward(self, model_input: MultiViewTransformerInput):
+        self._check_input(model_input)
+        B, _, h, w = model_input.features[0].shape
+        take, _ = feature_take_indices(self.depth, self.indices)
+        toks = [fused.NchwToNlcFn.apply(f) for f in model_input.features]
+        finals, inter = self.forward_tokens(toks, B, h, w, self._pack(), "", take, self.norm_intermediate)
+        inter_out = [MultiViewTransformerOutput(features=[fused.NlcToNchwFn.apply(t, B, h, w) for t in lvl]) for lvl in inter]
+        if self.intermediates_only:
+            return inter_out
+        return MultiViewTransformerOutput(features=[fused.NlcToNchwFn.apply(t, B, h, w) for t in finals]), inter_out
 
 
 class MultiViewAlternatingAttentionTransformer(MultiViewGlobalAttentionTransformer):
@@ -358,10 +389,16 @@ class MultiViewAlternatingAttentionTransformer(MultiViewGlobalAttentionTransform
     _PE_NON_REF_DEFAULT = False
 
 
-# registry surface: info_sharing/__init__.py:23-37 (in-scope entries; the IFR variants of the self-attention transformers
-# are not built)
+class MultiViewAlternatingAttentionTransformerIFR(MultiViewGlobalAttentionTransformerIFR):
+    """alternating_attention_transformer.py:503-: intermediate-feature-returner variant of the alternating transformer."""
+
+    ALTERNATING = True
+    _PE_NON_REF_DEFAULT = False
+
+
+# registry surface: info_sharing/__init__.py:23-37 (in-scope entries)
 INFO_SHARING_CLASSES = {
     "cross_attention": (MultiViewCrossAttentionTransformer, MultiViewCrossAttentionTransformerIFR),
-    "global_attention": (MultiViewGlobalAttentionTransformer, None),
-    "alternating_attention": (MultiViewAlternatingAttentionTransformer, None),
+    "alternating_attention": (MultiViewAlternatingAttentionTransformer, MultiViewAlternatingAttentionTransformerIFR),
+    "global_attention": (MultiViewGlobalAttentionTransformer, MultiViewGlobalAttentionTransformerIFR),
 }
