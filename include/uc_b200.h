@@ -211,6 +211,36 @@ UC_API int uc_attn_bwd(const uc_attn_bwd_params* p, uc_stream_t stream);
 UC_API int uc_patchify(const float* img, void* cols_bf16, int32_t B, int32_t C, int32_t H, int32_t W, int32_t patch,
                 uc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Block option flags.
+ * qk_norm: `q, k = self.q_norm(q), self.k_norm(k)` with norm_layer(head_dim) on [B,H,N,64] (utils/transformer_blocks.py:199-200,
+ * :222, :306-307, :347), followed by the positional encoding (:224-229).  On the packed projection buffer that is a
+ * LayerNorm over every 64-column head segment of a row:
+ *   fwd: y[r, h*64 + :] = rope2d(LN_64(x[r, h*64 + :]) * gamma + beta)      (RoPE only with positions + rope_table)
+ *   bwd: y holds dL/d(normalised, UN-rotated values) on entry (uc_attn_bwd applies the inverse RoPE) and dL/dx on exit;
+ *        statistics are recomputed from x; dgamma / dbeta [64] are ACCUMULATED.
+ * LayerScale (utils/transformer_blocks.py:389-412, used as x + ls(f(norm(x))), :484-485, :643-646):
+ *   fwd: out = res + gamma[c] * z (res optional);  bwd: dz = gamma[c] * dy, dgamma[c] += sum_rows dy * z.  bf16 [rows][cols].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* x;      /* bf16 [rows][ldx]: the raw projection (q or k columns of a packed buffer) */
+  void* y;            /* bf16 [rows][ldy]: fwd output / bwd gradient (in place) */
+  int64_t ldx, ldy;
+  const float* gamma; /* [64] */
+  const float* beta;  /* [64] (fwd) */
+  float* dgamma;      /* [64] fp32, accumulated (bwd) */
+  float* dbeta;       /* [64] fp32, accumulated (bwd) */
+  const int32_t* positions; /* optional [rows][2] int32 (y,x) (fwd) */
+  const float* rope_table;  /* optional [P][16][2] from uc_rope2d_table (fwd) */
+  int32_t rows, heads;
+  float eps;
+} uc_headnorm_params;
+UC_API int uc_headnorm_fwd(const uc_headnorm_params* p, uc_stream_t stream);
+UC_API int uc_headnorm_bwd(const uc_headnorm_params* p, uc_stream_t stream);
+UC_API int uc_layerscale_fwd(const void* z, const void* res, const float* gamma, void* out, int32_t rows, int32_t cols, uc_stream_t stream);
+UC_API int uc_layerscale_bwd(const void* dy, const void* z, const float* gamma, void* dz, float* dgamma, int32_t rows, int32_t cols,
+                             uc_stream_t stream);
+
 /* column sums of a [rows][cols] matrix (bias gradients), ACCUMULATED into fp32 out[cols] */
 UC_API int uc_colsum(const void* x, int32_t x_dtype, int64_t ld, int32_t rows, int32_t cols, float* out, uc_stream_t stream);
 

@@ -157,12 +157,27 @@ def softmax_q_multiplier(n_tokens: int, softmax_scaling=None) -> float:
     return m
 
 
+def qk_norm(sd: SD, p: str, q: Tensor, k: Tensor) -> Tuple[Tensor, Tensor]:
+    """`q, k = self.q_norm(q), self.k_norm(k)` with norm_layer(head_dim) on [B,H,N,d] (utils/transformer_blocks.py:199-200,
+    :222, :306-307, :347); Identity when the block was built with qk_norm=False (no `q_norm.*` keys)."""
+    if (p + "q_norm.weight") not in sd:
+        return q, k
+    return (layer_norm(q, sd[p + "q_norm.weight"], sd[p + "q_norm.bias"]),
+            layer_norm(k, sd[p + "k_norm.weight"], sd[p + "k_norm.bias"]))
+
+
+def layer_scale(sd: SD, name: str, t: Tensor) -> Tensor:
+    """LayerScale (utils/transformer_blocks.py:389-412): t * gamma; Identity when the block has no `ls*.gamma` (init_values=None)."""
+    return t * sd[name] if name in sd else t
+
+
 def self_attention(sd: SD, p: str, x: Tensor, pos: Optional[Tensor], heads: int, base: float, softmax_scaling=None) -> Tensor:
-    """libs/croco/blocks.py:105-130 == utils/transformer_blocks.py:208-257 (DUSt3R flags; optional softmax scaling)."""
+    """libs/croco/blocks.py:105-130 == utils/transformer_blocks.py:208-257 (optional qk_norm and softmax scaling)."""
     B, N, C = x.shape
     d = C // heads
     qkv = linear(x, sd[p + "qkv.weight"], sd.get(p + "qkv.bias")).view(B, N, 3, heads, d).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0], qkv[1], qkv[2]
+    q, k = qk_norm(sd, p, q, k)
     if pos is not None:
         q, k = rope2d(q, pos, base), rope2d(k, pos, base)
     q = q * softmax_q_multiplier(N, softmax_scaling)
@@ -178,6 +193,7 @@ def cross_attention(sd: SD, p: str, xq: Tensor, y: Tensor, qpos, kpos, heads: in
     q = linear(xq, sd[p + "projq.weight"], sd.get(p + "projq.bias")).view(B, Nq, heads, d).permute(0, 2, 1, 3)
     k = linear(y, sd[p + "projk.weight"], sd.get(p + "projk.bias")).view(B, Nk, heads, d).permute(0, 2, 1, 3)
     v = linear(y, sd[p + "projv.weight"], sd.get(p + "projv.bias")).view(B, Nk, heads, d).permute(0, 2, 1, 3)
+    q, k = qk_norm(sd, p, q, k)
     if qpos is not None:
         q, k = rope2d(q, qpos, base), rope2d(k, kpos, base)
     q = q * softmax_q_multiplier(Nq, softmax_scaling)
@@ -186,23 +202,23 @@ def cross_attention(sd: SD, p: str, xq: Tensor, y: Tensor, qpos, kpos, heads: in
 
 
 def encoder_block(sd: SD, p: str, x: Tensor, pos: Tensor, heads: int, base: float, softmax_scaling=None) -> Tensor:
-    """libs/croco/blocks.py:158-161 (== SelfAttentionBlock, utils/transformer_blocks.py:497-499, without LayerScale)."""
-    x = x + self_attention(sd, p + "attn.", layer_norm(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"]), pos, heads, base,
-                           softmax_scaling)
-    x = x + mlp(sd, p + "mlp.", layer_norm(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"]))
+    """libs/croco/blocks.py:158-161 == SelfAttentionBlock (utils/transformer_blocks.py:497-499; LayerScale when `ls*.gamma` exist)."""
+    x = x + layer_scale(sd, p + "ls1.gamma", self_attention(sd, p + "attn.", layer_norm(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"]),
+                                                           pos, heads, base, softmax_scaling))
+    x = x + layer_scale(sd, p + "ls2.gamma", mlp(sd, p + "mlp.", layer_norm(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"])))
     return x
 
 
 def decoder_block(sd: SD, p: str, x: Tensor, y: Tensor, xpos, ypos, heads: int, base: float, softmax_scaling=None) -> Tensor:
-    """utils/transformer_blocks.py:643-646 (LayerScale/DropPath are Identity for DUSt3R)."""
-    x = x + self_attention(sd, p + "attn.", layer_norm(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"]), xpos, heads, base,
-                           softmax_scaling)
+    """utils/transformer_blocks.py:643-646 (DropPath is Identity; LayerScale when `ls*.gamma` exist, Identity for DUSt3R)."""
+    x = x + layer_scale(sd, p + "ls1.gamma", self_attention(sd, p + "attn.", layer_norm(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"]),
+                                                           xpos, heads, base, softmax_scaling))
     y_ = layer_norm(y, sd[p + "norm_y.weight"], sd[p + "norm_y.bias"])
-    x = x + cross_attention(
+    x = x + layer_scale(sd, p + "ls2.gamma", cross_attention(
         sd, p + "cross_attn.", layer_norm(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"]), y_, xpos, ypos, heads, base,
         softmax_scaling,
-    )
-    x = x + mlp(sd, p + "mlp.", layer_norm(x, sd[p + "norm3.weight"], sd[p + "norm3.bias"]))
+    ))
+    x = x + layer_scale(sd, p + "ls3.gamma", mlp(sd, p + "mlp.", layer_norm(x, sd[p + "norm3.weight"], sd[p + "norm3.bias"])))
     return x
 
 
@@ -504,6 +520,8 @@ def seeded_state_dict(shapes: Dict[str, Sequence[int]], seed: int, dtype=torch.f
             v = rs.uniform(-a, a, size=shp)
         elif "norm" in k and k.endswith("weight"):
             v = 1.0 + 0.1 * rs.standard_normal(shp)
+        elif k.endswith("gamma"):  # LayerScale: O(1) so that the scaled branch matters in the parity metric
+            v = 1.0 + 0.3 * rs.standard_normal(shp)
         else:
             v = 0.02 * rs.standard_normal(shp)
         sd[k] = torch.from_numpy(np.ascontiguousarray(v)).to(dtype)

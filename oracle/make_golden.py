@@ -315,7 +315,7 @@ def golden_encoder_manyar(name, seed, C=128, depth=2, heads=2, hw=(32, 48), B=3)
 
 
 def golden_self_attention_info_sharing(name, cls_name, seed, rope, V=2, B=2, hw=(3, 4), C_in=192, dim=128, depth=4, heads=2,
-                                       scaling=False, indices=None, norm_intermediate=True):
+                                       scaling=False, indices=None, norm_intermediate=True, qk_norm=False, init_values=None):
     """`MultiViewGlobalAttentionTransformer` / `MultiViewAlternatingAttentionTransformer` on V views, with
     sequential view-index positional encodings (the default draws them at random) and optional RoPE.  With `indices` the
     class is the `...IFR` variant and the loss weights intermediate level k by (0.5 + k)."""
@@ -328,7 +328,7 @@ def golden_self_attention_info_sharing(name, cls_name, seed, rope, V=2, B=2, hw=
     # a callable, not the string "rope": the alternating transformer does not resolve the string (it would call a str)
     m = cls(name="mv", input_embed_dim=C_in, depth=depth, dim=dim, num_heads=heads, use_rand_idx_pe_for_non_reference_views=False,
             custom_positional_encoding=RoPE2D(freq=100.0) if rope else None,
-            use_scalable_softmax=scaling, use_entropy_scaling=scaling,
+            use_scalable_softmax=scaling, use_entropy_scaling=scaling, qk_norm=qk_norm, init_values=init_values,
             **(dict(indices=list(indices), norm_intermediate=norm_intermediate) if indices is not None else {}))
     sm = (True, True, m.base_token_count_for_entropy_scaling, m.entropy_scaling_growth_factor) if scaling else None
     # seeded parameters only: `view_pos_table` is a persistent BUFFER (the sinusoid table), not a weight
@@ -367,29 +367,37 @@ def golden_self_attention_info_sharing(name, cls_name, seed, rope, V=2, B=2, hw=
     arrays.update({f"inter{k}_{v}": inter[k][v] for k in range(len(inter)) for v in range(V)})
     arrays.update(grad_qkv1=params[k0].grad, grad_proj_embed=params["proj_embed.weight"].grad, grad_in0=feats[0].grad,
                   grad_norm_w=params["norm.weight"].grad, grad_fc2_b1=params["self_attention_blocks.1.mlp.fc2.bias"].grad)
+    for extra in ("attn.q_norm.weight", "attn.k_norm.bias", "ls1.gamma", "ls2.gamma", "attn.proj.bias"):
+        kx = "self_attention_blocks.1." + extra
+        if kx in params and (qk_norm or init_values):
+            _check(f"{name} grad {kx}", osd[kx].grad, params[kx].grad, 1e-4)
+            arrays["grad_" + extra.replace(".", "_")] = params[kx].grad
     _save(name, dict(cls=cls_name, seed=seed, rope=bool(rope), V=V, B=B, hw=list(hw), C_in=C_in, dim=dim, depth=depth, heads=heads,
                      pe_for_non_ref=bool(m.use_pe_for_non_reference_views), scaling=bool(scaling),
                      indices=list(indices) if indices is not None else None, norm_intermediate=bool(norm_intermediate),
+                     qk_norm=bool(qk_norm), init_values=init_values,
                      shapes={k: list(v) for k, v in shapes.items()}), arrays)
 
 
-def golden_cross_attention_scaled(name, seed, B=2, hw=(3, 4), C_in=192, dim=128, depth=2, heads=2):
+def golden_cross_attention_scaled(name, seed, B=2, hw=(3, 4), C_in=192, dim=128, depth=2, heads=2, scaling=True, qk_norm=False,
+                                  init_values=None):
     """`MultiViewCrossAttentionTransformer(use_scalable_softmax=True, use_entropy_scaling=True)` (the two
-    token-count-dependent query multipliers, utils/transformer_blocks.py:231-241, :360-370)."""
+    token-count-dependent query multipliers, utils/transformer_blocks.py:231-241, :360-370); with `qk_norm` / `init_values`
+    the per-head q/k LayerNorms (:199-200, :306-307) and LayerScale (:389-412) instead."""
     from uniception.models.info_sharing.base import MultiViewTransformerInput
     from uniception.models.info_sharing.cross_attention_transformer import MultiViewCrossAttentionTransformer
     from uniception.models.libs.croco.pos_embed import RoPE2D
 
     m = MultiViewCrossAttentionTransformer(name="mv", input_embed_dim=C_in, num_views=2, depth=depth, dim=dim, num_heads=heads,
-                                           custom_positional_encoding=RoPE2D(freq=100.0), use_scalable_softmax=True,
-                                           use_entropy_scaling=True)
+                                           custom_positional_encoding=RoPE2D(freq=100.0), use_scalable_softmax=scaling,
+                                           use_entropy_scaling=scaling, qk_norm=qk_norm, init_values=init_values)
     sd, shapes = _load_seeded(m, seed)
     g = torch.Generator().manual_seed(seed + 1)
     feats = [torch.randn(B, C_in, *hw, generator=g).requires_grad_(True) for _ in range(2)]
     out = m(MultiViewTransformerInput(features=feats)).features
     sum(o.sum() for o in out).backward()
     params = dict(m.named_parameters())
-    sm = (True, True, m.base_token_count_for_entropy_scaling, m.entropy_scaling_growth_factor)
+    sm = (True, True, m.base_token_count_for_entropy_scaling, m.entropy_scaling_growth_factor) if scaling else None
     osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     of = [f.detach().clone().requires_grad_(True) for f in feats]
     oo = O.info_sharing(osd, "", of, depth, heads, softmax_scaling=sm)
@@ -401,7 +409,14 @@ def golden_cross_attention_scaled(name, seed, B=2, hw=(3, 4), C_in=192, dim=128,
     arrays = {f"feat{v}": feats[v].detach() for v in range(2)}
     arrays.update({f"out{v}": out[v] for v in range(2)})
     arrays.update(grad_projq=params[k0].grad, grad_qkv=params["multi_view_branches.0.1.attn.qkv.weight"].grad, grad_in0=feats[0].grad)
-    _save(name, dict(seed=seed, B=B, hw=list(hw), C_in=C_in, dim=dim, depth=depth, heads=heads, softmax_scaling=list(sm),
+    for extra in ("cross_attn.q_norm.weight", "cross_attn.k_norm.bias", "attn.q_norm.bias", "ls1.gamma", "ls2.gamma", "ls3.gamma",
+                  "cross_attn.proj.bias", "mlp.fc2.bias"):
+        kx = "multi_view_branches.1.0." + extra
+        if kx in params and (qk_norm or init_values):
+            _check(f"{name} grad {kx}", osd[kx].grad, params[kx].grad, 1e-4)
+            arrays["grad_" + extra.replace(".", "_")] = params[kx].grad
+    _save(name, dict(seed=seed, B=B, hw=list(hw), C_in=C_in, dim=dim, depth=depth, heads=heads, softmax_scaling=list(sm) if sm else None,
+                     qk_norm=bool(qk_norm), init_values=init_values,
                      shapes={k: list(v) for k, v in shapes.items()}), arrays)
 
 
@@ -425,6 +440,9 @@ def main():
     golden_self_attention_info_sharing("alternating_attn_tiny", "MultiViewAlternatingAttentionTransformer", seed=53, rope=True)
     golden_self_attention_info_sharing("global_attn_tiny_scaled", "MultiViewGlobalAttentionTransformer", seed=54, rope=True, scaling=True)
     golden_cross_attention_scaled("cross_attn_tiny_scaled", seed=55)
+    golden_cross_attention_scaled("cross_attn_tiny_qknorm_ls", seed=58, scaling=False, qk_norm=True, init_values=0.5)
+    golden_self_attention_info_sharing("alternating_attn_tiny_qknorm_ls", "MultiViewAlternatingAttentionTransformer", seed=59,
+                                       rope=True, V=3, qk_norm=True, init_values=0.5)
     golden_self_attention_info_sharing("global_attn_tiny_ifr", "MultiViewGlobalAttentionTransformerIFR", seed=56, rope=True,
                                        indices=[1, 3])
     golden_self_attention_info_sharing("alternating_attn_tiny_ifr", "MultiViewAlternatingAttentionTransformerIFR", seed=57, rope=True,

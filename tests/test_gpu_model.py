@@ -353,7 +353,8 @@ def test_encoder_manyar_mixed_aspect_ratio_vs_reference_golden():
     assert O.parity(enc.enc_blocks[0].attn.qkv.weight.grad, a["grad_qkv0"].to(DEV))[1] <= 5e-2
 
 
-@pytest.mark.parametrize("name", ["global_attn_tiny", "global_attn_tiny_rope", "alternating_attn_tiny", "global_attn_tiny_scaled"])
+@pytest.mark.parametrize("name", ["global_attn_tiny", "global_attn_tiny_rope", "alternating_attn_tiny", "global_attn_tiny_scaled",
+                                  "alternating_attn_tiny_qknorm_ls"])
 def test_self_attention_info_sharing_vs_reference_golden(name):
     """`MultiViewGlobalAttentionTransformer` / `MultiViewAlternatingAttentionTransformer` on the B200 engine vs
     the reference's golden outputs and gradients (2 and 3 views, with and without RoPE)."""
@@ -361,7 +362,8 @@ def test_self_attention_info_sharing_vs_reference_golden(name):
     m = getattr(U, cfg["cls"])(name="mv", input_embed_dim=cfg["C_in"], depth=cfg["depth"], dim=cfg["dim"], num_heads=cfg["heads"],
                                use_rand_idx_pe_for_non_reference_views=False,
                                custom_positional_encoding=U.RoPE2D(freq=100.0) if cfg["rope"] else None,
-                               use_scalable_softmax=cfg.get("scaling", False), use_entropy_scaling=cfg.get("scaling", False))
+                               use_scalable_softmax=cfg.get("scaling", False), use_entropy_scaling=cfg.get("scaling", False),
+                               qk_norm=cfg.get("qk_norm", False), init_values=cfg.get("init_values"))
     sm = (True, True, 444, 1.4) if cfg.get("scaling") else None
     m.load_state_dict(weights(cfg), strict=False)  # view_pos_table is a buffer (the sinusoid table), not a weight
     m = m.to(DEV)
@@ -381,6 +383,13 @@ def test_self_attention_info_sharing_vs_reference_golden(name):
     assert O.parity(g, a["grad_qkv1"].to(DEV))[1] <= 5e-2
     assert O.parity(m.proj_embed.weight.grad, a["grad_proj_embed"].to(DEV))[1] <= 5e-2
     assert O.parity(feats[0].grad, a["grad_in0"].to(DEV))[1] <= 5e-2
+    if cfg.get("qk_norm"):  # uc_headnorm_* and uc_layerscale_* on the path
+        blk = m.self_attention_blocks[1]
+        for prm, arr in ((blk.attn.q_norm.weight, "grad_attn_q_norm_weight"), (blk.attn.k_norm.bias, "grad_attn_k_norm_bias"),
+                         (blk.ls1.gamma, "grad_ls1_gamma"), (blk.ls2.gamma, "grad_ls2_gamma"), (blk.attn.proj.bias, "grad_attn_proj_bias")):
+            e = O.parity(prm.grad, a[arr].to(DEV))[1]
+            print(f"  {arr}: rel {e:.3e}")
+            assert e <= 5e-2, (arr, e)
 
 
 @pytest.mark.parametrize("name", ["global_attn_tiny_ifr", "alternating_attn_tiny_ifr"])
@@ -423,6 +432,36 @@ def test_self_attention_info_sharing_ifr_vs_reference_golden(name):
     m.intermediates_only = True
     only = m(U.MultiViewTransformerInput(features=[f.detach() for f in feats]))
     assert isinstance(only, list) and len(only) == len(cfg["indices"])
+
+
+def test_cross_attention_qk_norm_layerscale_vs_reference_golden():
+    """`MultiViewCrossAttentionTransformer(qk_norm=True, init_values=...)`: per-head q/k LayerNorm fused with
+    RoPE (uc_headnorm_*) and LayerScale (uc_layerscale_*) vs the reference's golden outputs and gradients."""
+    cfg, a = load("cross_attn_tiny_qknorm_ls")
+    m = U.MultiViewCrossAttentionTransformer(name="mv", input_embed_dim=cfg["C_in"], num_views=2, depth=cfg["depth"], dim=cfg["dim"],
+                                             num_heads=cfg["heads"], custom_positional_encoding=U.RoPE2D(freq=100.0),
+                                             qk_norm=True, init_values=cfg["init_values"])
+    m.load_state_dict(weights(cfg))
+    m = m.to(DEV)
+    feats = [a["feat0"].to(DEV).requires_grad_(True), a["feat1"].to(DEV).requires_grad_(True)]
+    out = m(U.MultiViewTransformerInput(features=feats)).features
+    sd = {k: v.to(DEV) for k, v in weights(cfg).items()}
+    fin = [f.detach() for f in feats]
+    ref_err = max(_autocast_err(lambda: O.info_sharing(sd, "", fin, cfg["depth"], cfg["heads"])))
+    err = max(O.parity(out[v], a[f"out{v}"].to(DEV))[1] for v in range(2))
+    print(f"cross-attn + qk_norm + LayerScale: ours vs reference golden rel {err:.3e} (autocast-bf16 oracle: {ref_err:.3e})")
+    assert err <= 1.5 * ref_err + 2e-3, (err, ref_err)
+    sum(o.sum() for o in out).backward()
+    blk = m.multi_view_branches[1][0]
+    checks = ((blk.cross_attn.q_norm.weight, "grad_cross_attn_q_norm_weight"), (blk.cross_attn.k_norm.bias, "grad_cross_attn_k_norm_bias"),
+              (blk.attn.q_norm.bias, "grad_attn_q_norm_bias"), (blk.ls1.gamma, "grad_ls1_gamma"), (blk.ls2.gamma, "grad_ls2_gamma"),
+              (blk.ls3.gamma, "grad_ls3_gamma"), (blk.cross_attn.proj.bias, "grad_cross_attn_proj_bias"),
+              (blk.mlp.fc2.bias, "grad_mlp_fc2_bias"), (blk.cross_attn.projq.weight, "grad_projq"))
+    for prm, arr in checks:
+        e = O.parity(prm.grad, a[arr].to(DEV))[1]
+        print(f"  {arr}: rel {e:.3e}")
+        assert e <= 5e-2, (arr, e)
+    assert O.parity(feats[0].grad, a["grad_in0"].to(DEV))[1] <= 5e-2
 
 
 def test_cross_attention_softmax_scaling_vs_reference_golden():

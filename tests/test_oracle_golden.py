@@ -168,7 +168,8 @@ def test_encoder_manyar_golden():
            O.croco_encoder(sd, "encoder.", a["img"], cfg["depth"], cfg["heads"]), 2e-6)  # per-sample vs batched matmul rounding
 
 
-@pytest.mark.parametrize("name", ["global_attn_tiny", "global_attn_tiny_rope", "alternating_attn_tiny", "global_attn_tiny_scaled"])
+@pytest.mark.parametrize("name", ["global_attn_tiny", "global_attn_tiny_rope", "alternating_attn_tiny", "global_attn_tiny_scaled",
+                                  "alternating_attn_tiny_qknorm_ls"])
 def test_self_attention_info_sharing_golden(name):
     """global / alternating attention transformers -- oracle == the reference's golden (fwd + bwd), and our
     parameter containers expose the reference's state-dict keys (incl. the `view_pos_table` buffer, first)."""
@@ -178,7 +179,8 @@ def test_self_attention_info_sharing_golden(name):
     m = getattr(U, cfg["cls"])(name="mv", input_embed_dim=cfg["C_in"], depth=cfg["depth"], dim=cfg["dim"], num_heads=cfg["heads"],
                                use_rand_idx_pe_for_non_reference_views=False,
                                custom_positional_encoding=U.RoPE2D(freq=100.0) if cfg["rope"] else None,
-                               use_scalable_softmax=cfg.get("scaling", False), use_entropy_scaling=cfg.get("scaling", False))
+                               use_scalable_softmax=cfg.get("scaling", False), use_entropy_scaling=cfg.get("scaling", False),
+                               qk_norm=cfg.get("qk_norm", False), init_values=cfg.get("init_values"))
     sm = (True, True, 444, 1.4) if cfg.get("scaling") else None
     assert list(m.state_dict().keys()) == ["view_pos_table"] + list(cfg["shapes"].keys())
     assert m.use_pe_for_non_reference_views == cfg["pe_for_non_ref"]
@@ -193,6 +195,11 @@ def test_self_attention_info_sharing_golden(name):
     _close(sd["self_attention_blocks.1.attn.qkv.weight"].grad, a["grad_qkv1"], 1e-4)
     _close(sd["proj_embed.weight"].grad, a["grad_proj_embed"], 1e-4)
     _close(feats[0].grad, a["grad_in0"], 1e-4)
+    if cfg.get("qk_norm"):  # per-head q/k LayerNorms and LayerScale
+        assert m.self_attention_blocks[1].ls1.gamma.shape == (cfg["dim"],)
+        for key, arr in (("attn.q_norm.weight", "grad_attn_q_norm_weight"), ("attn.k_norm.bias", "grad_attn_k_norm_bias"),
+                         ("ls1.gamma", "grad_ls1_gamma"), ("ls2.gamma", "grad_ls2_gamma"), ("attn.proj.bias", "grad_attn_proj_bias")):
+            _close(sd["self_attention_blocks.1." + key].grad, a[arr], 1e-4)
 
 
 @pytest.mark.parametrize("name", ["global_attn_tiny_ifr", "alternating_attn_tiny_ifr"])
@@ -223,6 +230,33 @@ def test_self_attention_info_sharing_ifr_golden(name):
     _close(sd["norm.weight"].grad, a["grad_norm_w"], 1e-4)
     _close(sd["self_attention_blocks.1.mlp.fc2.bias"].grad, a["grad_fc2_b1"], 1e-4)
     _close(feats[0].grad, a["grad_in0"], 1e-4)
+
+
+def test_cross_attention_qk_norm_layerscale_golden():
+    """`MultiViewCrossAttentionTransformer(qk_norm=True, init_values=0.5)` -- oracle == reference golden, and our
+    containers register q_norm / k_norm / ls{1,2,3}.gamma under the reference's keys in the reference's order."""
+    import uniception_b200 as U
+
+    cfg, a = load("cross_attn_tiny_qknorm_ls")
+    m = U.MultiViewCrossAttentionTransformer(name="mv", input_embed_dim=cfg["C_in"], num_views=2, depth=cfg["depth"], dim=cfg["dim"],
+                                             num_heads=cfg["heads"], custom_positional_encoding=U.RoPE2D(freq=100.0),
+                                             qk_norm=True, init_values=cfg["init_values"])
+    assert list(m.state_dict().keys()) == list(cfg["shapes"].keys())
+    assert float(m.multi_view_branches[0][0].ls2.gamma.detach()[0]) == cfg["init_values"]
+    sd = {k: v.requires_grad_(True) for k, v in weights(cfg).items()}
+    feats = [a["feat0"].clone().requires_grad_(True), a["feat1"].clone()]
+    out = O.info_sharing(sd, "", feats, cfg["depth"], cfg["heads"])
+    _close(out[0], a["out0"])
+    _close(out[1], a["out1"])
+    sum(o.sum() for o in out).backward()
+    bp = "multi_view_branches.1.0."
+    for key in ("cross_attn.q_norm.weight", "cross_attn.k_norm.bias", "attn.q_norm.bias", "ls1.gamma", "ls2.gamma", "ls3.gamma",
+                "cross_attn.proj.bias", "mlp.fc2.bias"):
+        _close(sd[bp + key].grad, a["grad_" + key.replace(".", "_")], 1e-4)
+    _close(sd[bp + "cross_attn.projq.weight"].grad, a["grad_projq"], 1e-4)
+    # the flags matter: dropping the q/k norms changes the output
+    plain = O.info_sharing({k: v for k, v in sd.items() if "_norm." not in k}, "", [f.detach() for f in feats], cfg["depth"], cfg["heads"])
+    assert O.parity(plain[0], a["out0"])[1] > 1e-3
 
 
 def test_cross_attention_softmax_scaling_golden():

@@ -138,6 +138,60 @@ def check_gemm_epilogues():
     return ok
 
 
+def check_block_options():
+    """uc_headnorm_{fwd,bwd} (qk_norm + fused RoPE) and uc_layerscale_{fwd,bwd} vs fp32 torch math on the same bf16 inputs."""
+    import torch
+    import dust3r_oracle as O
+    from uniception_b200 import engine as E, ops
+    ok = True
+    torch.manual_seed(9)
+    B, H, hh, ww = 3, 3, 5, 7  # 105 rows x 3 heads: a ragged tail for the 4-groups-per-warp loop
+    N, Cq = hh * ww, H * 64
+    rows = B * N
+    qkv = (torch.randn(rows, 3 * Cq, device="cuda") * 1.5 + 0.3).bfloat16()
+    g, bt = 1 + 0.2 * torch.randn(64, device="cuda"), 0.1 * torch.randn(64, device="cuda")
+    pos = O.patch_positions(B, hh, ww, "cuda")
+    rope = E.Rope(B, hh, ww, 100.0, 1.0, "cuda")
+    for use_rope in (False, True):
+        out = torch.zeros(rows, 2 * Cq, device="cuda", dtype=torch.bfloat16)
+        x = qkv[:, Cq:2 * Cq]  # the k third of a packed qkv buffer (ld = 3C), written to the second half of a [rows, 2C] buffer
+        ops.headnorm_fwd(x, out[:, Cq:], g, bt, 1e-6, rope.pos if use_rope else None, rope.table if use_rope else None)
+        xf = x.float().reshape(B, N, H, 64).permute(0, 2, 1, 3).requires_grad_(True)
+        gp, bp = g.clone().requires_grad_(True), bt.clone().requires_grad_(True)
+        ref = O.layer_norm(xf, gp, bp)
+        ref_n = ref
+        if use_rope:
+            ref = O.rope2d(ref, pos, 100.0, 1.0)
+        ref2 = ref.permute(0, 2, 1, 3).reshape(rows, Cq)
+        ok &= _report(f"headnorm fwd rope={use_rope}", out[:, Cq:].float(), ref2.detach(), 5e-3)
+        e = bool((out[:, :Cq] == 0).all())
+        print(f"[{'OK ' if e else 'BAD'}] headnorm fwd leaves the neighbouring columns alone", flush=True)
+        ok &= e
+    # backward: gradient w.r.t. the normalised, un-rotated values -> gradient w.r.t. x (in place), dgamma, dbeta accumulated
+    dn = torch.randn(rows, 3 * Cq, device="cuda").bfloat16()
+    gbuf = dn.clone()
+    dg, db = torch.ones(64, device="cuda"), torch.ones(64, device="cuda")  # accumulate on top of existing content
+    ops.headnorm_bwd(gbuf[:, Cq:2 * Cq], qkv[:, Cq:2 * Cq], g, dg, db, 1e-6)
+    ref_n.backward(dn[:, Cq:2 * Cq].float().reshape(B, N, H, 64).permute(0, 2, 1, 3))
+    ok &= _report("headnorm bwd dx", gbuf[:, Cq:2 * Cq].float(), xf.grad.permute(0, 2, 1, 3).reshape(rows, Cq), 5e-3)
+    ok &= _report("headnorm bwd dgamma", dg - 1, gp.grad, 1e-4)
+    ok &= _report("headnorm bwd dbeta", db - 1, bp.grad, 1e-4)
+    e = torch.equal(gbuf[:, :Cq], dn[:, :Cq]) and torch.equal(gbuf[:, 2 * Cq:], dn[:, 2 * Cq:])
+    print(f"[{'OK ' if e else 'BAD'}] headnorm bwd leaves the neighbouring columns alone", flush=True)
+    ok &= e
+    # LayerScale
+    for (r, c) in ((777, 768), (64, 128)):
+        z, res, dy = (torch.randn(r, c, device="cuda").bfloat16() for _ in range(3))
+        gam = 1 + 0.3 * torch.randn(c, device="cuda")
+        ok &= _report(f"layerscale fwd {r}x{c}", ops.layerscale_fwd(z, res, gam).float(), res.float() + gam * z.float(), 5e-3)
+        ok &= _report(f"layerscale fwd (no residual) {r}x{c}", ops.layerscale_fwd(z, None, gam).float(), gam * z.float(), 5e-3)
+        dgam = torch.zeros(c, device="cuda")
+        dz = ops.layerscale_bwd(dy, z, gam, dgam)
+        ok &= _report(f"layerscale bwd dz {r}x{c}", dz.float(), gam * dy.float(), 5e-3)
+        ok &= _report(f"layerscale bwd dgamma {r}x{c}", dgam, (dy.float() * z.float()).sum(0), 1e-4)
+    return ok
+
+
 def check_elementwise():
     import torch
     import dust3r_oracle as O

@@ -101,6 +101,13 @@ class HeadPostBwdParams(C.Structure):
     ]
 
 
+class HeadNormParams(C.Structure):
+    _fields_ = [
+        ("x", vp), ("y", vp), ("ldx", i64), ("ldy", i64), ("gamma", vp), ("beta", vp), ("dgamma", vp), ("dbeta", vp),
+        ("positions", vp), ("rope_table", vp), ("rows", i32), ("heads", i32), ("eps", f32),
+    ]
+
+
 # every symbol include/uc_b200.h declares (checked by tests/test_cabi.py)
 EXPORTS = {
     "uc_version": (C.c_int, []),
@@ -126,6 +133,10 @@ EXPORTS = {
     "uc_bilinear_fwd": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "uc_bilinear_bwd": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "uc_elementwise": (C.c_int, [i32, vp, vp, vp, vp, i64, vp]),
+    "uc_headnorm_fwd": (C.c_int, [C.POINTER(HeadNormParams), vp]),
+    "uc_headnorm_bwd": (C.c_int, [C.POINTER(HeadNormParams), vp]),
+    "uc_layerscale_fwd": (C.c_int, [vp, vp, vp, vp, i32, i32, vp]),
+    "uc_layerscale_bwd": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, vp]),
 }
 
 for _name, (_res, _args) in EXPORTS.items():

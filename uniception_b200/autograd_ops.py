@@ -133,6 +133,25 @@ class LayerNormFn(torch.autograd.Function):
         return dx.to(xin.dtype) if xin.dtype != torch.bfloat16 else dx, dg, db, None
 
 
+class LayerScaleFn(torch.autograd.Function):
+    """x * gamma (utils/transformer_blocks.py:389-412) on bf16 token tensors."""
+
+    @staticmethod
+    def forward(ctx, x, gamma):
+        xin = x.contiguous() if x.dtype == torch.bfloat16 else x.to(torch.bfloat16).contiguous()
+        ctx.save_for_backward(xin, gamma.detach())
+        ctx.in_dtype = x.dtype
+        return ops.layerscale_fwd(xin, None, gamma.detach())
+
+    @staticmethod
+    def backward(ctx, dy):
+        xin, gamma = ctx.saved_tensors
+        dyc = dy.contiguous() if dy.dtype == torch.bfloat16 else dy.to(torch.bfloat16).contiguous()
+        dg = torch.zeros_like(gamma)
+        dx = ops.layerscale_bwd(dyc, xin, gamma, dg)
+        return dx if ctx.in_dtype == torch.bfloat16 else dx.to(ctx.in_dtype), dg
+
+
 class AttentionFn(torch.autograd.Function):
     """softmax(q k^T / 8) v on token-major bf16 sources; optional fused 2-D RoPE (rotated copies in
     forward, inverse rotation fused into the backward kernels)."""
@@ -184,6 +203,10 @@ def mlp(x, fc1: nn.Linear, fc2: nn.Linear, residual=None):
 
 def layer_norm(x, norm: nn.LayerNorm):
     return LayerNormFn.apply(x, norm.weight, norm.bias, norm.eps)
+
+
+def layer_scale(x, gamma):
+    return LayerScaleFn.apply(x, gamma)
 
 
 def attention(q_src, kv_src, B, Nq, Nk, H, q_off, k_off, v_off, qpos=None, kpos=None, rope=None, scale=0.125):

@@ -2,9 +2,10 @@
 
 `Mlp`, `Attention`, `Block` mirror libs/croco/blocks.py:64-161 (encoder flavour);
 `CrossAttention`, `CrossAttentionBlock` mirror utils/transformer_blocks.py:260-386, :517-647.
-Only the DUSt3R option set is implemented natively (qk_norm=False, LayerScale/DropPath identity,
-no scalable-softmax / entropy scaling, dropout 0, GELU, head_dim 64); other settings raise
-NotImplementedError at construction instead of silently running something else.
+`SelfAttentionBlock`, `LayerScale` mirror utils/transformer_blocks.py:389-514.
+Built natively: the DUSt3R option set plus qk_norm, LayerScale (init_values) and the softmax-scaling flags; dropout,
+stochastic depth, non-GELU activations, head_dim != 64, latent_attn_dim and DiffAttention raise NotImplementedError at
+construction instead of silently running something else.
 
 The fused whole-module engines (encoders.py / info_sharing.py) never call these modules' forward:
 they read the parameters through a ParamPack.  The `forward` methods here exist so the blocks are
@@ -27,6 +28,30 @@ from .rope import fusable_rope
 def _require(cond: bool, what: str):
     if not cond:
         raise NotImplementedError(f"uniception_b200: {what} is outside the B200 hot path (SURVEY.md 8f)")
+
+
+class LayerScale(nn.Module):
+    """utils/transformer_blocks.py:389-412 (parameter container; the fused engines apply gamma in `uc_layerscale_*`)."""
+
+    def __init__(self, dim: int, init_values: float = 1e-5, inplace: bool = False):
+        super().__init__()
+        self.inplace = inplace
+        self.gamma = nn.Parameter(init_values * torch.ones(dim))
+
+    def forward(self, x):
+        return A.layer_scale(x, self.gamma)
+
+
+def _head_norm(norm_layer, head_dim: int, qk_norm: bool) -> nn.Module:
+    if not qk_norm:
+        return nn.Identity()
+    check_norm_layer(norm_layer)
+    return norm_layer(head_dim)
+
+
+def _standalone_only_plain(mod: nn.Module) -> None:
+    _require(not isinstance(getattr(mod, "q_norm", None), nn.LayerNorm),
+             "qk_norm in a stand-alone block forward (use the fused transformer modules)")
 
 
 class Mlp(nn.Module):
@@ -52,11 +77,12 @@ class Attention(nn.Module):
 
     def __init__(self, dim, rope=None, num_heads=8, qkv_bias=False, attn_drop=0.0, proj_drop=0.0, qk_norm=False,
                  custom_positional_encoding: Optional[Callable] = None, use_scalable_softmax=False, use_entropy_scaling=False,
-                 base_token_count_for_entropy_scaling=444, entropy_scaling_growth_factor=1.4, **_ignored):
+                 base_token_count_for_entropy_scaling=444, entropy_scaling_growth_factor=1.4, norm_layer=nn.LayerNorm,
+                 latent_attn_dim=None, **_ignored):
         super().__init__()
         assert dim % num_heads == 0, "dim should be divisible by num_heads"
+        _require(latent_attn_dim is None, "latent_attn_dim")
         _require(dim // num_heads == 64, f"head_dim {dim // num_heads} (only 64)")
-        _require(not qk_norm, "qk_norm")
         _require(attn_drop == 0.0 and proj_drop == 0.0, "attention dropout")
         # softmax scaling by the token count (utils/transformer_blocks.py:231-241) folds into the kernels' scale
         self.softmax_scaling = (use_scalable_softmax, use_entropy_scaling, base_token_count_for_entropy_scaling,
@@ -65,12 +91,15 @@ class Attention(nn.Module):
         self.head_dim = dim // num_heads
         self.scale = self.head_dim ** -0.5
         self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.q_norm = _head_norm(norm_layer, self.head_dim, qk_norm)  # registration order of transformer_blocks.py:194-202
+        self.k_norm = _head_norm(norm_layer, self.head_dim, qk_norm)
         self.proj = nn.Linear(dim, dim)
         self.rope = rope if rope is not None else custom_positional_encoding
         self.custom_positional_encoding = self.rope
 
     def forward(self, x, xpos=None, residual=None):
         B, N, C = x.shape
+        _standalone_only_plain(self)
         if self.rope is not None:
             assert xpos is not None, "Positions of tokens (xpos) are a required input when using custom positional encoding"
         qkv = A.linear(x, self.qkv.weight, self.qkv.bias)
@@ -107,7 +136,6 @@ class CrossAttention(nn.Module):
         super().__init__()
         assert dim % num_heads == 0, "dim should be divisible by num_heads"
         _require(dim // num_heads == 64, f"head_dim {dim // num_heads} (only 64)")
-        _require(not qk_norm, "qk_norm")
         _require(attn_drop == 0.0 and proj_drop == 0.0, "attention dropout")
         self.softmax_scaling = (use_scalable_softmax, use_entropy_scaling, base_token_count_for_entropy_scaling,
                                 entropy_scaling_growth_factor) if (use_scalable_softmax or use_entropy_scaling) else None
@@ -117,12 +145,15 @@ class CrossAttention(nn.Module):
         self.projq = nn.Linear(dim, dim, bias=qkv_bias)
         self.projk = nn.Linear(dim, dim, bias=qkv_bias)
         self.projv = nn.Linear(dim, dim, bias=qkv_bias)
+        self.q_norm = _head_norm(norm_layer, self.head_dim, qk_norm)  # transformer_blocks.py:306-307
+        self.k_norm = _head_norm(norm_layer, self.head_dim, qk_norm)
         self.proj = nn.Linear(dim, dim)
         self.custom_positional_encoding = custom_positional_encoding
 
     def forward(self, query, key, value, qpos=None, kpos=None, residual=None):
         B, Nq, C = query.shape
         Nk = key.shape[1]
+        _standalone_only_plain(self)
         q = A.linear(query, self.projq.weight, self.projq.bias)
         k = A.linear(key, self.projk.weight, self.projk.bias)
         v = A.linear(value, self.projv.weight, self.projv.bias)
@@ -140,38 +171,75 @@ class CrossAttentionBlock(nn.Module):
                  custom_positional_encoding=None, norm_cross_tokens=True, use_scalable_softmax=False,
                  use_entropy_scaling=False, base_token_count_for_entropy_scaling=444, entropy_scaling_growth_factor=1.4):
         super().__init__()
-        _require(not init_values, "LayerScale")
         _require(drop_path == 0.0, "stochastic depth")
         _require(mlp_layer is Mlp, "a custom mlp_layer")
+        ls = (lambda: LayerScale(dim, init_values=init_values)) if init_values else nn.Identity
         common = dict(num_heads=num_heads, qkv_bias=qkv_bias, qk_norm=qk_norm, attn_drop=attn_drop, proj_drop=proj_drop,
+                      norm_layer=norm_layer,
                       custom_positional_encoding=custom_positional_encoding, use_scalable_softmax=use_scalable_softmax,
                       use_entropy_scaling=use_entropy_scaling,
                       base_token_count_for_entropy_scaling=base_token_count_for_entropy_scaling,
                       entropy_scaling_growth_factor=entropy_scaling_growth_factor)
         self.norm1 = norm_layer(dim)
         self.attn = Attention(dim, **common)
-        self.ls1 = nn.Identity()
+        self.ls1 = ls()
         self.drop_path1 = nn.Identity()
         self.norm_y = norm_layer(dim) if norm_cross_tokens else nn.Identity()
         self.custom_positional_encoding = custom_positional_encoding
         self.norm2 = norm_layer(dim)
-        self.cross_attn = CrossAttention(dim, norm_layer=norm_layer, **common)
-        self.ls2 = nn.Identity()
+        self.cross_attn = CrossAttention(dim, **common)
+        self.ls2 = ls()
         self.drop_path2 = nn.Identity()
         self.norm3 = norm_layer(dim)
         self.mlp = mlp_layer(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=proj_drop)
-        self.ls3 = nn.Identity()
+        self.ls3 = ls()
         self.drop_path3 = nn.Identity()
 
     def forward(self, x, y, xpos=None, ypos=None):
         if self.custom_positional_encoding is not None:
             assert xpos is not None, "Positions of tokens (xpos) are a required input when using custom positional encoding"
             assert ypos is not None, "Positions of cross tokens (ypos) are a required input when using custom positional encoding"
-        x = self.attn(A.layer_norm(x, self.norm1), xpos, residual=x)
         y_ = A.layer_norm(y, self.norm_y) if isinstance(self.norm_y, nn.LayerNorm) else y
+        if isinstance(self.ls1, LayerScale):
+            x = x + self.ls1(self.attn(A.layer_norm(x, self.norm1), xpos))
+            x = x + self.ls2(self.cross_attn(A.layer_norm(x, self.norm2), y_, y_, xpos, ypos))
+            return x + self.ls3(self.mlp(A.layer_norm(x, self.norm3)))
+        x = self.attn(A.layer_norm(x, self.norm1), xpos, residual=x)
         x = self.cross_attn(A.layer_norm(x, self.norm2), y_, y_, xpos, ypos, residual=x)
         x = self.mlp(A.layer_norm(x, self.norm3), residual=x)
         return x
+
+
+class SelfAttentionBlock(nn.Module):
+    """utils/transformer_blocks.py:415-514 (registration order kept: norm1, attn, ls1, norm2, mlp, ls2)."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=4.0, qkv_bias=False, qk_norm=False, proj_drop=0.0, attn_drop=0.0,
+                 init_values=None, drop_path=0.0, act_layer=nn.GELU, norm_layer=nn.LayerNorm, mlp_layer=Mlp,
+                 custom_positional_encoding=None, use_scalable_softmax=False, use_entropy_scaling=False,
+                 base_token_count_for_entropy_scaling=444, entropy_scaling_growth_factor=1.4):
+        super().__init__()
+        _require(drop_path == 0.0, "stochastic depth")
+        _require(mlp_layer is Mlp, "a custom mlp_layer")
+        ls = (lambda: LayerScale(dim, init_values=init_values)) if init_values else nn.Identity
+        self.norm1 = norm_layer(dim)
+        self.attn = Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, qk_norm=qk_norm, attn_drop=attn_drop, proj_drop=proj_drop,
+                              norm_layer=norm_layer, custom_positional_encoding=custom_positional_encoding,
+                              use_scalable_softmax=use_scalable_softmax, use_entropy_scaling=use_entropy_scaling,
+                              base_token_count_for_entropy_scaling=base_token_count_for_entropy_scaling,
+                              entropy_scaling_growth_factor=entropy_scaling_growth_factor)
+        self.ls1 = ls()
+        self.drop_path1 = nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = mlp_layer(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=proj_drop)
+        self.ls2 = ls()
+        self.drop_path2 = nn.Identity()
+
+    def forward(self, x, xpos=None):
+        if isinstance(self.ls1, LayerScale):
+            x = x + self.ls1(self.attn(A.layer_norm(x, self.norm1), xpos))
+            return x + self.ls2(self.mlp(A.layer_norm(x, self.norm2)))
+        x = self.attn(A.layer_norm(x, self.norm1), xpos, residual=x)
+        return self.mlp(A.layer_norm(x, self.norm2), residual=x)
 
 
 def check_norm_layer(norm_layer) -> None:

@@ -129,10 +129,56 @@ def ln_bwd(pk: ParamPack, name: str, dy, x, mean, rstd, dres=None, colsum=None):
                              dx_colsum=colsum)
 
 
+def has_param(pk: ParamPack, name: str) -> bool:
+    return name in pk.params
+
+
+def ls_name(pk: ParamPack, block_prefix: str, k: int) -> Optional[str]:
+    """`{block}.ls{k}.gamma` when the block was built with LayerScale (init_values, utils/transformer_blocks.py:389-412)."""
+    n = f"{block_prefix}ls{k}.gamma"
+    return n if n in pk.params else None
+
+
+def out_proj_fwd(pk: ParamPack, name: str, inp, x, ls: Optional[str]):
+    """x + [gamma *] Linear(inp): the sub-block's output projection with the residual add.  Returns (new x, z) where z is the
+    un-scaled projection (saved for the LayerScale backward) or None."""
+    if ls is None:
+        return linear_fwd(pk, name, inp, residual=x), None
+    z = linear_fwd(pk, name, inp)
+    return ops.layerscale_fwd(z, x, pk.w32(ls)), z
+
+
+def out_proj_grad(pk: ParamPack, dx2, z, ls: Optional[str]):
+    """Gradient w.r.t. the un-scaled projection output (LayerScale backward; identity without it)."""
+    if ls is None:
+        return dx2
+    return ops.layerscale_bwd(dx2, z, pk.w32(ls), pk.grad(ls))
+
+
+def headnorm_fwd(pk: ParamPack, name: str, x, y, rope: Optional[Rope]):
+    """qk_norm: y = rope(LayerNorm_64(x)) on every head segment (utils/transformer_blocks.py:222-229, :347-358)."""
+    ops.headnorm_fwd(x, y, pk.w32(name + ".weight"), pk.w32(name + ".bias"), LN_EPS,
+                     rope.pos if rope is not None else None, rope.table if rope is not None else None)
+
+
+def headnorm_bwd(pk: ParamPack, name: str, g, x):
+    ops.headnorm_bwd(g, x, pk.w32(name + ".weight"), pk.grad(name + ".weight"), pk.grad(name + ".bias"), LN_EPS)
+
+
+_SINK_SUFFIXES = ("cross_attn.proj", "attn.proj", "mlp.fc2")
+
+
 def bias_sink(pk: ParamPack, linear_name: Optional[str], like: Optional[torch.Tensor] = None):
-    """Gradient buffer of `linear_name`.bias if that Linear trains and the fused column sum applies, else None."""
+    """Gradient buffer of `linear_name`.bias if that Linear trains and the fused column sum applies, else None.
+    A block with LayerScale scales the residual-stream gradient before it reaches the projection, so its output
+    projections take the un-fused bias-gradient path."""
     if linear_name is None or not pk.requires_grad(linear_name + ".weight"):
         return None
+    for suf in _SINK_SUFFIXES:
+        if linear_name.endswith(suf):
+            if (linear_name[:-len(suf)] + "ls1.gamma") in pk.params:
+                return None
+            break
     g = pk.grad(linear_name + ".bias")
     if g.shape[0] % 128 != 0 or g.shape[0] > 1024:  # uc_layernorm_bwd's fast path (csrc/elementwise.cu)
         return None
@@ -158,44 +204,58 @@ def attn_scale(softmax_scaling, n_queries: int, head_dim: int = 64) -> float:
 
 
 
-def self_attn_fwd(pk, p, x, B, N, H, rope: Optional[Rope], norm: str, saved: list, scale: float = 0.125):
-    """x += proj(attn(rope(qkv(LN(x)))))  -- returns the new residual stream."""
+def self_attn_fwd(pk, p, x, B, N, H, rope: Optional[Rope], norm: str, saved: list, scale: float = 0.125, ls: Optional[str] = None):
+    """x += [ls *] proj(attn(rope([qk_norm] qkv(LN(x)))))  -- returns the new residual stream."""
     C = H * 64
     h1, mean, rstd = ln_fwd(pk, p + norm, x)
-    qkv = linear_fwd(pk, p + "attn.qkv", h1, rope=rope, rope_cols=2 * C)
-    o, lse = ops.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, H, N, N, scale)
-    x2 = linear_fwd(pk, p + "attn.proj", o, residual=x)
-    saved.append((x, mean, rstd, h1, qkv, o, lse, scale))
+    if has_param(pk, p + "attn.q_norm.weight"):  # qk_norm: raw projection, then LayerNorm_64 + RoPE on the q and k head segments
+        qkv = linear_fwd(pk, p + "attn.qkv", h1)
+        qk = _empty(qkv.shape[0], 2 * C, qkv)
+        headnorm_fwd(pk, p + "attn.q_norm", qkv[:, :C], qk[:, :C], rope)
+        headnorm_fwd(pk, p + "attn.k_norm", qkv[:, C:2 * C], qk[:, C:], rope)
+        q, k = qk[:, :C], qk[:, C:]
+    else:
+        qkv = linear_fwd(pk, p + "attn.qkv", h1, rope=rope, rope_cols=2 * C)
+        qk, q, k = None, qkv[:, :C], qkv[:, C:2 * C]
+    o, lse = ops.attn_fwd(q, k, qkv[:, 2 * C:], B, H, N, N, scale)
+    x2, z = out_proj_fwd(pk, p + "attn.proj", o, x, ls)
+    saved.append((x, mean, rstd, h1, qkv, o, lse, scale, qk, z))
     return x2
 
 
-def self_attn_bwd(pk, p, dx2, B, N, H, rope: Optional[Rope], norm: str, saved, bias_done=False, out_sink=None):
+def self_attn_bwd(pk, p, dx2, B, N, H, rope: Optional[Rope], norm: str, saved, bias_done=False, out_sink=None,
+                  ls: Optional[str] = None):
     """dx2: gradient w.r.t. the sub-block output (bf16).  Returns gradient w.r.t. its input.
     bias_done: colsum(dx2) already sits in attn.proj.bias.grad; out_sink: bias-gradient buffer fed by the returned dx."""
-    x, mean, rstd, h1, qkv, o, lse, scale = saved
+    x, mean, rstd, h1, qkv, o, lse, scale, qk, z = saved
     C = H * 64
-    d_o = linear_bwd(pk, p + "attn.proj", dx2, o, bias_done=bias_done)
+    d_o = linear_bwd(pk, p + "attn.proj", out_proj_grad(pk, dx2, z, ls), o, bias_done=bias_done and ls is None)
     dqkv = torch.empty_like(qkv)
-    ops.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, d_o, lse, B, H, N, N, scale,
+    q, k = (qkv[:, :C], qkv[:, C:2 * C]) if qk is None else (qk[:, :C], qk[:, C:])
+    ops.attn_bwd(q, k, qkv[:, 2 * C:], o, d_o, lse, B, H, N, N, scale,
                  dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:],
                  q_positions=rope.pos if rope is not None else None, k_positions=rope.pos if rope is not None else None,
                  rope_table=rope.table if rope is not None else None)
+    if qk is not None:
+        headnorm_bwd(pk, p + "attn.q_norm", dqkv[:, :C], qkv[:, :C])
+        headnorm_bwd(pk, p + "attn.k_norm", dqkv[:, C:2 * C], qkv[:, C:2 * C])
     d_h1 = linear_bwd(pk, p + "attn.qkv", dqkv, h1)
     return ln_bwd(pk, p + norm, d_h1, x, mean, rstd, dres=dx2, colsum=out_sink)
 
 
-def mlp_fwd(pk, p, x, norm: str, saved: list):
+def mlp_fwd(pk, p, x, norm: str, saved: list, ls: Optional[str] = None):
     h, mean, rstd = ln_fwd(pk, p + norm, x)
     act, pre = linear_fwd(pk, p + "mlp.fc1", h, gelu=True)
-    x2 = linear_fwd(pk, p + "mlp.fc2", act, residual=x)
-    saved.append((x, mean, rstd, h, pre, act))
+    x2, z = out_proj_fwd(pk, p + "mlp.fc2", act, x, ls)
+    saved.append((x, mean, rstd, h, pre, act, z))
     return x2
 
 
-def mlp_bwd(pk, p, dx2, norm: str, saved, bias_done=False, out_sink=None):
-    x, mean, rstd, h, pre, act = saved
+def mlp_bwd(pk, p, dx2, norm: str, saved, bias_done=False, out_sink=None, ls: Optional[str] = None):
+    x, mean, rstd, h, pre, act, z = saved
     fc1_sink = pk.grad(p + "mlp.fc1.bias") if pk.requires_grad(p + "mlp.fc1.weight") else None
-    d_pre = linear_bwd(pk, p + "mlp.fc2", dx2, act, gelu_pre=pre, bias_done=bias_done, dx_sink=fc1_sink)  # fc1.bias.grad = colsum(d_pre)
+    d_pre = linear_bwd(pk, p + "mlp.fc2", out_proj_grad(pk, dx2, z, ls), act, gelu_pre=pre, bias_done=bias_done and ls is None,
+                       dx_sink=fc1_sink)  # fc1.bias.grad = colsum(d_pre)
     d_h = linear_bwd(pk, p + "mlp.fc1", d_pre, h, bias_done=fc1_sink is not None)
     return ln_bwd(pk, p + norm, d_h, x, mean, rstd, dres=dx2, colsum=out_sink)
 
@@ -356,35 +416,47 @@ class ViewStreams:
 # two-view (N-view) cross-attention decoder (info_sharing/cross_attention_transformer.py:191-275)
 # ------------------------------------------------------------------------------------------------
 def _cross_fwd(pk, p, x, y, B, Nq, Nk, H, rope_q: Optional[Rope], rope_k: Optional[Rope], saved: list, has_norm_y: bool,
-               scale: float = 0.125):
+               scale: float = 0.125, ls: Optional[str] = None):
     C = H * 64
+    qkn = has_param(pk, p + "cross_attn.q_norm.weight")
     if has_norm_y:
         yn, ymean, yrstd = ln_fwd(pk, p + "norm_y", y)
     else:
         yn, ymean, yrstd = y, None, None
     h2, mean, rstd = ln_fwd(pk, p + "norm2", x)
-    q = linear_fwd(pk, p + "cross_attn.projq", h2, rope=rope_q, rope_cols=C)
+    q = linear_fwd(pk, p + "cross_attn.projq", h2, rope=None if qkn else rope_q, rope_cols=C)
     # projk | projv are adjacent in the pack -> one GEMM with N = 2C, RoPE on the k half only
     wkv = pk.w16_rows(p + "cross_attn.projk.weight", p + "cross_attn.projv.weight")
     bkv = pk.w32_span(p + "cross_attn.projk.bias", p + "cross_attn.projv.bias")
-    kv = linear_fwd(pk, "", yn, rope=rope_k, rope_cols=C, w16=wkv, bias=bkv)
-    o, lse = ops.attn_fwd(q, kv[:, :C], kv[:, C:], B, H, Nq, Nk, scale)
-    x2 = linear_fwd(pk, p + "cross_attn.proj", o, residual=x)
-    saved.append((x, mean, rstd, h2, q, kv, o, lse, y, yn, ymean, yrstd, scale))
+    kv = linear_fwd(pk, "", yn, rope=None if qkn else rope_k, rope_cols=C, w16=wkv, bias=bkv)
+    if qkn:  # q, k: raw projections kept for the backward; normalised + rotated copies feed the attention
+        qn, kn = torch.empty_like(q), _empty(kv.shape[0], C, kv)
+        headnorm_fwd(pk, p + "cross_attn.q_norm", q, qn, rope_q)
+        headnorm_fwd(pk, p + "cross_attn.k_norm", kv[:, :C], kn, rope_k)
+    else:
+        qn, kn = q, kv[:, :C]
+    o, lse = ops.attn_fwd(qn, kn, kv[:, C:], B, H, Nq, Nk, scale)
+    x2, z = out_proj_fwd(pk, p + "cross_attn.proj", o, x, ls)
+    saved.append((x, mean, rstd, h2, q, kv, o, lse, y, yn, ymean, yrstd, scale, qn if qkn else None, kn if qkn else None, z))
     return x2
 
 
-def _cross_bwd(pk, p, dx2, B, Nq, Nk, H, rope_q, rope_k, saved, has_norm_y: bool, bias_done=False, out_sink=None):
+def _cross_bwd(pk, p, dx2, B, Nq, Nk, H, rope_q, rope_k, saved, has_norm_y: bool, bias_done=False, out_sink=None,
+               ls: Optional[str] = None):
     """Returns (dx, d_yn): gradient w.r.t. the block's own stream and w.r.t. norm_y(y) (bf16)."""
-    x, mean, rstd, h2, q, kv, o, lse, y, yn, ymean, yrstd, scale = saved
+    x, mean, rstd, h2, q, kv, o, lse, y, yn, ymean, yrstd, scale, qn, kn, z = saved
     C = H * 64
-    d_o = linear_bwd(pk, p + "cross_attn.proj", dx2, o, bias_done=bias_done)
+    d_o = linear_bwd(pk, p + "cross_attn.proj", out_proj_grad(pk, dx2, z, ls), o, bias_done=bias_done and ls is None)
     dq = torch.empty_like(q)
     dkv = torch.empty_like(kv)
-    ops.attn_bwd(q, kv[:, :C], kv[:, C:], o, d_o, lse, B, H, Nq, Nk, scale, dq, dkv[:, :C], dkv[:, C:],
+    ops.attn_bwd(q if qn is None else qn, kv[:, :C] if kn is None else kn, kv[:, C:], o, d_o, lse, B, H, Nq, Nk, scale,
+                 dq, dkv[:, :C], dkv[:, C:],
                  q_positions=rope_q.pos if rope_q is not None else None,
                  k_positions=rope_k.pos if rope_k is not None else None,
                  rope_table=rope_q.table if rope_q is not None else None)
+    if qn is not None:
+        headnorm_bwd(pk, p + "cross_attn.q_norm", dq, q)
+        headnorm_bwd(pk, p + "cross_attn.k_norm", dkv[:, :C], kv[:, :C])
     d_h2 = linear_bwd(pk, p + "cross_attn.projq", dq, h2)
     wkv = pk.w16_rows(p + "cross_attn.projk.weight", p + "cross_attn.projv.weight")
     gkv = pk.grad_span(p + "cross_attn.projk.weight", p + "cross_attn.projv.weight").view(2 * C, -1)
@@ -425,9 +497,9 @@ def decoder_fwd(pk: ParamPack, p: str, toks: List[torch.Tensor], B: int, h: int,
                 else:  # other views concatenated along tokens, per batch element
                     y = torch.cat([xs[i].view(B, N, -1) for i in range(nv) if i != v], dim=1).reshape(B * N * (nv - 1), -1)
                 sc = attn_scale(softmax_scaling, N)
-                x = self_attn_fwd(pk, bp, xs[v], B, N, heads, rope, "norm1", bs, sc)
-                x = _cross_fwd(pk, bp, x, y, B, N, N * (nv - 1), heads, rope, rope_o, bs, has_norm_y, sc)
-                x = mlp_fwd(pk, bp, x, "norm3", bs)
+                x = self_attn_fwd(pk, bp, xs[v], B, N, heads, rope, "norm1", bs, sc, ls_name(pk, bp, 1))
+                x = _cross_fwd(pk, bp, x, y, B, N, N * (nv - 1), heads, rope, rope_o, bs, has_norm_y, sc, ls_name(pk, bp, 2))
+                x = mlp_fwd(pk, bp, x, "norm3", bs, ls_name(pk, bp, 3))
             new.append(x)
             lvl.append(bs)
         vs.join()
@@ -503,13 +575,14 @@ def decoder_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[torch.Te
             bs = lvl[v]
             with vs.on(v):
                 s_cross = bias_sink(pk, bp + "cross_attn.proj")
-                dx = mlp_bwd(pk, bp, dxs[v], "norm3", bs[2], bias_done=done[v], out_sink=s_cross)
+                dx = mlp_bwd(pk, bp, dxs[v], "norm3", bs[2], bias_done=done[v], out_sink=s_cross, ls=ls_name(pk, bp, 3))
                 s_attn = bias_sink(pk, bp + "attn.proj")
                 dx, d_yn[v] = _cross_bwd(pk, bp, dx, B, N, N * (nv - 1), heads, rope, rope_o, bs[1], has_norm_y,
-                                         bias_done=s_cross is not None, out_sink=s_attn)
+                                         bias_done=s_cross is not None, out_sink=s_attn, ls=ls_name(pk, bp, 2))
                 # if no fold follows for this view (the other view carries no gradient), norm1's backward is final
                 s_own = stream_sink(v, k - 1) if (nv == 2 and dxs[1 - v] is None) else None
-                d_own[v] = self_attn_bwd(pk, bp, dx, B, N, heads, rope, "norm1", bs[0], bias_done=s_attn is not None, out_sink=s_own)
+                d_own[v] = self_attn_bwd(pk, bp, dx, B, N, heads, rope, "norm1", bs[0], bias_done=s_attn is not None, out_sink=s_own,
+                                         ls=ls_name(pk, bp, 1))
             own_done[v] = s_own is not None
             ready[v] = vs.event(v)
         # fold the cross-view gradients: d tokens_v(k-1) = d_own[v] + sum_{u != v} norm_y_u'(d_yn[u])|_v
@@ -591,8 +664,8 @@ def mv_self_attn_fwd(pk: ParamPack, p: str, toks: List[torch.Tensor], B: int, h:
         Bb, Nn = (B * nv, N) if frame else (B, nv * N)
         bs: list = []
         bp = f"{p}self_attention_blocks.{i}."
-        x = self_attn_fwd(pk, bp, x, Bb, Nn, heads, rope, "norm1", bs, attn_scale(softmax_scaling, Nn))
-        x = mlp_fwd(pk, bp, x, "norm2", bs)
+        x = self_attn_fwd(pk, bp, x, Bb, Nn, heads, rope, "norm1", bs, attn_scale(softmax_scaling, Nn), ls_name(pk, bp, 1))
+        x = mlp_fwd(pk, bp, x, "norm2", bs, ls_name(pk, bp, 2))
         saved["blocks"].append(bs)
         if i in take:
             if norm_intermediate:
@@ -642,12 +715,13 @@ def mv_self_attn_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[tor
         bs = saved["blocks"][i]
         bp = f"{p}self_attention_blocks.{i}."
         sink = bias_sink(pk, bp + "attn.proj")
-        dx = mlp_bwd(pk, bp, dx, "norm2", bs[1], bias_done=done, out_sink=sink)
+        dx = mlp_bwd(pk, bp, dx, "norm2", bs[1], bias_done=done, out_sink=sink, ls=ls_name(pk, bp, 2))
         if i > 0:
             nxt = bias_sink(pk, f"{p}self_attention_blocks.{i - 1}.mlp.fc2") if (i - 1) not in inter_at else None
         else:
             nxt = bias_sink(pk, p + "proj_embed") if has_proj_embed else None
-        dx = self_attn_bwd(pk, bp, dx, Bb, Nn, heads, rope, "norm1", bs[0], bias_done=sink is not None, out_sink=nxt)
+        dx = self_attn_bwd(pk, bp, dx, Bb, Nn, heads, rope, "norm1", bs[0], bias_done=sink is not None, out_sink=nxt,
+                           ls=ls_name(pk, bp, 1))
         done = nxt is not None
         pk.notify_done(bp)
     if dx is None:

@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import fused
-from .blocks import Block, CrossAttentionBlock, Mlp, _require, check_norm_layer
+from .blocks import CrossAttentionBlock, Mlp, SelfAttentionBlock, _require, check_norm_layer
 from .encoders import IntermediateFeatureReturner, PositionGetter, feature_take_indices
 from .params import ParamPack, get_pack
 from .rope import RoPE2D, fusable_rope
@@ -254,7 +254,8 @@ class MultiViewGlobalAttentionTransformer(UniCeptionInfoSharingBase):
     """UniCeption Multi-View Global-Attention Transformer on the B200 engine (global_attention_transformer.py:25-462):
     all views' tokens form one sequence of V*N tokens per batch element, `depth` SelfAttentionBlocks, final norm.
     Same constructor, state-dict keys (incl. the `view_pos_table` buffer) and I/O dataclasses as the reference.
-    Not built: additional input tokens, qk_norm / LayerScale / softmax-scaling flags (NotImplementedError)."""
+    Block flags built: qk_norm, LayerScale (init_values), scalable softmax / entropy scaling.  Not built: additional input
+    tokens, dropout / stochastic depth, activation checkpointing (NotImplementedError)."""
 
     ALTERNATING = False
     _PE_NON_REF_DEFAULT = True
@@ -272,8 +273,9 @@ class MultiViewGlobalAttentionTransformer(UniCeptionInfoSharingBase):
         if use_pe_for_non_reference_views is None:
             use_pe_for_non_reference_views = self._PE_NON_REF_DEFAULT
         check_norm_layer(norm_layer)
-        if qk_norm or init_values or drop_path or proj_drop or attn_drop:
-            raise NotImplementedError("uniception_b200: qk_norm / LayerScale / dropout block options (SURVEY.md 8f4)")
+        if drop_path or proj_drop or attn_drop:
+            raise NotImplementedError("uniception_b200: dropout / stochastic-depth block options (SURVEY.md 8f4)")
+        self.qk_norm, self.init_values = qk_norm, init_values
         self.softmax_scaling = (use_scalable_softmax, use_entropy_scaling, base_token_count_for_entropy_scaling,
                                 entropy_scaling_growth_factor) if (use_scalable_softmax or use_entropy_scaling) else None
         if gradient_checkpointing:
@@ -296,7 +298,12 @@ class MultiViewGlobalAttentionTransformer(UniCeptionInfoSharingBase):
         if custom_positional_encoding is not None and fusable_rope(custom_positional_encoding) is None:
             raise NotImplementedError("uniception_b200: only RoPE2D positional encodings are fused")
         self.self_attention_blocks = nn.ModuleList(
-            [Block(dim, num_heads, mlp_ratio, qkv_bias=qkv_bias, norm_layer=norm_layer, rope=custom_positional_encoding)
+            [SelfAttentionBlock(dim=dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_norm=qk_norm,
+                                init_values=init_values, act_layer=act_layer, norm_layer=norm_layer, mlp_layer=mlp_layer,
+                                custom_positional_encoding=custom_positional_encoding, use_scalable_softmax=use_scalable_softmax,
+                                use_entropy_scaling=use_entropy_scaling,
+                                base_token_count_for_entropy_scaling=base_token_count_for_entropy_scaling,
+                                entropy_scaling_growth_factor=entropy_scaling_growth_factor)
              for _ in range(depth)])
         self.norm = norm_layer(dim)
         if distinguish_ref_and_non_ref_views:

@@ -147,6 +147,50 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dres=None, dx_colsum=
     return dx.view(x.shape)
 
 
+def headnorm_fwd(x, y, gamma, beta, eps, positions=None, rope_table=None):
+    """qk_norm (+ fused RoPE): x, y bf16 column slices [rows, H*64] of packed projection buffers; gamma/beta fp32 [64]."""
+    _cuda(x, y, gamma, beta)
+    assert x.dtype == y.dtype == torch.bfloat16 and x.stride(1) == 1 and y.stride(1) == 1 and x.shape == y.shape
+    assert x.shape[1] % 64 == 0 and gamma.numel() == 64 and beta.numel() == 64
+    p = L.HeadNormParams(_ptr(x), _ptr(y), x.stride(0), y.stride(0), _ptr(gamma), _ptr(beta), None, None,
+                         _ptr(positions), _ptr(rope_table), x.shape[0], x.shape[1] // 64, float(eps))
+    L.check(L.lib.uc_headnorm_fwd(C.byref(p), _stream()))
+    return y
+
+
+def headnorm_bwd(g, x, gamma, dgamma, dbeta, eps):
+    """In place on g: gradient w.r.t. the normalised (un-rotated) q or k -> gradient w.r.t. the raw projection x;
+    dgamma / dbeta (fp32 [64]) are accumulated."""
+    _cuda(g, x, gamma, dgamma, dbeta)
+    assert x.dtype == g.dtype == torch.bfloat16 and x.stride(1) == 1 and g.stride(1) == 1 and x.shape == g.shape
+    assert x.shape[1] % 64 == 0 and gamma.numel() == 64 and dgamma.dtype == dbeta.dtype == torch.float32
+    p = L.HeadNormParams(_ptr(x), _ptr(g), x.stride(0), g.stride(0), _ptr(gamma), None, _ptr(dgamma), _ptr(dbeta),
+                         None, None, x.shape[0], x.shape[1] // 64, float(eps))
+    L.check(L.lib.uc_headnorm_bwd(C.byref(p), _stream()))
+    return g
+
+
+def layerscale_fwd(z, res, gamma):
+    """res + gamma * z (bf16 [rows, C] contiguous; gamma fp32 [C]); res may be None."""
+    _cuda(z, gamma)
+    assert z.dtype == torch.bfloat16 and z.is_contiguous() and gamma.dtype == torch.float32 and gamma.numel() == z.shape[-1]
+    assert res is None or (res.dtype == torch.bfloat16 and res.is_contiguous() and res.shape == z.shape)
+    out = torch.empty_like(z)
+    z2 = z.reshape(-1, z.shape[-1])
+    L.check(L.lib.uc_layerscale_fwd(_ptr(z), _ptr(res), _ptr(gamma), _ptr(out), z2.shape[0], z2.shape[1], _stream()))
+    return out
+
+
+def layerscale_bwd(dy, z, gamma, dgamma):
+    """dz = gamma * dy (returned, bf16); dgamma (fp32 [C]) += column sums of dy * z."""
+    _cuda(dy, z, gamma, dgamma)
+    assert dy.dtype == z.dtype == torch.bfloat16 and dy.is_contiguous() and z.is_contiguous() and dy.shape == z.shape
+    dz = torch.empty_like(dy)
+    z2 = z.reshape(-1, z.shape[-1])
+    L.check(L.lib.uc_layerscale_bwd(_ptr(dy), _ptr(z), _ptr(gamma), _ptr(dz), _ptr(dgamma), z2.shape[0], z2.shape[1], _stream()))
+    return dz
+
+
 def attn_fwd(q, k, v, B, H, Nq, Nk, scale, out=None):
     """q: [B*Nq, >=H*64] bf16 view (row stride = ld), k/v: [B*Nk, ...]; returns (o [B*Nq, H*64], lse [B,H,Nq])."""
     _cuda(q, k, v)
