@@ -375,18 +375,32 @@ def view_sinusoid_table(n_position: int, d_hid: int, base: float = 10000.0) -> T
 def self_attention_info_sharing(sd: SD, p: str, feats: List[Tensor], depth: int, heads: int, *, alternating: bool = False,
                                 base: Optional[float] = None, distinguish_ref: bool = True, pe_for_non_ref: bool = True,
                                 max_num_views_for_pe: int = 1000, softmax_scaling=None, indices: Optional[Sequence[int]] = None,
-                                norm_intermediate: bool = True):
+                                norm_intermediate: bool = True, extra: Optional[Tensor] = None,
+                                extra_per_view: Optional[List[Tensor]] = None):
     """`MultiViewGlobalAttentionTransformer.forward` (global_attention_transformer.py:224-462) and, with
-    `alternating=True`, `MultiViewAlternatingAttentionTransformer.forward` (alternating_attention_transformer.py:397-442:
-    even depths attend over all V*N tokens, odd depths inside each view), for `use_rand_idx_pe_for_non_reference_views=False`
-    and no additional tokens.  Blocks are `SelfAttentionBlock`s (utils/transformer_blocks.py:415-514): without LayerScale /
-    DropPath that is `encoder_block`'s arithmetic.  base: RoPE frequency base when `custom_positional_encoding="rope"`, else None.
+    `alternating=True`, `MultiViewAlternatingAttentionTransformer.forward` (alternating_attention_transformer.py:397-447:
+    even depths attend over all tokens, odd depths inside each view), for `use_rand_idx_pe_for_non_reference_views=False`.
+    Blocks are `SelfAttentionBlock`s (utils/transformer_blocks.py:415-514).  base: RoPE frequency base when
+    `custom_positional_encoding="rope"`, else None.
+    extra [B, C, T] / extra_per_view (V x [B, C, Tv]): additional input tokens (:266-333).  Per-view extras follow their
+    view's patch tokens and receive its view encoding; global extras close the sequence, get no view encoding and skip the
+    frame-level blocks of the alternating variant.
     indices: the IFR variants (global_attention_transformer.py:766-774, :880-897): also collect `norm(x)` (or x) after those
-    depths and return (final per-view maps, [per-view maps per taken depth])."""
+    depths.  Returns per-view maps -- or, with additional tokens, the triple (maps, global token features [B, dim, T] or None,
+    per-view token features or None) -- and with `indices` the pair (that for the final output, [that per taken depth])."""
     V = len(feats)
     B, C_in, h, w = feats[0].shape
     N = h * w
-    x = torch.stack(feats, dim=1).permute(0, 1, 3, 4, 2).reshape(B, V * N, C_in)
+    assert base is None or (extra is None and extra_per_view is None), "no positional encoding with additional tokens (:341-351)"
+    seqs = []
+    for v in range(V):
+        t = feats[v].reshape(B, C_in, N)
+        if extra_per_view is not None:
+            t = torch.cat([t, extra_per_view[v]], dim=2)
+        seqs.append(t.permute(0, 2, 1))
+    Np = seqs[0].shape[1]
+    T = extra.shape[2] if extra is not None else 0
+    x = torch.cat(seqs + ([extra.permute(0, 2, 1)] if extra is not None else []), dim=1)
     if p + "proj_embed.weight" in sd:
         x = linear(x, sd[p + "proj_embed.weight"], sd[p + "proj_embed.bias"])
     dim = x.shape[-1]
@@ -396,15 +410,17 @@ def self_attention_info_sharing(sd: SD, p: str, feats: List[Tensor], depth: int,
         pe[0] = tab[0]
         if pe_for_non_ref:
             pe[1:] = tab[1:V]
-        x = x + pe.repeat_interleave(N, dim=0)[None]
+        pe = torch.cat([pe.repeat_interleave(Np, dim=0), torch.zeros(T, dim, device=x.device)], dim=0)
+        x = x + pe[None]
     pos = patch_positions(B, h, w, x.device).repeat(1, V, 1) if base is not None else None
     inter = []
     for i in range(depth):
         bp = f"{p}self_attention_blocks.{i}."
         if alternating and i % 2 == 1:
-            xf = x.reshape(B * V, N, dim)
+            xf = x[:, :V * Np].reshape(B * V, Np, dim)
             pf = pos.reshape(B * V, N, 2) if pos is not None else None
-            x = encoder_block(sd, bp, xf, pf, heads, base, softmax_scaling).reshape(B, V * N, dim)
+            xf = encoder_block(sd, bp, xf, pf, heads, base, softmax_scaling).reshape(B, V * Np, dim)
+            x = torch.cat([xf, x[:, V * Np:]], dim=1)
         else:
             x = encoder_block(sd, bp, x, pos, heads, base, softmax_scaling)
         if indices is not None and i in indices:
@@ -412,8 +428,13 @@ def self_attention_info_sharing(sd: SD, p: str, feats: List[Tensor], depth: int,
     x = layer_norm(x, sd[p + "norm.weight"], sd[p + "norm.bias"])
 
     def views(t):
-        t = t.reshape(B, V, h, w, dim).permute(0, 1, 4, 2, 3)
-        return [t[:, v].contiguous() for v in range(V)]
+        tv = t[:, :V * Np].reshape(B, V, Np, dim)
+        maps = [tv[:, v, :N].reshape(B, h, w, dim).permute(0, 3, 1, 2).contiguous() for v in range(V)]
+        if extra is None and extra_per_view is None:
+            return maps
+        pv = [tv[:, v, N:].permute(0, 2, 1).contiguous() for v in range(V)] if extra_per_view is not None else None
+        ex = t[:, V * Np:].permute(0, 2, 1).contiguous() if extra is not None else None
+        return maps, ex, pv
 
     if indices is None:
         return views(x)

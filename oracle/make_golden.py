@@ -379,6 +379,77 @@ def golden_self_attention_info_sharing(name, cls_name, seed, rope, V=2, B=2, hw=
                      shapes={k: list(v) for k, v in shapes.items()}), arrays)
 
 
+def golden_additional_tokens(name, cls_name, seed, V=2, T=2, Tv=1, B=2, hw=(3, 4), C_in=192, dim=128, depth=4, heads=2, indices=None):
+    """Additional input tokens in the global / alternating attention transformers (global_attention_transformer.py:266-333,
+    :434-461; alternating_attention_transformer.py:402-447): T global tokens and Tv tokens per view, no positional encoding
+    plugin (the reference refuses RoPE with additional tokens).  The loss weights maps 1, global extras 2, per-view extras 3
+    (and intermediate level k by 0.5 + k on top)."""
+    from uniception.models.info_sharing import alternating_attention_transformer as AT, global_attention_transformer as GT
+    from uniception.models.info_sharing.base import MultiViewTransformerInput
+
+    cls = getattr(GT, cls_name, None) or getattr(AT, cls_name)
+    m = cls(name="mv", input_embed_dim=C_in, depth=depth, dim=dim, num_heads=heads, use_rand_idx_pe_for_non_reference_views=False,
+            **(dict(indices=list(indices)) if indices is not None else {}))
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if k != "view_pos_table"}
+    m.load_state_dict(O.seeded_state_dict(shapes, seed), strict=False)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(seed + 1)
+    feats = [torch.randn(B, C_in, *hw, generator=g).requires_grad_(True) for _ in range(V)]
+    extra = torch.randn(B, C_in, T, generator=g).requires_grad_(True) if T else None
+    per_view = [torch.randn(B, C_in, Tv, generator=g).requires_grad_(True) for _ in range(V)] if Tv else None
+
+    def level_loss(maps, ex, pv):
+        return sum(t.sum() for t in maps) + (2 * ex.sum() if ex is not None else 0) + (3 * sum(t.sum() for t in pv) if pv else 0)
+
+    def unpack(o):
+        return o.features, o.additional_token_features, o.additional_token_features_per_view
+
+    res = m(MultiViewTransformerInput(features=feats, additional_input_tokens=extra, additional_input_tokens_per_view=per_view))
+    inter = []
+    if indices is not None:
+        res, inter = res
+    levels = [unpack(res)] + [unpack(o) for o in inter]
+    sum((1.0 if k == 0 else k - 0.5) * level_loss(*lv) for k, lv in enumerate(levels)).backward()
+    params = dict(m.named_parameters())
+    osd = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "view_pos_table"}
+    of = [f.detach().clone().requires_grad_(True) for f in feats]
+    oe = extra.detach().clone().requires_grad_(True) if T else None
+    opv = [t.detach().clone().requires_grad_(True) for t in per_view] if Tv else None
+    oo = O.self_attention_info_sharing(osd, "", of, depth, heads, alternating="Alternating" in cls_name,
+                                       distinguish_ref=m.distinguish_ref_and_non_ref_views, pe_for_non_ref=m.use_pe_for_non_reference_views,
+                                       indices=indices, extra=oe, extra_per_view=opv)
+    olevels = [oo] if indices is None else [oo[0]] + list(oo[1])
+    arrays = {f"feat{v}": feats[v].detach() for v in range(V)}
+    for k, (lv, olv) in enumerate(zip(levels, olevels)):
+        for v in range(V):
+            _check(f"{name} level{k} view{v}", olv[0][v], lv[0][v])
+            arrays[f"l{k}_out{v}"] = lv[0][v]
+        if T:
+            _check(f"{name} level{k} global extras", olv[1], lv[1])
+            arrays[f"l{k}_extra"] = lv[1]
+        if Tv:
+            for v in range(V):
+                _check(f"{name} level{k} per-view extras {v}", olv[2][v], lv[2][v])
+                arrays[f"l{k}_pv{v}"] = lv[2][v]
+    sum((1.0 if k == 0 else k - 0.5) * level_loss(*lv) for k, lv in enumerate(olevels)).backward()
+    k0 = "self_attention_blocks.1.attn.qkv.weight"
+    _check(f"{name} grad {k0}", osd[k0].grad, params[k0].grad, 1e-4)
+    _check(f"{name} grad input0", of[0].grad, feats[0].grad, 1e-4)
+    arrays.update(grad_qkv1=params[k0].grad, grad_proj_embed=params["proj_embed.weight"].grad, grad_in0=feats[0].grad,
+                  grad_fc2_b1=params["self_attention_blocks.1.mlp.fc2.bias"].grad, grad_fc2_b0=params["self_attention_blocks.0.mlp.fc2.bias"].grad,
+                  grad_proj_embed_b=params["proj_embed.bias"].grad)
+    if T:
+        _check(f"{name} grad global extras", oe.grad, extra.grad, 1e-4)
+        arrays.update(extra=extra.detach(), grad_extra=extra.grad)
+    if Tv:
+        _check(f"{name} grad per-view extras", opv[V - 1].grad, per_view[V - 1].grad, 1e-4)
+        arrays.update({f"pv{v}": per_view[v].detach() for v in range(V)})
+        arrays["grad_pv_last"] = per_view[V - 1].grad
+    _save(name, dict(cls=cls_name, seed=seed, V=V, T=T, Tv=Tv, B=B, hw=list(hw), C_in=C_in, dim=dim, depth=depth, heads=heads,
+                     pe_for_non_ref=bool(m.use_pe_for_non_reference_views), indices=list(indices) if indices is not None else None,
+                     shapes={k: list(v) for k, v in shapes.items()}), arrays)
+
+
 def golden_cross_attention_scaled(name, seed, B=2, hw=(3, 4), C_in=192, dim=128, depth=2, heads=2, scaling=True, qk_norm=False,
                                   init_values=None):
     """`MultiViewCrossAttentionTransformer(use_scalable_softmax=True, use_entropy_scaling=True)` (the two
@@ -443,6 +514,10 @@ def main():
     golden_cross_attention_scaled("cross_attn_tiny_qknorm_ls", seed=58, scaling=False, qk_norm=True, init_values=0.5)
     golden_self_attention_info_sharing("alternating_attn_tiny_qknorm_ls", "MultiViewAlternatingAttentionTransformer", seed=59,
                                        rope=True, V=3, qk_norm=True, init_values=0.5)
+    golden_additional_tokens("global_attn_tiny_tokens", "MultiViewGlobalAttentionTransformer", seed=60, V=3, T=2, Tv=1)
+    golden_additional_tokens("alternating_attn_tiny_tokens", "MultiViewAlternatingAttentionTransformerIFR", seed=61, V=2, T=3, Tv=2,
+                             indices=[0, 1])
+    golden_additional_tokens("alternating_attn_tiny_pv_tokens", "MultiViewAlternatingAttentionTransformer", seed=62, V=2, T=0, Tv=2)
     golden_self_attention_info_sharing("global_attn_tiny_ifr", "MultiViewGlobalAttentionTransformerIFR", seed=56, rope=True,
                                        indices=[1, 3])
     golden_self_attention_info_sharing("alternating_attn_tiny_ifr", "MultiViewAlternatingAttentionTransformerIFR", seed=57, rope=True,

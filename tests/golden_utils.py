@@ -38,3 +38,29 @@ def c5_modules(cfg):
                                     layer_dims=[12, 24, 48, 96], feature_dim=32)
     m.dpt_regressor_head = DPTRegressionProcessor(input_feature_dim=32, output_dim=1)
     return m
+
+
+def token_levels(cfg, a, dev="cpu"):
+    """additional-token fixtures: [(maps, global extras or None, per-view extras or None)] for the final output and every
+    tapped depth, plus the per-level loss weights used by oracle/make_golden.py:golden_additional_tokens."""
+    n_levels = 1 + (len(cfg["indices"]) if cfg.get("indices") else 0)
+    V = cfg["V"]
+    levels = []
+    for k in range(n_levels):
+        maps = [a[f"l{k}_out{v}"].to(dev) for v in range(V)]
+        ex = a[f"l{k}_extra"].to(dev) if cfg["T"] else None
+        pv = [a[f"l{k}_pv{v}"].to(dev) for v in range(V)] if cfg["Tv"] else None
+        levels.append((maps, ex, pv))
+    return levels, [1.0 if k == 0 else k - 0.5 for k in range(n_levels)]
+
+
+def token_loss(levels, weights_):
+    tot = 0
+    for (maps, ex, pv), wk in zip(levels, weights_):
+        lv = sum(t.sum() for t in maps)
+        if ex is not None:
+            lv = lv + 2 * ex.sum()
+        if pv is not None:
+            lv = lv + 3 * sum(t.sum() for t in pv)
+        tot = tot + wk * lv
+    return tot

@@ -434,6 +434,61 @@ def test_self_attention_info_sharing_ifr_vs_reference_golden(name):
     assert isinstance(only, list) and len(only) == len(cfg["indices"])
 
 
+@pytest.mark.parametrize("name", ["global_attn_tiny_tokens", "alternating_attn_tiny_tokens", "alternating_attn_tiny_pv_tokens"])
+def test_additional_input_tokens_vs_reference_golden(name):
+    """global / per-view additional input tokens through the B200 engine (ragged sequence lengths V*(N+Tv)+T; the
+    alternating variant's frame-level blocks skip the global tokens) vs the reference's golden outputs and gradients."""
+    from golden_utils import token_levels, token_loss
+
+    cfg, a = load(name)
+    kw = dict(indices=cfg["indices"]) if cfg["indices"] is not None else {}
+    m = getattr(U, cfg["cls"])(name="mv", input_embed_dim=cfg["C_in"], depth=cfg["depth"], dim=cfg["dim"], num_heads=cfg["heads"],
+                               use_rand_idx_pe_for_non_reference_views=False, **kw)
+    m.load_state_dict(weights(cfg), strict=False)
+    m = m.to(DEV)
+    V = cfg["V"]
+    feats = [a[f"feat{v}"].to(DEV).requires_grad_(True) for v in range(V)]
+    extra = a["extra"].to(DEV).requires_grad_(True) if cfg["T"] else None
+    pv = [a[f"pv{v}"].to(DEV).requires_grad_(True) for v in range(V)] if cfg["Tv"] else None
+    res = m(U.MultiViewTransformerInput(features=feats, additional_input_tokens=extra, additional_input_tokens_per_view=pv))
+    outs = [res] if cfg["indices"] is None else [res[0]] + list(res[1])
+    ours = [(o.features, o.additional_token_features, o.additional_token_features_per_view) for o in outs]
+    gold, wts = token_levels(cfg, a, DEV)
+    sd = {k: v.to(DEV) for k, v in weights(cfg).items()}
+
+    def flat(levels):
+        return [t for (mm, ee, pp) in levels for t in list(mm) + ([ee] if ee is not None else []) + (list(pp) if pp is not None else [])]
+
+    def oracle_all():
+        o = O.self_attention_info_sharing(sd, "", [f.detach() for f in feats], cfg["depth"], cfg["heads"],
+                                          alternating="Alternating" in cfg["cls"], pe_for_non_ref=cfg["pe_for_non_ref"],
+                                          indices=cfg["indices"], extra=extra.detach() if extra is not None else None,
+                                          extra_per_view=[t.detach() for t in pv] if pv is not None else None)
+        return flat([o] if cfg["indices"] is None else [o[0]] + list(o[1]))
+
+    ref_err = max(_autocast_err(oracle_all))
+    fo, fg = flat(ours), flat(gold)
+    assert len(fo) == len(fg) and all(x.shape == g.shape for x, g in zip(fo, fg))
+    err = max(O.parity(x, g)[1] for x, g in zip(fo, fg))
+    print(f"{name}: ours vs reference golden rel {err:.3e} over {len(fo)} outputs (autocast-bf16 oracle: {ref_err:.3e})")
+    assert err <= 1.5 * ref_err + 2e-3, (err, ref_err)
+    token_loss(ours, wts).backward()
+    blk = m.self_attention_blocks
+    for prm, arr in ((blk[1].attn.qkv.weight, "grad_qkv1"), (blk[1].mlp.fc2.bias, "grad_fc2_b1"), (blk[0].mlp.fc2.bias, "grad_fc2_b0"),
+                     (m.proj_embed.weight, "grad_proj_embed"), (m.proj_embed.bias, "grad_proj_embed_b"), (feats[0], "grad_in0"),
+                     (extra, "grad_extra"), (pv[-1] if pv else None, "grad_pv_last")):
+        if prm is None:
+            continue
+        e = O.parity(prm.grad, a[arr].to(DEV))[1]
+        print(f"  {arr}: rel {e:.3e}")
+        assert e <= 5e-2, (arr, e)
+    # the reference refuses a positional-encoding plugin together with additional tokens (global_attention_transformer.py:341-351)
+    m2 = getattr(U, cfg["cls"])(name="mv", input_embed_dim=cfg["C_in"], depth=2, dim=cfg["dim"], num_heads=cfg["heads"],
+                                custom_positional_encoding="rope" if "Global" in cfg["cls"] else U.RoPE2D(freq=100.0)).to(DEV)
+    with pytest.raises(ValueError):
+        m2(U.MultiViewTransformerInput(features=[f.detach() for f in feats], additional_input_tokens=extra, additional_input_tokens_per_view=pv))
+
+
 def test_cross_attention_qk_norm_layerscale_vs_reference_golden():
     """`MultiViewCrossAttentionTransformer(qk_norm=True, init_values=...)`: per-head q/k LayerNorm fused with
     RoPE (uc_headnorm_*) and LayerScale (uc_layerscale_*) vs the reference's golden outputs and gradients."""

@@ -232,6 +232,39 @@ def test_self_attention_info_sharing_ifr_golden(name):
     _close(feats[0].grad, a["grad_in0"], 1e-4)
 
 
+@pytest.mark.parametrize("name", ["global_attn_tiny_tokens", "alternating_attn_tiny_tokens", "alternating_attn_tiny_pv_tokens"])
+def test_additional_input_tokens_golden(name):
+    """global and per-view additional input tokens -- oracle == reference golden for every output (maps, global
+    token features, per-view token features; final and tapped levels) and for the gradients."""
+    from golden_utils import token_levels, token_loss
+
+    cfg, a = load(name)
+    sd = {k: v.requires_grad_(True) for k, v in weights(cfg).items()}
+    feats = [a[f"feat{v}"].clone().requires_grad_(True) for v in range(cfg["V"])]
+    extra = a["extra"].clone().requires_grad_(True) if cfg["T"] else None
+    pv = [a[f"pv{v}"].clone().requires_grad_(True) for v in range(cfg["V"])] if cfg["Tv"] else None
+    out = O.self_attention_info_sharing(sd, "", feats, cfg["depth"], cfg["heads"], alternating="Alternating" in cfg["cls"],
+                                        pe_for_non_ref=cfg["pe_for_non_ref"], indices=cfg["indices"], extra=extra, extra_per_view=pv)
+    ours = [out] if cfg["indices"] is None else [out[0]] + list(out[1])
+    gold, wts = token_levels(cfg, a)
+    for (m_, e_, p_), (gm, ge, gp) in zip(ours, gold):
+        for x, g in zip(m_, gm):
+            _close(x, g)
+        if ge is not None:
+            _close(e_, ge)
+        if gp is not None:
+            for x, g in zip(p_, gp):
+                _close(x, g)
+    token_loss(ours, wts).backward()
+    _close(sd["self_attention_blocks.1.attn.qkv.weight"].grad, a["grad_qkv1"], 1e-4)
+    _close(sd["self_attention_blocks.0.mlp.fc2.bias"].grad, a["grad_fc2_b0"], 1e-4)
+    _close(feats[0].grad, a["grad_in0"], 1e-4)
+    if cfg["T"]:
+        _close(extra.grad, a["grad_extra"], 1e-4)
+    if cfg["Tv"]:
+        _close(pv[-1].grad, a["grad_pv_last"], 1e-4)
+
+
 def test_cross_attention_qk_norm_layerscale_golden():
     """`MultiViewCrossAttentionTransformer(qk_norm=True, init_values=0.5)` -- oracle == reference golden, and our
     containers register q_norm / k_norm / ls{1,2,3}.gamma under the reference's keys in the reference's order."""

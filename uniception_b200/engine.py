@@ -635,75 +635,84 @@ def decoder_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[torch.Te
 # global / alternating self-attention over all views (info_sharing/global_attention_transformer.py:224-462,
 # alternating_attention_transformer.py:397-442): the encoder block arithmetic on the concatenated token set
 # ------------------------------------------------------------------------------------------------
-def mv_self_attn_fwd(pk: ParamPack, p: str, toks: List[torch.Tensor], B: int, h: int, w: int, depth: int, heads: int,
-                     rope_base: Optional[float], rope_f0: float, alternating: bool, view_pe: Optional[torch.Tensor],
-                     has_proj_embed: bool, softmax_scaling=None, take: Sequence[int] = (), norm_intermediate: bool = True):
-    """toks: per-view bf16 [B*N, C_in]; view_pe: fp32 [V, dim] view-index encodings added after proj_embed (or None).
-    Rows are ordered (batch, view, token), so the SAME buffer is a [B, V*N] sequence set for the global layers and a
-    [B*V, N] one for the frame-level layers of the alternating variant: no data movement between the two.
+def mv_self_attn_fwd(pk: ParamPack, p: str, x_in: torch.Tensor, B: int, nv: int, n_view: int, n_extra: int, h: int, w: int,
+                     depth: int, heads: int, rope_base: Optional[float], rope_f0: float, alternating: bool,
+                     view_pe: Optional[torch.Tensor], has_proj_embed: bool, softmax_scaling=None, take: Sequence[int] = (),
+                     norm_intermediate: bool = True):
+    """x_in: bf16 [B*L, C_in], rows ordered (batch, [view, token], extra) with L = nv*n_view + n_extra: per view its h*w patch
+    tokens followed by its per-view additional tokens (n_view of them in total), then n_extra global additional tokens
+    (global_attention_transformer.py:266-333).  view_pe: fp32 [V, dim] view-index encodings added after proj_embed to the view
+    tokens only (:365-400), or None.  With n_extra == 0 the SAME buffer is a [B, V*n_view] sequence set for the global layers and
+    a [B*V, n_view] one for the frame-level layers of the alternating variant: no data movement between the two; with global
+    additional tokens the frame layers run on a gathered copy of the view rows and the extra rows skip the block
+    (alternating_attention_transformer.py:402-447).
     take / norm_intermediate: intermediate-feature-returner variants (global_attention_transformer.py:766-774).
-    Returns (per-view final tokens, [per-view intermediate tokens per taken depth], saved)."""
-    nv, N, dev = len(toks), h * w, toks[0].device
-    x_in = torch.cat([t.view(B, N, -1) for t in toks], dim=1).reshape(B * nv * N, -1)
+    Returns (final normalised tokens [B*L, dim], [intermediate [B*L, dim] per taken depth], saved)."""
+    dev = x_in.device
+    L = nv * n_view + n_extra
     rope = Rope(B * nv, h, w, rope_base, rope_f0, dev) if rope_base is not None else None
+    assert rope is None or (n_extra == 0 and n_view == h * w), "RoPE is not defined for additional tokens"
     pe = None
-    if view_pe is not None:  # [V, dim] -> one row per token, bf16 like the residual stream it is added to
-        pe = view_pe.to(torch.bfloat16).repeat_interleave(N, dim=0).repeat(B, 1).contiguous()
+    if view_pe is not None:  # [V, dim] -> one row per token (zeros for the global extras), bf16 like the stream it is added to
+        rows = view_pe.to(torch.bfloat16).repeat_interleave(n_view, dim=0)
+        if n_extra:
+            rows = torch.cat([rows, torch.zeros(n_extra, rows.shape[1], dtype=rows.dtype, device=dev)], dim=0)
+        pe = rows.repeat(B, 1).contiguous()
     if has_proj_embed:
         x = linear_fwd(pk, p + "proj_embed", x_in, residual=pe)  # the view encoding rides the GEMM's residual epilogue
     else:
         x = x_in if pe is None else ops.elementwise(0, x_in.contiguous(), pe)
-    saved = {"x_in": x_in, "blocks": [], "B": B, "N": N, "nv": nv, "rope": rope, "inter": []}
-
-    def split(t):
-        return [u.reshape(B * N, -1).contiguous() for u in t.view(B, nv, N, -1).unbind(1)]
-
+    saved = {"x_in": x_in, "blocks": [], "B": B, "L": L, "nv": nv, "n_view": n_view, "n_extra": n_extra, "rope": rope, "inter": []}
+    nvt = nv * n_view
     inter = []
     for i in range(depth):
         frame = alternating and i % 2 == 1
-        Bb, Nn = (B * nv, N) if frame else (B, nv * N)
         bs: list = []
         bp = f"{p}self_attention_blocks.{i}."
-        x = self_attn_fwd(pk, bp, x, Bb, Nn, heads, rope, "norm1", bs, attn_scale(softmax_scaling, Nn), ls_name(pk, bp, 1))
-        x = mlp_fwd(pk, bp, x, "norm2", bs, ls_name(pk, bp, 2))
+        if frame and n_extra:
+            x3 = x.view(B, L, -1)
+            xv = x3[:, :nvt].reshape(B * nvt, -1)
+            xv = self_attn_fwd(pk, bp, xv, B * nv, n_view, heads, rope, "norm1", bs, attn_scale(softmax_scaling, n_view), ls_name(pk, bp, 1))
+            xv = mlp_fwd(pk, bp, xv, "norm2", bs, ls_name(pk, bp, 2))
+            x = torch.cat([xv.view(B, nvt, -1), x3[:, nvt:]], dim=1).reshape(B * L, -1)
+        else:
+            Bb, Nn = (B * nv, n_view) if frame else (B, L)
+            x = self_attn_fwd(pk, bp, x, Bb, Nn, heads, rope, "norm1", bs, attn_scale(softmax_scaling, Nn), ls_name(pk, bp, 1))
+            x = mlp_fwd(pk, bp, x, "norm2", bs, ls_name(pk, bp, 2))
         saved["blocks"].append(bs)
         if i in take:
             if norm_intermediate:
                 yi, m, r = ln_fwd(pk, p + "norm", x)
                 saved["inter"].append((i, x, m, r))
-                inter.append(split(yi))
+                inter.append(yi)
             else:
                 saved["inter"].append((i, None, None, None))
-                inter.append(split(x))
+                inter.append(x)
     y, mean, rstd = ln_fwd(pk, p + "norm", x)
     saved["final"] = (x, mean, rstd)
-    return split(y), inter, saved
+    return y, inter, saved
 
 
-def mv_self_attn_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[torch.Tensor]], depth: int, heads: int,
+def mv_self_attn_bwd(pk: ParamPack, p: str, saved, d_out: Optional[torch.Tensor], depth: int, heads: int,
                      alternating: bool, has_proj_embed: bool, need_input_grad: bool = True,
-                     d_inter: Sequence[Sequence[Optional[torch.Tensor]]] = ()):
-    B, N, nv, rope = saved["B"], saved["N"], saved["nv"], saved["rope"]
+                     d_inter: Sequence[Optional[torch.Tensor]] = ()):
+    """d_out / d_inter[k]: bf16 [B*L, dim] gradients of the final / tapped outputs (or None).  Returns d x_in or None."""
+    B, L, nv, n_view, n_extra, rope = saved["B"], saved["L"], saved["nv"], saved["n_view"], saved["n_extra"], saved["rope"]
     x, mean, rstd = saved["final"]
-    C = x.shape[1]
-
-    def join(parts):
-        """per-view gradients ([B*N, C] or None) -> [(b, v, n) rows, C], or None when every view is None."""
-        if all(d is None for d in parts):
-            return None
-        ps = [(d if d is not None else torch.zeros(B * N, C, dtype=torch.bfloat16, device=x.device)).view(B, N, -1) for d in parts]
-        return torch.stack(ps, dim=1).reshape(B * nv * N, -1).contiguous()
-
+    nvt = nv * n_view
+    # fused bias-gradient sinks hand colsum(dx) of one block to the next; with global extras the frame-level blocks see
+    # only the view rows, so the cross-block sinks would sum the wrong row set
+    xsink = not (alternating and n_extra)
     inter_at = {i: (k, xi, m, r) for k, (i, xi, m, r) in enumerate(saved["inter"])}
-    dy = join(d_outs)
-    sink = bias_sink(pk, f"{p}self_attention_blocks.{depth - 1}.mlp.fc2") if (depth > 0 and (depth - 1) not in inter_at) else None
-    dx = ln_bwd(pk, p + "norm", dy, x, mean, rstd, colsum=sink) if dy is not None else None
+    sink = bias_sink(pk, f"{p}self_attention_blocks.{depth - 1}.mlp.fc2") if (depth > 0 and xsink and (depth - 1) not in inter_at) else None
+    dx = ln_bwd(pk, p + "norm", d_out.contiguous(), x, mean, rstd, colsum=sink) if d_out is not None else None
     done = dx is not None and sink is not None
     for i in reversed(range(depth)):
         if i in inter_at:
             k, xi, m, r = inter_at[i]
-            g = join(d_inter[k]) if k < len(d_inter) and d_inter[k] is not None else None
+            g = d_inter[k] if k < len(d_inter) else None
             if g is not None:
+                g = g.contiguous()
                 if xi is not None:  # normalised intermediate: through the shared final norm
                     dx = ln_bwd(pk, p + "norm", g, xi, m, r, dres=dx)
                 else:
@@ -711,28 +720,32 @@ def mv_self_attn_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[tor
         if dx is None:
             continue
         frame = alternating and i % 2 == 1
-        Bb, Nn = (B * nv, N) if frame else (B, nv * N)
         bs = saved["blocks"][i]
         bp = f"{p}self_attention_blocks.{i}."
         sink = bias_sink(pk, bp + "attn.proj")
-        dx = mlp_bwd(pk, bp, dx, "norm2", bs[1], bias_done=done, out_sink=sink, ls=ls_name(pk, bp, 2))
         if i > 0:
-            nxt = bias_sink(pk, f"{p}self_attention_blocks.{i - 1}.mlp.fc2") if (i - 1) not in inter_at else None
+            nxt = bias_sink(pk, f"{p}self_attention_blocks.{i - 1}.mlp.fc2") if (xsink and (i - 1) not in inter_at) else None
         else:
-            nxt = bias_sink(pk, p + "proj_embed") if has_proj_embed else None
-        dx = self_attn_bwd(pk, bp, dx, Bb, Nn, heads, rope, "norm1", bs[0], bias_done=sink is not None, out_sink=nxt,
-                           ls=ls_name(pk, bp, 1))
+            nxt = bias_sink(pk, p + "proj_embed") if (has_proj_embed and xsink) else None
+        if frame and n_extra:
+            d3 = dx.view(B, L, -1)
+            dv = d3[:, :nvt].reshape(B * nvt, -1)
+            dv = mlp_bwd(pk, bp, dv, "norm2", bs[1], bias_done=False, out_sink=sink, ls=ls_name(pk, bp, 2))
+            dv = self_attn_bwd(pk, bp, dv, B * nv, n_view, heads, rope, "norm1", bs[0], bias_done=sink is not None, out_sink=None,
+                               ls=ls_name(pk, bp, 1))
+            dx = torch.cat([dv.view(B, nvt, -1), d3[:, nvt:]], dim=1).reshape(B * L, -1)
+        else:
+            Bb, Nn = (B * nv, n_view) if frame else (B, L)
+            dx = mlp_bwd(pk, bp, dx, "norm2", bs[1], bias_done=done, out_sink=sink, ls=ls_name(pk, bp, 2))
+            dx = self_attn_bwd(pk, bp, dx, Bb, Nn, heads, rope, "norm1", bs[0], bias_done=sink is not None, out_sink=nxt,
+                               ls=ls_name(pk, bp, 1))
         done = nxt is not None
         pk.notify_done(bp)
     if dx is None:
-        return [None] * nv
+        return None
     if has_proj_embed:  # the view encoding is a constant: its gradient is dropped
-        d_in = linear_bwd(pk, p + "proj_embed", dx, saved["x_in"], need_dx=need_input_grad, bias_done=done and depth > 0)
-    else:
-        d_in = dx
-    if d_in is None:
-        return [None] * nv
-    return [t.reshape(B * N, -1).contiguous() for t in d_in.view(B, nv, N, -1).unbind(1)]
+        return linear_bwd(pk, p + "proj_embed", dx, saved["x_in"], need_dx=need_input_grad, bias_done=done and depth > 0)
+    return dx
 
 
 # ------------------------------------------------------------------------------------------------

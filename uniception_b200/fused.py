@@ -75,32 +75,30 @@ class DecoderFn(torch.autograd.Function):
 
 
 class MultiViewSelfAttnFn(torch.autograd.Function):
-    """Global / alternating self-attention info sharing: per-view token tensors in; per-view normalised tokens, then the
-    flattened intermediates (depth-major), out."""
+    """Global / alternating self-attention info sharing on the assembled token sequence: x_in [B*L, C_in] (rows: batch,
+    [view, token], global extras) -> final normalised tokens [B*L, dim], then one [B*L, dim] tensor per tapped depth."""
 
     @staticmethod
-    def forward(ctx, pk: ParamPack, prefix: str, cfg: dict, nv: int, *tensors):
-        toks = [t.contiguous() if t.dtype == torch.bfloat16 else t.to(torch.bfloat16).contiguous() for t in tensors[:nv]]
-        outs, inter, saved = E.mv_self_attn_fwd(pk, prefix, toks, cfg["B"], cfg["h"], cfg["w"], cfg["depth"], cfg["heads"],
-                                                cfg["rope_base"], cfg["rope_f0"], cfg["alternating"], cfg["view_pe"],
-                                                cfg["has_proj_embed"], cfg.get("softmax_scaling"), cfg.get("take", ()),
-                                                cfg.get("norm_intermediate", True))
-        ctx.pk, ctx.prefix, ctx.cfg, ctx.saved, ctx.nv = pk, prefix, cfg, saved, nv
-        ctx.n_levels = len(inter)
-        ctx.in_dtypes = [t.dtype for t in tensors[:nv]]
-        return (*outs, *[t for lvl in inter for t in lvl])
+    def forward(ctx, pk: ParamPack, prefix: str, cfg: dict, x_in, *params):
+        xb = x_in.contiguous() if x_in.dtype == torch.bfloat16 else x_in.to(torch.bfloat16).contiguous()
+        y, inter, saved = E.mv_self_attn_fwd(pk, prefix, xb, cfg["B"], cfg["nv"], cfg["n_view"], cfg["n_extra"], cfg["h"], cfg["w"],
+                                             cfg["depth"], cfg["heads"], cfg["rope_base"], cfg["rope_f0"], cfg["alternating"],
+                                             cfg["view_pe"], cfg["has_proj_embed"], cfg.get("softmax_scaling"), cfg.get("take", ()),
+                                             cfg.get("norm_intermediate", True))
+        ctx.pk, ctx.prefix, ctx.cfg, ctx.saved = pk, prefix, cfg, saved
+        ctx.in_dtype = x_in.dtype
+        return (y, *inter)
 
     @staticmethod
     def backward(ctx, *grads):
-        pk, nv, cfg = ctx.pk, ctx.nv, ctx.cfg
+        pk, cfg = ctx.pk, ctx.cfg
         _prep_grads(pk)
-        need_in = any(ctx.needs_input_grad[4:4 + nv])
-        d_inter = [list(grads[nv + l * nv: nv + (l + 1) * nv]) for l in range(ctx.n_levels)]
-        d_in = E.mv_self_attn_bwd(pk, ctx.prefix, ctx.saved, list(grads[:nv]), cfg["depth"], cfg["heads"], cfg["alternating"],
-                                  cfg["has_proj_embed"], need_input_grad=need_in, d_inter=d_inter)
+        d_in = E.mv_self_attn_bwd(pk, ctx.prefix, ctx.saved, grads[0], cfg["depth"], cfg["heads"], cfg["alternating"],
+                                  cfg["has_proj_embed"], need_input_grad=ctx.needs_input_grad[3], d_inter=list(grads[1:]))
         ctx.saved = None
-        d_in = [g if (g is None or g.dtype == dt) else g.to(dt) for g, dt in zip(d_in, ctx.in_dtypes)]
-        return (None, None, None, None, *d_in) + (None,) * (len(ctx.needs_input_grad) - 4 - nv)
+        if d_in is not None and d_in.dtype != ctx.in_dtype:
+            d_in = d_in.to(ctx.in_dtype)
+        return (None, None, None, d_in) + (None,) * (len(ctx.needs_input_grad) - 4)
 
 
 class LinearHeadFn(torch.autograd.Function):

@@ -254,8 +254,8 @@ class MultiViewGlobalAttentionTransformer(UniCeptionInfoSharingBase):
     """UniCeption Multi-View Global-Attention Transformer on the B200 engine (global_attention_transformer.py:25-462):
     all views' tokens form one sequence of V*N tokens per batch element, `depth` SelfAttentionBlocks, final norm.
     Same constructor, state-dict keys (incl. the `view_pos_table` buffer) and I/O dataclasses as the reference.
-    Block flags built: qk_norm, LayerScale (init_values), scalable softmax / entropy scaling.  Not built: additional input
-    tokens, dropout / stochastic depth, activation checkpointing (NotImplementedError)."""
+    Additional input tokens (global and per-view) are supported.  Block flags built: qk_norm, LayerScale (init_values),
+    scalable softmax / entropy scaling.  Not built: dropout / stochastic depth, activation checkpointing (NotImplementedError)."""
 
     ALTERNATING = False
     _PE_NON_REF_DEFAULT = True
@@ -335,35 +335,80 @@ class MultiViewGlobalAttentionTransformer(UniCeptionInfoSharingBase):
             pe[1:] = self.view_pos_table[idx.to(self.view_pos_table.device)]
         return pe
 
-    def forward_tokens(self, toks: List[torch.Tensor], B: int, h: int, w: int, pk: ParamPack, prefix: str, take=(),
-                       norm_intermediate=True):
-        """per-view tokens -> (per-view final tokens, [[per-view intermediate tokens] per taken depth])."""
-        nv = len(toks)
+    def forward_sequence(self, x_in: torch.Tensor, B: int, nv: int, n_view: int, n_extra: int, h: int, w: int, pk: ParamPack,
+                         prefix: str, take=(), norm_intermediate=True):
+        """assembled token sequence [B*L, C_in] -> (final [B*L, dim], [tapped [B*L, dim]]); L = nv*n_view + n_extra."""
         fr = fusable_rope(self.custom_positional_encoding)
-        cfg = dict(B=B, h=h, w=w, depth=self.depth, heads=self.num_heads, rope_base=fr[0] if fr else None,
-                   rope_f0=fr[1] if fr else 1.0, alternating=self.ALTERNATING, view_pe=self._view_pe(nv),
-                   has_proj_embed=isinstance(self.proj_embed, nn.Linear), softmax_scaling=self.softmax_scaling,
-                   take=tuple(take), norm_intermediate=norm_intermediate)
-        outs = fused.MultiViewSelfAttnFn.apply(pk, prefix, cfg, nv, *toks, *pk.params.values())
-        rest = outs[nv:]
-        return list(outs[:nv]), [list(rest[l * nv:(l + 1) * nv]) for l in range(len(rest) // nv)]
+        cfg = dict(B=B, nv=nv, n_view=n_view, n_extra=n_extra, h=h, w=w, depth=self.depth, heads=self.num_heads,
+                   rope_base=fr[0] if fr else None, rope_f0=fr[1] if fr else 1.0, alternating=self.ALTERNATING,
+                   view_pe=self._view_pe(nv), has_proj_embed=isinstance(self.proj_embed, nn.Linear),
+                   softmax_scaling=self.softmax_scaling, take=tuple(take), norm_intermediate=norm_intermediate)
+        outs = fused.MultiViewSelfAttnFn.apply(pk, prefix, cfg, x_in, *pk.params.values())
+        return outs[0], list(outs[1:])
 
     def _check_input(self, model_input):
         feats = model_input.features
         assert len(feats) <= self.max_num_views_for_pe, f"Expected less than {self.max_num_views_for_pe} views, got {len(feats)}"
         assert all(f.shape[1] == self.input_embed_dim for f in feats), f"All views must have input dimension {self.input_embed_dim}"
         assert all(f.ndim == 4 for f in feats), "All views must have 4 dimensions (N, C, H, W)"
-        if model_input.additional_input_tokens is not None or model_input.additional_input_tokens_per_view is not None:
-            raise NotImplementedError("uniception_b200: additional input tokens are not built (SURVEY.md 8f2)")
+        B = feats[0].shape[0]
+        per_view, extra = model_input.additional_input_tokens_per_view, model_input.additional_input_tokens
+        if per_view is not None:  # global_attention_transformer.py:268-282
+            assert len(per_view) == len(feats), \
+                f"Number of additional token tensors ({len(per_view)}) must match number of views ({len(feats)})"
+            assert all(t.ndim == 3 for t in per_view), "Additional tokens per view must have 3 dimensions (N, C, T)"
+            assert all(t.shape[1] == self.input_embed_dim for t in per_view), \
+                f"Additional tokens per view must have input dimension {self.input_embed_dim}"
+            assert all(t.shape[0] == B for t in per_view), "Batch size mismatch for additional tokens per view"
+        if extra is not None:  # :323-329
+            assert extra.ndim == 3, "Additional tokens must have 3 dimensions (N, C, T)"
+            assert extra.shape[1] == self.input_embed_dim, f"Additional tokens must have input dimension {self.input_embed_dim}"
+            assert extra.shape[0] == B, "Batch size mismatch for additional tokens"
+        if self.custom_positional_encoding is not None and (per_view is not None or extra is not None):  # :341-351
+            raise ValueError("Custom positional encoding is not supported when additional_input_tokens or "
+                             "additional_input_tokens_per_view are provided. Please set custom_positional_encoding=None "
+                             "or remove additional tokens from the input.")
         if not feats[0].is_cuda:
             raise RuntimeError(f"uniception_b200.{type(self).__name__} runs on CUDA only (no CPU fallback)")
 
+    def _assemble(self, model_input):
+        """per-view maps (+ per-view / global additional tokens, [B, C, T]) -> bf16 [B*L, C_in] rows ordered (batch, [view,
+        patch tokens then the view's extras], global extras) (global_attention_transformer.py:266-333)."""
+        feats = model_input.features
+        B, C, h, w = feats[0].shape
+        N = h * w
+        per_view, extra = model_input.additional_input_tokens_per_view, model_input.additional_input_tokens
+        parts = []
+        for v, f in enumerate(feats):
+            parts.append(fused.NchwToNlcFn.apply(f).view(B, N, C))
+            if per_view is not None:
+                parts.append(per_view[v].permute(0, 2, 1).to(torch.bfloat16))
+        n_view = N + (per_view[0].shape[2] if per_view is not None else 0)
+        n_extra = 0
+        if extra is not None:
+            n_extra = extra.shape[2]
+            parts.append(extra.permute(0, 2, 1).to(torch.bfloat16))
+        x_in = torch.cat(parts, dim=1).reshape(B * (len(feats) * n_view + n_extra), C)
+        return x_in, (B, len(feats), n_view, n_extra, h, w)
+
+    def _split(self, y: torch.Tensor, layout, model_input) -> MultiViewTransformerOutput:
+        """[B*L, dim] -> per-view maps (+ per-view / global additional token features [B, dim, T]) (:434-461)."""
+        B, nv, n_view, n_extra, h, w = layout
+        N = h * w
+        y3 = y.view(B, nv * n_view + n_extra, -1)
+        views = (y3[:, :nv * n_view] if n_extra else y3).reshape(B, nv, n_view, -1).unbind(1)
+        feats = [fused.NlcToNchwFn.apply((t[:, :N] if n_view > N else t).reshape(B * N, -1), B, h, w) for t in views]
+        per_view = None
+        if model_input.additional_input_tokens_per_view is not None:
+            per_view = [t[:, N:].permute(0, 2, 1).float().contiguous() for t in views]
+        extra = y3[:, nv * n_view:].permute(0, 2, 1).float().contiguous() if model_input.additional_input_tokens is not None else None
+        return MultiViewTransformerOutput(features=feats, additional_token_features=extra, additional_token_features_per_view=per_view)
+
     def forward(self, model_input: MultiViewTransformerInput) -> MultiViewTransformerOutput:
         self._check_input(model_input)
-        B, _, h, w = model_input.features[0].shape
-        toks = [fused.NchwToNlcFn.apply(f) for f in model_input.features]
-        outs, _ = self.forward_tokens(toks, B, h, w, self._pack(), "")
-        return MultiViewTransformerOutput(features=[fused.NlcToNchwFn.apply(t, B, h, w) for t in outs])
+        x_in, layout = self._assemble(model_input)
+        y, _ = self.forward_sequence(x_in, *layout, self._pack(), "")
+        return self._split(y, layout, model_input)
 
 
 class MultiViewGlobalAttentionTransformerIFR(MultiViewGlobalAttentionTransformer, IntermediateFeatureReturner):
@@ -378,14 +423,13 @@ class MultiViewGlobalAttentionTransformerIFR(MultiViewGlobalAttentionTransformer
 
     def forward(self, model_input: MultiViewTransformerInput):
         self._check_input(model_input)
-        B, _, h, w = model_input.features[0].shape
         take, _ = feature_take_indices(self.depth, self.indices)
-        toks = [fused.NchwToNlcFn.apply(f) for f in model_input.features]
-        finals, inter = self.forward_tokens(toks, B, h, w, self._pack(), "", take, self.norm_intermediate)
-        inter_out = [MultiViewTransformerOutput(features=[fused.NlcToNchwFn.apply(t, B, h, w) for t in lvl]) for lvl in inter]
+        x_in, layout = self._assemble(model_input)
+        y, inter = self.forward_sequence(x_in, *layout, self._pack(), "", take, self.norm_intermediate)
+        inter_out = [self._split(t, layout, model_input) for t in inter]
         if self.intermediates_only:
             return inter_out
-        return MultiViewTransformerOutput(features=[fused.NlcToNchwFn.apply(t, B, h, w) for t in finals]), inter_out
+        return self._split(y, layout, model_input), inter_out
 
 
 class MultiViewAlternatingAttentionTransformer(MultiViewGlobalAttentionTransformer):
