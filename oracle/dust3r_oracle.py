@@ -173,7 +173,8 @@ def layer_scale(sd: SD, name: str, t: Tensor) -> Tensor:
 
 def self_attention(sd: SD, p: str, x: Tensor, pos: Optional[Tensor], heads: int, base: float, softmax_scaling=None) -> Tensor:
     """libs/croco/blocks.py:105-130 == utils/transformer_blocks.py:208-257 (optional qk_norm and softmax scaling)."""
-    B, N, C = x.shape
+    B, N, _ = x.shape
+    C = sd[p + "qkv.weight"].shape[0] // 3  # == dim, or latent_attn_dim (utils/transformer_blocks.py:178-199)
     d = C // heads
     qkv = linear(x, sd[p + "qkv.weight"], sd.get(p + "qkv.bias")).view(B, N, 3, heads, d).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0], qkv[1], qkv[2]

@@ -379,6 +379,36 @@ def golden_self_attention_info_sharing(name, cls_name, seed, rope, V=2, B=2, hw=
                      shapes={k: list(v) for k, v in shapes.items()}), arrays)
 
 
+def golden_self_attention_block(name, seed, B=2, hw=(4, 5), dim=192, latent=128, heads=2):
+    """A stand-alone `SelfAttentionBlock` (utils/transformer_blocks.py:415-514) with every built option at once:
+    latent_attn_dim, qk_norm, LayerScale, RoPE."""
+    from functools import partial
+
+    from uniception.models.libs.croco.pos_embed import RoPE2D
+    from uniception.models.utils.transformer_blocks import SelfAttentionBlock
+
+    m = SelfAttentionBlock(dim=dim, num_heads=heads, latent_attn_dim=latent, qkv_bias=True, qk_norm=True, init_values=0.5,
+                           norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), custom_positional_encoding=RoPE2D(freq=100.0))
+    sd, shapes = _load_seeded(m, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(B, hw[0] * hw[1], dim, generator=g).requires_grad_(True)
+    pos = O.patch_positions(B, hw[0], hw[1], "cpu")
+    y = m(x, pos)
+    y.sum().backward()
+    params = dict(m.named_parameters())
+    osd = {"b." + k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ox = x.detach().clone().requires_grad_(True)
+    oy = O.encoder_block(osd, "b.", ox, pos, heads, 100.0)
+    _check(f"{name} out", oy, y)
+    oy.sum().backward()
+    arrays = dict(x=x.detach(), y=y, grad_x=x.grad)
+    for k in ("attn.qkv.weight", "attn.q_norm.weight", "attn.proj.weight", "ls1.gamma", "ls2.gamma", "mlp.fc1.bias"):
+        _check(f"{name} grad {k}", osd["b." + k].grad, params[k].grad, 1e-4)
+        arrays["grad_" + k.replace(".", "_")] = params[k].grad
+    _check(f"{name} grad x", ox.grad, x.grad, 1e-4)
+    _save(name, dict(seed=seed, B=B, hw=list(hw), dim=dim, latent=latent, heads=heads, shapes={k: list(v) for k, v in shapes.items()}), arrays)
+
+
 def golden_additional_tokens(name, cls_name, seed, V=2, T=2, Tv=1, B=2, hw=(3, 4), C_in=192, dim=128, depth=4, heads=2, indices=None):
     """Additional input tokens in the global / alternating attention transformers (global_attention_transformer.py:266-333,
     :434-461; alternating_attention_transformer.py:402-447): T global tokens and Tv tokens per view, no positional encoding
@@ -514,6 +544,7 @@ def main():
     golden_cross_attention_scaled("cross_attn_tiny_qknorm_ls", seed=58, scaling=False, qk_norm=True, init_values=0.5)
     golden_self_attention_info_sharing("alternating_attn_tiny_qknorm_ls", "MultiViewAlternatingAttentionTransformer", seed=59,
                                        rope=True, V=3, qk_norm=True, init_values=0.5)
+    golden_self_attention_block("self_attn_block_latent_qknorm_ls", seed=63)
     golden_additional_tokens("global_attn_tiny_tokens", "MultiViewGlobalAttentionTransformer", seed=60, V=3, T=2, Tv=1)
     golden_additional_tokens("alternating_attn_tiny_tokens", "MultiViewAlternatingAttentionTransformerIFR", seed=61, V=2, T=3, Tv=2,
                              indices=[0, 1])

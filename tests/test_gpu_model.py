@@ -193,6 +193,35 @@ def test_granular_blocks_vs_oracle():
     assert x2.grad is not None and cblk.cross_attn.projk.weight.grad is not None
 
 
+def test_self_attention_block_options_vs_reference_golden():
+    """stand-alone `SelfAttentionBlock` with latent_attn_dim + qk_norm + LayerScale + RoPE through the granular
+    autograd ops (HeadNormFn, LayerScaleFn, AttentionFn) vs the reference's golden output and gradients."""
+    from functools import partial
+
+    from uniception_b200.blocks import SelfAttentionBlock
+
+    cfg, a = load("self_attn_block_latent_qknorm_ls")
+    blk = SelfAttentionBlock(cfg["dim"], cfg["heads"], cfg["latent"], qkv_bias=True, qk_norm=True, init_values=0.5,
+                             norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), custom_positional_encoding=U.RoPE2D(freq=100.0))
+    blk.load_state_dict(weights(cfg))
+    blk = blk.to(DEV)
+    x = a["x"].to(DEV).requires_grad_(True)
+    pos = O.patch_positions(cfg["B"], cfg["hw"][0], cfg["hw"][1], DEV)
+    y = blk(x, pos)
+    sd = {"b." + k: v.to(DEV) for k, v in weights(cfg).items()}
+    ref_err = max(_autocast_err(lambda: [O.encoder_block(sd, "b.", x.detach(), pos, cfg["heads"], 100.0)]))
+    err = O.parity(y.float(), a["y"].to(DEV))[1]
+    print(f"SelfAttentionBlock(latent, qk_norm, LayerScale): ours vs reference golden rel {err:.3e} (autocast-bf16 oracle: {ref_err:.3e})")
+    assert err <= 1.5 * ref_err + 2e-3, (err, ref_err)
+    y.float().sum().backward()
+    for prm, k in ((blk.attn.qkv.weight, "attn.qkv.weight"), (blk.attn.q_norm.weight, "attn.q_norm.weight"),
+                   (blk.attn.proj.weight, "attn.proj.weight"), (blk.ls1.gamma, "ls1.gamma"), (blk.ls2.gamma, "ls2.gamma"),
+                   (blk.mlp.fc1.bias, "mlp.fc1.bias"), (x, "x")):
+        e = O.parity(prm.grad.float(), a["grad_" + k.replace(".", "_")].to(DEV))[1]
+        print(f"  grad {k}: rel {e:.3e}")
+        assert e <= 5e-2, (k, e)
+
+
 def test_full_size_property_checks():
     """BASELINE.json sizes (ViT-L/16 + 12-layer decoder, 512x512, B=1 pair): size-independent
     properties -- confidence >= 1, finite outputs, batch-permutation equivariance and

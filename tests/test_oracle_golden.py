@@ -265,6 +265,30 @@ def test_additional_input_tokens_golden(name):
         _close(pv[-1].grad, a["grad_pv_last"], 1e-4)
 
 
+def test_self_attention_block_latent_qk_norm_layerscale_golden():
+    """a stand-alone `SelfAttentionBlock(latent_attn_dim, qk_norm, init_values, RoPE)` -- oracle == reference golden,
+    and our container registers the reference's keys in the reference's order."""
+    from functools import partial
+
+    import uniception_b200 as U
+    from uniception_b200.blocks import SelfAttentionBlock
+
+    cfg, a = load("self_attn_block_latent_qknorm_ls")
+    blk = SelfAttentionBlock(cfg["dim"], cfg["heads"], cfg["latent"], qkv_bias=True, qk_norm=True, init_values=0.5,
+                             norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), custom_positional_encoding=U.RoPE2D(freq=100.0))
+    assert list(blk.state_dict().keys()) == list(cfg["shapes"].keys())
+    assert {k: list(v.shape) for k, v in blk.state_dict().items()} == cfg["shapes"]
+    sd = {"b." + k: v.requires_grad_(True) for k, v in weights(cfg).items()}
+    x = a["x"].clone().requires_grad_(True)
+    pos = O.patch_positions(cfg["B"], cfg["hw"][0], cfg["hw"][1], "cpu")
+    y = O.encoder_block(sd, "b.", x, pos, cfg["heads"], 100.0)
+    _close(y, a["y"])
+    y.sum().backward()
+    for k in ("attn.qkv.weight", "attn.q_norm.weight", "attn.proj.weight", "ls1.gamma", "ls2.gamma", "mlp.fc1.bias"):
+        _close(sd["b." + k].grad, a["grad_" + k.replace(".", "_")], 1e-4)
+    _close(x.grad, a["grad_x"], 1e-4)
+
+
 def test_cross_attention_qk_norm_layerscale_golden():
     """`MultiViewCrossAttentionTransformer(qk_norm=True, init_values=0.5)` -- oracle == reference golden, and our
     containers register q_norm / k_norm / ls{1,2,3}.gamma under the reference's keys in the reference's order."""

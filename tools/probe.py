@@ -18,6 +18,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 def _err(x, ref):
     x, ref = x.double(), ref.double()
     d = (x - ref)
+    d, ref = d.detach(), ref.detach()
     return float(d.abs().max()), float(d.norm() / ref.norm().clamp_min(1e-30))
 
 

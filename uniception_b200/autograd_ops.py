@@ -152,6 +152,31 @@ class LayerScaleFn(torch.autograd.Function):
         return dx if ctx.in_dtype == torch.bfloat16 else dx.to(ctx.in_dtype), dg
 
 
+class HeadNormFn(torch.autograd.Function):
+    """qk_norm on columns [off, off+C) of a packed projection: LayerNorm over every 64-wide head segment
+    (utils/transformer_blocks.py:199-200, :222).  RoPE stays in `AttentionFn`, whose backward returns the gradient w.r.t. the
+    un-rotated values this function produced."""
+
+    @staticmethod
+    def forward(ctx, src, off, C, weight, bias, eps):
+        s2 = _act2d(src)
+        out = torch.empty(s2.shape[0], C, dtype=torch.bfloat16, device=s2.device)
+        ops.headnorm_fwd(s2[:, off:off + C], out, weight.detach().contiguous(), bias.detach().contiguous(), eps)
+        ctx.save_for_backward(s2, weight.detach().contiguous())
+        ctx.meta = (off, C, eps, src.shape, src.dtype)
+        return out.view(*src.shape[:-1], C)
+
+    @staticmethod
+    def backward(ctx, dy):
+        s2, w = ctx.saved_tensors
+        off, C, eps, shp, dt = ctx.meta
+        dsrc = torch.zeros(s2.shape, dtype=torch.bfloat16, device=s2.device)
+        dsrc[:, off:off + C] = _act2d(dy)
+        dg, db = torch.zeros_like(w), torch.zeros_like(w)
+        ops.headnorm_bwd(dsrc[:, off:off + C], s2[:, off:off + C], w, dg, db, eps)
+        return (dsrc.view(shp) if dt == torch.bfloat16 else dsrc.view(shp).to(dt)), None, None, dg, db, None
+
+
 class AttentionFn(torch.autograd.Function):
     """softmax(q k^T / 8) v on token-major bf16 sources; optional fused 2-D RoPE (rotated copies in
     forward, inverse rotation fused into the backward kernels)."""
@@ -203,6 +228,10 @@ def mlp(x, fc1: nn.Linear, fc2: nn.Linear, residual=None):
 
 def layer_norm(x, norm: nn.LayerNorm):
     return LayerNormFn.apply(x, norm.weight, norm.bias, norm.eps)
+
+
+def head_norm(src, off, C, norm: nn.LayerNorm):
+    return HeadNormFn.apply(src, off, C, norm.weight, norm.bias, norm.eps)
 
 
 def layer_scale(x, gamma):

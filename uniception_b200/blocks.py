@@ -49,11 +49,6 @@ def _head_norm(norm_layer, head_dim: int, qk_norm: bool) -> nn.Module:
     return norm_layer(head_dim)
 
 
-def _standalone_only_plain(mod: nn.Module) -> None:
-    _require(not isinstance(getattr(mod, "q_norm", None), nn.LayerNorm),
-             "qk_norm in a stand-alone block forward (use the fused transformer modules)")
-
-
 class Mlp(nn.Module):
     def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, bias=True, drop=0.0):
         super().__init__()
@@ -80,31 +75,41 @@ class Attention(nn.Module):
                  base_token_count_for_entropy_scaling=444, entropy_scaling_growth_factor=1.4, norm_layer=nn.LayerNorm,
                  latent_attn_dim=None, **_ignored):
         super().__init__()
-        assert dim % num_heads == 0, "dim should be divisible by num_heads"
-        _require(latent_attn_dim is None, "latent_attn_dim")
-        _require(dim // num_heads == 64, f"head_dim {dim // num_heads} (only 64)")
+        if latent_attn_dim is not None:  # utils/transformer_blocks.py:178-199: q/k/v live in a latent width
+            assert latent_attn_dim % num_heads == 0, "latent_attn_dim should be divisible by num_heads"
+        else:
+            assert dim % num_heads == 0, "dim should be divisible by num_heads"
+        self.latent_attn = latent_attn_dim is not None
+        width = latent_attn_dim if self.latent_attn else dim
+        _require(width // num_heads == 64, f"head_dim {width // num_heads} (only 64)")
         _require(attn_drop == 0.0 and proj_drop == 0.0, "attention dropout")
         # softmax scaling by the token count (utils/transformer_blocks.py:231-241) folds into the kernels' scale
         self.softmax_scaling = (use_scalable_softmax, use_entropy_scaling, base_token_count_for_entropy_scaling,
                                 entropy_scaling_growth_factor) if (use_scalable_softmax or use_entropy_scaling) else None
         self.num_heads = num_heads
-        self.head_dim = dim // num_heads
+        self.head_dim = width // num_heads
         self.scale = self.head_dim ** -0.5
-        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.qkv = nn.Linear(dim, width * 3, bias=qkv_bias)
         self.q_norm = _head_norm(norm_layer, self.head_dim, qk_norm)  # registration order of transformer_blocks.py:194-202
         self.k_norm = _head_norm(norm_layer, self.head_dim, qk_norm)
-        self.proj = nn.Linear(dim, dim)
+        self.proj = nn.Linear(width, dim)
         self.rope = rope if rope is not None else custom_positional_encoding
         self.custom_positional_encoding = self.rope
 
     def forward(self, x, xpos=None, residual=None):
-        B, N, C = x.shape
-        _standalone_only_plain(self)
+        B, N, _ = x.shape
+        C = self.num_heads * self.head_dim  # the latent width with latent_attn_dim
         if self.rope is not None:
             assert xpos is not None, "Positions of tokens (xpos) are a required input when using custom positional encoding"
         qkv = A.linear(x, self.qkv.weight, self.qkv.bias)
-        o = A.attention(qkv, qkv, B, N, N, self.num_heads, q_off=0, k_off=C, v_off=2 * C, qpos=xpos, kpos=xpos, rope=self.rope,
-                        scale=attn_scale(self.softmax_scaling, N))
+        scale = attn_scale(self.softmax_scaling, N)
+        if isinstance(self.q_norm, nn.LayerNorm):
+            qn = A.head_norm(qkv, 0, C, self.q_norm)
+            kv = torch.cat((A.head_norm(qkv, C, C, self.k_norm), qkv[..., 2 * C:]), dim=-1)
+            o = A.attention(qn, kv, B, N, N, self.num_heads, q_off=0, k_off=0, v_off=C, qpos=xpos, kpos=xpos, rope=self.rope, scale=scale)
+        else:
+            o = A.attention(qkv, qkv, B, N, N, self.num_heads, q_off=0, k_off=C, v_off=2 * C, qpos=xpos, kpos=xpos, rope=self.rope,
+                            scale=scale)
         return A.linear(o, self.proj.weight, self.proj.bias, residual=residual)
 
 
@@ -153,10 +158,11 @@ class CrossAttention(nn.Module):
     def forward(self, query, key, value, qpos=None, kpos=None, residual=None):
         B, Nq, C = query.shape
         Nk = key.shape[1]
-        _standalone_only_plain(self)
         q = A.linear(query, self.projq.weight, self.projq.bias)
         k = A.linear(key, self.projk.weight, self.projk.bias)
         v = A.linear(value, self.projv.weight, self.projv.bias)
+        if isinstance(self.q_norm, nn.LayerNorm):
+            q, k = A.head_norm(q, 0, C, self.q_norm), A.head_norm(k, 0, C, self.k_norm)
         kv = torch.cat((k, v), dim=-1)
         o = A.attention(q, kv, B, Nq, Nk, self.num_heads, q_off=0, k_off=0, v_off=C, qpos=qpos, kpos=kpos,
                         rope=self.custom_positional_encoding, scale=attn_scale(self.softmax_scaling, Nq))
@@ -213,8 +219,8 @@ class CrossAttentionBlock(nn.Module):
 class SelfAttentionBlock(nn.Module):
     """utils/transformer_blocks.py:415-514 (registration order kept: norm1, attn, ls1, norm2, mlp, ls2)."""
 
-    def __init__(self, dim, num_heads, mlp_ratio=4.0, qkv_bias=False, qk_norm=False, proj_drop=0.0, attn_drop=0.0,
-                 init_values=None, drop_path=0.0, act_layer=nn.GELU, norm_layer=nn.LayerNorm, mlp_layer=Mlp,
+    def __init__(self, dim, num_heads, latent_attn_dim=None, mlp_ratio=4.0, qkv_bias=False, qk_norm=False, proj_drop=0.0,
+                 attn_drop=0.0, init_values=None, drop_path=0.0, act_layer=nn.GELU, norm_layer=nn.LayerNorm, mlp_layer=Mlp,
                  custom_positional_encoding=None, use_scalable_softmax=False, use_entropy_scaling=False,
                  base_token_count_for_entropy_scaling=444, entropy_scaling_growth_factor=1.4):
         super().__init__()
@@ -222,7 +228,7 @@ class SelfAttentionBlock(nn.Module):
         _require(mlp_layer is Mlp, "a custom mlp_layer")
         ls = (lambda: LayerScale(dim, init_values=init_values)) if init_values else nn.Identity
         self.norm1 = norm_layer(dim)
-        self.attn = Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, qk_norm=qk_norm, attn_drop=attn_drop, proj_drop=proj_drop,
+        self.attn = Attention(dim, latent_attn_dim=latent_attn_dim, num_heads=num_heads, qkv_bias=qkv_bias, qk_norm=qk_norm, attn_drop=attn_drop, proj_drop=proj_drop,
                               norm_layer=norm_layer, custom_positional_encoding=custom_positional_encoding,
                               use_scalable_softmax=use_scalable_softmax, use_entropy_scaling=use_entropy_scaling,
                               base_token_count_for_entropy_scaling=base_token_count_for_entropy_scaling,
