@@ -222,6 +222,43 @@ def test_self_attention_block_options_vs_reference_golden():
         assert e <= 5e-2, (k, e)
 
 
+def test_gradient_checkpointing_recompute_matches_and_saves_memory():
+    """`gradient_checkpointing=True` (info_sharing/base.py:59-71: every block under torch.utils.checkpoint) = per-block recompute
+    in the engine: same outputs and gradients as the plain path, lower peak memory."""
+    kw = dict(name="mv", input_embed_dim=192, depth=6, dim=256, num_heads=4, use_rand_idx_pe_for_non_reference_views=False,
+              custom_positional_encoding=U.RoPE2D(freq=100.0))
+    torch.manual_seed(3)
+    plain = U.MultiViewAlternatingAttentionTransformer(**kw).to(DEV)
+    ckpt = U.MultiViewAlternatingAttentionTransformer(gradient_checkpointing=True, **kw)
+    ckpt.load_state_dict(plain.state_dict())
+    ckpt = ckpt.to(DEV)
+    feats = [torch.randn(2, 192, 24, 24, device=DEV) for _ in range(3)]
+    # random cotangents: d sum(LayerNorm(x)) / dx vanishes identically for gamma = 1, which would leave only rounding noise
+    cot = [torch.randn(2, 256, 24, 24, device=DEV) for _ in range(3)]
+    res = {}
+    for tag, m in (("plain", plain), ("plain2", plain), ("ckpt", ckpt)):
+        m.zero_grad(set_to_none=True)
+        fin = [f.clone().requires_grad_(True) for f in feats]
+        torch.cuda.synchronize()
+        base = torch.cuda.memory_allocated()
+        out = m(U.MultiViewTransformerInput(features=fin)).features
+        held = torch.cuda.memory_allocated() - base  # activations kept for the backward
+        sum((o * c).sum() for o, c in zip(out, cot)).backward()
+        torch.cuda.synchronize()
+        res[tag] = (out, fin[0].grad, m.self_attention_blocks[2].attn.qkv.weight.grad.clone(), m.proj_embed.bias.grad.clone(), held)
+    for k in range(3):
+        assert torch.equal(res["ckpt"][0][k], res["plain"][0][k])  # the forward pass is deterministic
+    # the backward is not bit-reproducible (fp32 atomics in dq / wgrad, then bf16 rounding): the yardstick is the plain
+    # path's own run-to-run difference
+    for j, nm in ((1, "d_in0"), (2, "d_qkv2"), (3, "d_proj_embed_b")):
+        noise = O.parity(res["plain2"][j], res["plain"][j])[1]
+        e = O.parity(res["ckpt"][j], res["plain"][j])[1]
+        print(f"  {nm}: checkpointed vs plain {e:.2e} (plain run-to-run {noise:.2e})")
+        assert e <= 2 * noise + 1e-3, (nm, e, noise)
+    print(f"activations held after forward: plain {res['plain'][4] / 2**20:.1f} MiB, checkpointed {res['ckpt'][4] / 2**20:.1f} MiB")
+    assert res["ckpt"][4] < 0.5 * res["plain"][4]
+
+
 def test_full_size_property_checks():
     """BASELINE.json sizes (ViT-L/16 + 12-layer decoder, 512x512, B=1 pair): size-independent
     properties -- confidence >= 1, finite outputs, batch-permutation equivariance and

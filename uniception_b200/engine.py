@@ -635,10 +635,19 @@ def decoder_bwd(pk: ParamPack, p: str, saved, d_outs: Sequence[Optional[torch.Te
 # global / alternating self-attention over all views (info_sharing/global_attention_transformer.py:224-462,
 # alternating_attention_transformer.py:397-442): the encoder block arithmetic on the concatenated token set
 # ------------------------------------------------------------------------------------------------
+def _mv_block_fwd(pk: ParamPack, p: str, i: int, x, Bb: int, Nn: int, heads: int, rope, softmax_scaling):
+    """One SelfAttentionBlock on a [Bb*Nn, dim] token buffer -> (new stream, tensors saved for its backward)."""
+    bs: list = []
+    bp = f"{p}self_attention_blocks.{i}."
+    x = self_attn_fwd(pk, bp, x, Bb, Nn, heads, rope, "norm1", bs, attn_scale(softmax_scaling, Nn), ls_name(pk, bp, 1))
+    x = mlp_fwd(pk, bp, x, "norm2", bs, ls_name(pk, bp, 2))
+    return x, bs
+
+
 def mv_self_attn_fwd(pk: ParamPack, p: str, x_in: torch.Tensor, B: int, nv: int, n_view: int, n_extra: int, h: int, w: int,
                      depth: int, heads: int, rope_base: Optional[float], rope_f0: float, alternating: bool,
                      view_pe: Optional[torch.Tensor], has_proj_embed: bool, softmax_scaling=None, take: Sequence[int] = (),
-                     norm_intermediate: bool = True):
+                     norm_intermediate: bool = True, recompute: bool = False):
     """x_in: bf16 [B*L, C_in], rows ordered (batch, [view, token], extra) with L = nv*n_view + n_extra: per view its h*w patch
     tokens followed by its per-view additional tokens (n_view of them in total), then n_extra global additional tokens
     (global_attention_transformer.py:266-333).  view_pe: fp32 [V, dim] view-index encodings added after proj_embed to the view
@@ -647,6 +656,9 @@ def mv_self_attn_fwd(pk: ParamPack, p: str, x_in: torch.Tensor, B: int, nv: int,
     additional tokens the frame layers run on a gathered copy of the view rows and the extra rows skip the block
     (alternating_attention_transformer.py:402-447).
     take / norm_intermediate: intermediate-feature-returner variants (global_attention_transformer.py:766-774).
+    recompute: activation checkpointing per block (`gradient_checkpointing=True`: the reference wraps every block in
+    torch.utils.checkpoint, info_sharing/base.py:59-71, alternating_attention_transformer.py:178-180) -- only each block's input
+    is kept and the backward re-runs the block's forward kernels first.
     Returns (final normalised tokens [B*L, dim], [intermediate [B*L, dim] per taken depth], saved)."""
     dev = x_in.device
     L = nv * n_view + n_extra
@@ -662,24 +674,22 @@ def mv_self_attn_fwd(pk: ParamPack, p: str, x_in: torch.Tensor, B: int, nv: int,
         x = linear_fwd(pk, p + "proj_embed", x_in, residual=pe)  # the view encoding rides the GEMM's residual epilogue
     else:
         x = x_in if pe is None else ops.elementwise(0, x_in.contiguous(), pe)
-    saved = {"x_in": x_in, "blocks": [], "B": B, "L": L, "nv": nv, "n_view": n_view, "n_extra": n_extra, "rope": rope, "inter": []}
+    saved = {"x_in": x_in, "blocks": [], "B": B, "L": L, "nv": nv, "n_view": n_view, "n_extra": n_extra, "rope": rope, "inter": [],
+             "softmax_scaling": softmax_scaling}
     nvt = nv * n_view
     inter = []
     for i in range(depth):
         frame = alternating and i % 2 == 1
-        bs: list = []
-        bp = f"{p}self_attention_blocks.{i}."
         if frame and n_extra:
             x3 = x.view(B, L, -1)
-            xv = x3[:, :nvt].reshape(B * nvt, -1)
-            xv = self_attn_fwd(pk, bp, xv, B * nv, n_view, heads, rope, "norm1", bs, attn_scale(softmax_scaling, n_view), ls_name(pk, bp, 1))
-            xv = mlp_fwd(pk, bp, xv, "norm2", bs, ls_name(pk, bp, 2))
+            blk_in = x3[:, :nvt].reshape(B * nvt, -1)
+            xv, bs = _mv_block_fwd(pk, p, i, blk_in, B * nv, n_view, heads, rope, softmax_scaling)
             x = torch.cat([xv.view(B, nvt, -1), x3[:, nvt:]], dim=1).reshape(B * L, -1)
         else:
             Bb, Nn = (B * nv, n_view) if frame else (B, L)
-            x = self_attn_fwd(pk, bp, x, Bb, Nn, heads, rope, "norm1", bs, attn_scale(softmax_scaling, Nn), ls_name(pk, bp, 1))
-            x = mlp_fwd(pk, bp, x, "norm2", bs, ls_name(pk, bp, 2))
-        saved["blocks"].append(bs)
+            blk_in = x
+            x, bs = _mv_block_fwd(pk, p, i, blk_in, Bb, Nn, heads, rope, softmax_scaling)
+        saved["blocks"].append((blk_in, None) if recompute else (None, bs))
         if i in take:
             if norm_intermediate:
                 yi, m, r = ln_fwd(pk, p + "norm", x)
@@ -720,7 +730,11 @@ def mv_self_attn_bwd(pk: ParamPack, p: str, saved, d_out: Optional[torch.Tensor]
         if dx is None:
             continue
         frame = alternating and i % 2 == 1
-        bs = saved["blocks"][i]
+        blk_in, bs = saved["blocks"][i]
+        if bs is None:  # activation checkpointing: regenerate the block's saved tensors from its input
+            Bb, Nn = (B * nv, n_view) if frame else (B, L)
+            _, bs = _mv_block_fwd(pk, p, i, blk_in, Bb, Nn, heads, rope, saved["softmax_scaling"])
+            saved["blocks"][i] = None
         bp = f"{p}self_attention_blocks.{i}."
         sink = bias_sink(pk, bp + "attn.proj")
         if i > 0:

@@ -84,7 +84,7 @@ class MultiViewSelfAttnFn(torch.autograd.Function):
         y, inter, saved = E.mv_self_attn_fwd(pk, prefix, xb, cfg["B"], cfg["nv"], cfg["n_view"], cfg["n_extra"], cfg["h"], cfg["w"],
                                              cfg["depth"], cfg["heads"], cfg["rope_base"], cfg["rope_f0"], cfg["alternating"],
                                              cfg["view_pe"], cfg["has_proj_embed"], cfg.get("softmax_scaling"), cfg.get("take", ()),
-                                             cfg.get("norm_intermediate", True))
+                                             cfg.get("norm_intermediate", True), cfg.get("recompute", False))
         ctx.pk, ctx.prefix, ctx.cfg, ctx.saved = pk, prefix, cfg, saved
         ctx.in_dtype = x_in.dtype
         return (y, *inter)

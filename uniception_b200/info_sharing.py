@@ -255,7 +255,7 @@ class MultiViewGlobalAttentionTransformer(UniCeptionInfoSharingBase):
     all views' tokens form one sequence of V*N tokens per batch element, `depth` SelfAttentionBlocks, final norm.
     Same constructor, state-dict keys (incl. the `view_pos_table` buffer) and I/O dataclasses as the reference.
     Additional input tokens (global and per-view) are supported.  Block flags built: qk_norm, LayerScale (init_values),
-    scalable softmax / entropy scaling.  Not built: dropout / stochastic depth, activation checkpointing (NotImplementedError)."""
+    scalable softmax / entropy scaling, gradient_checkpointing (per-block recompute).  Not built: dropout / stochastic depth."""
 
     ALTERNATING = False
     _PE_NON_REF_DEFAULT = True
@@ -278,8 +278,9 @@ class MultiViewGlobalAttentionTransformer(UniCeptionInfoSharingBase):
         self.qk_norm, self.init_values = qk_norm, init_values
         self.softmax_scaling = (use_scalable_softmax, use_entropy_scaling, base_token_count_for_entropy_scaling,
                                 entropy_scaling_growth_factor) if (use_scalable_softmax or use_entropy_scaling) else None
-        if gradient_checkpointing:
-            raise NotImplementedError("uniception_b200: gradient checkpointing is not needed (activations fit 180 GB) and not built")
+        # per-block activation checkpointing (info_sharing/base.py:59-71): the engine keeps each block's input only and re-runs
+        # the block's forward kernels in the backward pass
+        self.gradient_checkpointing = gradient_checkpointing
         self.input_embed_dim = input_embed_dim
         self.distinguish_ref_and_non_ref_views = distinguish_ref_and_non_ref_views
         self.use_pe_for_non_reference_views = use_pe_for_non_reference_views
@@ -342,7 +343,8 @@ class MultiViewGlobalAttentionTransformer(UniCeptionInfoSharingBase):
         cfg = dict(B=B, nv=nv, n_view=n_view, n_extra=n_extra, h=h, w=w, depth=self.depth, heads=self.num_heads,
                    rope_base=fr[0] if fr else None, rope_f0=fr[1] if fr else 1.0, alternating=self.ALTERNATING,
                    view_pe=self._view_pe(nv), has_proj_embed=isinstance(self.proj_embed, nn.Linear),
-                   softmax_scaling=self.softmax_scaling, take=tuple(take), norm_intermediate=norm_intermediate)
+                   softmax_scaling=self.softmax_scaling, take=tuple(take), norm_intermediate=norm_intermediate,
+                   recompute=bool(self.gradient_checkpointing) and torch.is_grad_enabled())
         outs = fused.MultiViewSelfAttnFn.apply(pk, prefix, cfg, x_in, *pk.params.values())
         return outs[0], list(outs[1:])
 
