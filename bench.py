@@ -175,7 +175,17 @@ def run_b200(args):
     model = U.DUSt3R(name="dust3r", img_size=(S, S)).to(dev)
     pk = model.pack()
     if world > 1:  # identical weights on every rank, then overlapped gradient all-reduce
-        dist.broadcast(pk.flat, src=0)
+        # communicator creation makes NCCL print its version banner on stdout: keep stdout to the ONE JSON line
+        sys.stdout.flush()
+        keep = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.broadcast(pk.flat, src=0)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(keep, 1)
+            os.close(keep)
         pk.grad_sync = dp.GradSync(pk.flat_grad, pk.index)
     a_host, b_host = _synthetic_pair_batch(B, S, 1234 + rank)
     a_host, b_host = a_host.pin_memory(), b_host.pin_memory()
