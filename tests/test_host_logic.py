@@ -73,6 +73,47 @@ def test_error_behaviour_matches_reference():
         head(U.PredictionHeadInput(last_feature=torch.zeros(1, 64, 2, 2)))
 
 
+def test_self_attention_transformers_host_logic():
+    """Global / alternating attention transformers: registry, option containers, input validation and error
+    behaviour of the reference (global_attention_transformer.py:245-351) -- all before any kernel would launch."""
+    kw = dict(name="g", input_embed_dim=128, depth=2, dim=128, num_heads=2)
+    assert U.INFO_SHARING_CLASSES["global_attention"] == (U.MultiViewGlobalAttentionTransformer, U.MultiViewGlobalAttentionTransformerIFR)
+    assert U.INFO_SHARING_CLASSES["alternating_attention"] == (U.MultiViewAlternatingAttentionTransformer,
+                                                              U.MultiViewAlternatingAttentionTransformerIFR)
+    g = U.MultiViewGlobalAttentionTransformer(**kw)
+    assert g.use_pe_for_non_reference_views and not U.MultiViewAlternatingAttentionTransformer(**kw).use_pe_for_non_reference_views
+    assert list(g.state_dict())[0] == "view_pos_table" and g.view_pos_table.shape == (1000, 128)
+    assert isinstance(g.proj_embed, torch.nn.Identity)  # input_embed_dim == dim (global_attention_transformer.py:150-153)
+    f = [torch.zeros(1, 128, 2, 2), torch.zeros(1, 128, 2, 2)]
+    with pytest.raises(AssertionError):  # channel mismatch
+        g(U.MultiViewTransformerInput(features=[torch.zeros(1, 64, 2, 2)] * 2))
+    with pytest.raises(AssertionError):  # one token tensor per view
+        g(U.MultiViewTransformerInput(features=f, additional_input_tokens_per_view=[torch.zeros(1, 128, 1)]))
+    with pytest.raises(AssertionError):  # (N, C, T)
+        g(U.MultiViewTransformerInput(features=f, additional_input_tokens=torch.zeros(1, 128)))
+    with pytest.raises(AssertionError):  # batch mismatch
+        g(U.MultiViewTransformerInput(features=f, additional_input_tokens=torch.zeros(2, 128, 1)))
+    with pytest.raises(RuntimeError):  # CUDA only, no CPU fallback
+        g(U.MultiViewTransformerInput(features=f))
+    r = U.MultiViewGlobalAttentionTransformer(custom_positional_encoding="rope", **kw)
+    assert isinstance(r.custom_positional_encoding, U.RoPE2D)
+    with pytest.raises(ValueError):  # :341-351
+        r(U.MultiViewTransformerInput(features=f, additional_input_tokens=torch.zeros(1, 128, 1)))
+    with pytest.raises(ValueError):  # unknown positional-encoding name (:159-163)
+        U.MultiViewGlobalAttentionTransformer(custom_positional_encoding="sincos", **kw)
+    # option containers: qk_norm -> per-head LayerNorm(64); init_values -> LayerScale gamma; flags that are not built refuse
+    o = U.MultiViewAlternatingAttentionTransformer(qk_norm=True, init_values=0.1, gradient_checkpointing=True, **kw)
+    blk = o.self_attention_blocks[0]
+    assert blk.attn.q_norm.weight.shape == (64,) and float(blk.ls2.gamma.detach()[0]) == pytest.approx(0.1)
+    assert o.gradient_checkpointing
+    with pytest.raises(NotImplementedError):
+        U.MultiViewGlobalAttentionTransformer(drop_path=0.1, **kw)
+    with pytest.raises(NotImplementedError):  # head_dim must be 64
+        U.MultiViewGlobalAttentionTransformer(name="g", input_embed_dim=128, depth=1, dim=128, num_heads=4)
+    ifr = U.MultiViewGlobalAttentionTransformerIFR(indices=[0], intermediates_only=True, **kw)
+    assert ifr.indices == [0] and ifr.intermediates_only and ifr.norm_intermediate
+
+
 def test_adaptors_match_oracle_on_cpu():
     import dust3r_oracle as O
 
