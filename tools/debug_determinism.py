@@ -3,7 +3,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch
-from uniception_b200 import ops, engine as E
+from uniception_b200 import ops
 
 torch.manual_seed(0)
 dev = "cuda"

@@ -7,7 +7,6 @@ masters with a version-keyed bf16 operand cache, parameter gradients are returne
 from __future__ import annotations
 
 import weakref
-from typing import Optional
 
 import torch
 import torch.nn as nn

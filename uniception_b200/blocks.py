@@ -22,7 +22,6 @@ import torch.nn as nn
 
 from . import autograd_ops as A
 from .engine import attn_scale
-from .rope import fusable_rope
 
 
 def _require(cond: bool, what: str):

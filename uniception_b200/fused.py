@@ -7,8 +7,6 @@ used for fused wgrad in large-scale trainers; it is what lets dp.py all-reduce o
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
-
 import torch
 
 from . import engine as E

@@ -18,7 +18,7 @@ import torch.nn as nn
 
 from . import dpt_engine, fused, ops
 from .autograd_ops import LinearFn
-from .params import ParamPack, get_pack
+from .params import ParamPack
 
 
 # ---- dataclasses: prediction_heads/base.py:14-104 ----
