@@ -91,6 +91,33 @@ def linear_fwd(pk: ParamPack, name: str, x, *, residual=None, rope: Optional[Rop
     return out
 
 
+class _ColsumSide:
+    """Bias-gradient column sums that no producer kernel could fuse (q/k/v projections, proj_embed) are HBM-bound 10-35 us
+    kernels; on a side stream they run underneath the tensor-bound wgrad / dgrad GEMMs of the same Linear instead of in
+    front of them.  fork: the side stream waits for the caller's stream (dy is complete); join: the caller's stream waits
+    for the side stream before `linear_bwd` returns, so dy's block is not recycled early and the bias gradient is final
+    before the block is reported to the gradient all-reduce.  UC_COLSUM_STREAM=0 keeps everything on one stream."""
+
+    enabled = os.environ.get("UC_COLSUM_STREAM", "1") != "0"
+    _cache: Dict[tuple, "torch.cuda.Stream"] = {}
+
+    @classmethod
+    def run(cls, dy, gb):
+        """Launch colsum(dy) -> gb; returns the stream to join, or None when it ran on the caller's stream."""
+        if not cls.enabled:
+            ops.colsum_(dy, gb)
+            return None
+        cur = torch.cuda.current_stream(dy.device)
+        key = (str(dy.device), cur.cuda_stream)
+        side = cls._cache.get(key)
+        if side is None:
+            side = cls._cache[key] = torch.cuda.Stream(dy.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            ops.colsum_(dy, gb)
+        return side
+
+
 def linear_bwd(pk: ParamPack, name: str, dy, x_in, *, need_dx=True, gelu_pre=None, w16=None, wgrad=None, bgrad=None,
                train_w=None, bias_done=False, dx_sink=None):
     """dy [rows, out] bf16, x_in [rows, in] bf16.  Accumulates dW, db; returns dx (bf16) or None.
@@ -100,19 +127,22 @@ def linear_bwd(pk: ParamPack, name: str, dy, x_in, *, need_dx=True, gelu_pre=Non
     w = pk.w16(name + ".weight") if w16 is None else w16
     if train_w is None:
         train_w = pk.requires_grad(name + ".weight")
+    side = None
     if train_w:
-        gw = pk.grad(name + ".weight") if wgrad is None else wgrad
-        ops.gemm(dy, x_in, gw, a_layout=1, b_layout=1, atomic=True)
         if not bias_done:
             gb = pk.grad(name + ".bias") if bgrad is None else bgrad
-            ops.colsum_(dy, gb)
-    if not need_dx:
-        return None
-    dx = _empty(dy.shape[0], w.shape[1], dy)
-    if gelu_pre is not None:
-        ops.gemm(dy, w, dx, b_layout=1, gelu_bwd=True, aux_in=gelu_pre, c_colsum=dx_sink)
-    else:
-        ops.gemm(dy, w, dx, b_layout=1, c_colsum=dx_sink)
+            side = _ColsumSide.run(dy, gb)
+        gw = pk.grad(name + ".weight") if wgrad is None else wgrad
+        ops.gemm(dy, x_in, gw, a_layout=1, b_layout=1, atomic=True)
+    dx = None
+    if need_dx:
+        dx = _empty(dy.shape[0], w.shape[1], dy)
+        if gelu_pre is not None:
+            ops.gemm(dy, w, dx, b_layout=1, gelu_bwd=True, aux_in=gelu_pre, c_colsum=dx_sink)
+        else:
+            ops.gemm(dy, w, dx, b_layout=1, c_colsum=dx_sink)
+    if side is not None:
+        torch.cuda.current_stream(dy.device).wait_stream(side)
     return dx
 
 
