@@ -53,6 +53,20 @@ def _gemm_traffic():
         return None
 
 
+def _attn_tensor_pipe():
+    """BASELINE.json's secondary metric (fused-attention tensor-pipe %): the committed ncu capture of the attention kernels
+    (profiles/r01n_attn_tensor_pipe.json, sm__pipe_tensor_cycles_active of attn_fwd_kernel / attn_bwd_pipe_kernel at the
+    encoder shape); never measured under the bench's own timing.  None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01n_attn_tensor_pipe.json")) as f:
+            d = json.load(f)
+        enc = d["encoder_16x16x1024"]
+        return {"fwd_pct": enc["attn_fwd_kernel"]["tensor_pipe_pct"], "bwd_pct": enc["attn_bwd_pipe_kernel"]["tensor_pipe_pct"],
+                "metric": d["metric"], "source": "profiles/r01n_attn_tensor_pipe.json (ncu, not the timed run)"}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -320,6 +334,7 @@ def run_b200(args):
                          "step_tflops": (pairs_per_s / world) * flop_pair / 1e12 if flop_pair else None,
                          "step_frac_of_peak": (pairs_per_s / world) * flop_pair / 1e12 / sustained if flop_pair else None},
         }
+        line["attn_tensor_pipe"] = _attn_tensor_pipe()
         if not args.no_cpu_baseline and world == 1:
             v, cores, sample, _t, _n = cpu_oracle_pairs_per_sec(S, 1, 0, budget_s=25.0)
             line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
