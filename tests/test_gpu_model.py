@@ -259,6 +259,22 @@ def test_gradient_checkpointing_recompute_matches_and_saves_memory():
     assert res["ckpt"][4] < 0.5 * res["plain"][4]
 
 
+def test_reference_self_test_mirror_multi_view_cross_attention():
+    """The reference's in-module self-test (info_sharing/cross_attention_transformer.py:515-609) mirrored on the B200 modules:
+    2 / 3 / 4 views with and without RoPE, IFR last-n / explicit indices / `torch.equal` normalisation semantics, plus the
+    3- and 4-view cross-attention (Nk = (V-1)*N keys) against the oracle.  Body: tools/selftest_multiview.py."""
+    import os
+    import subprocess
+    import sys as _sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([_sys.executable, os.path.join(root, "tools", "selftest_multiview.py")], capture_output=True, text=True,
+                         timeout=600)
+    print(out.stdout[-1500:])
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert "SELFTEST OK" in out.stdout
+
+
 def test_full_size_property_checks():
     """BASELINE.json sizes (ViT-L/16 + 12-layer decoder, 512x512, B=1 pair): size-independent
     properties -- confidence >= 1, finite outputs, batch-permutation equivariance and
