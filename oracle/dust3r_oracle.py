@@ -94,6 +94,59 @@ def pixel_shuffle(x: Tensor, p: int) -> Tensor:
 # --------------------------------------------------------------------------------------
 # float ops
 # --------------------------------------------------------------------------------------
+# The restatement above/below spells every op out (mean / var / erf / softmax) so that it can be read against the reference
+# line by line.  The reference ITSELF calls the fused torch functionals -- nn.LayerNorm -> F.layer_norm, nn.GELU -> F.gelu,
+# F.scaled_dot_product_attention by default (utils/config.py:13-17, libs/croco/blocks.py:123-126,
+# utils/transformer_blocks.py:244, :373) and, when its CUDA RoPE extension is not built, the PyTorch RoPE fallback with an
+# activation-dtype angle table and a host sync per call (libs/croco/pos_embed.py:116-155).  In fp32 the two spellings agree
+# to rounding (tests/test_oracle_golden.py); under torch.autocast they do NOT (autocast runs F.layer_norm / softmax in fp32 but
+# leaves a hand-written mean/var in bf16), so everything that measures "the reference under bf16 autocast" -- the parity
+# yardstick of the GPU tests and bench.py's gpu_eager_baseline -- runs inside `reference_functionals()`.
+_FUNCTIONAL = False
+_ROPE_CACHE: Dict = {}
+
+
+class reference_functionals:
+    """Context manager: route layer_norm / gelu / sdpa / rope2d through the torch calls the reference makes."""
+
+    def __init__(self, enabled: bool = True):
+        self.enabled = enabled
+
+    def __enter__(self):
+        global _FUNCTIONAL
+        self.prev, _FUNCTIONAL = _FUNCTIONAL, self.enabled
+        return self
+
+    def __exit__(self, *exc):
+        global _FUNCTIONAL
+        _FUNCTIONAL = self.prev
+        return False
+
+
+def _rope2d_reference_fallback(tokens: Tensor, positions: Tensor, base: float, f0: float) -> Tensor:
+    """libs/croco/pos_embed.py:116-155 as written: cos/sin table cached per (D, seq_len, device, dtype), angles rounded to
+    the activation dtype BEFORE cos/sin (:120-123), `int(positions.max()) + 1` = one device->host sync per call (:149)."""
+    D = tokens.size(3) // 2
+    seq_len = int(positions.max()) + 1
+    key = (D, seq_len, str(tokens.device), tokens.dtype, float(base), float(f0))
+    if key not in _ROPE_CACHE:
+        inv_freq = f0 / (base ** (torch.arange(0, D, 2).float().to(tokens.device) / D))
+        t = torch.arange(seq_len, device=tokens.device, dtype=inv_freq.dtype)
+        freqs = torch.einsum("i,j->ij", t, inv_freq).to(tokens.dtype)
+        freqs = torch.cat((freqs, freqs), dim=-1)
+        _ROPE_CACHE[key] = (freqs.cos(), freqs.sin())
+    cos, sin = _ROPE_CACHE[key]
+
+    def rope1d(tok, pos1d):
+        c = F.embedding(pos1d, cos)[:, None, :, :]
+        s_ = F.embedding(pos1d, sin)[:, None, :, :]
+        x1, x2 = tok[..., : tok.shape[-1] // 2], tok[..., tok.shape[-1] // 2:]
+        return (tok * c) + (torch.cat((-x2, x1), dim=-1) * s_)
+
+    y, x = tokens.chunk(2, dim=-1)
+    return torch.cat((rope1d(y, positions[:, :, 0]), rope1d(x, positions[:, :, 1])), dim=-1)
+
+
 def rope2d(tokens: Tensor, positions: Tensor, base: float = 100.0, f0: float = 1.0) -> Tensor:
     """2-D rotary embedding on tokens [B,H,N,D], positions [B,N,2] (y,x) integers.
 
@@ -102,6 +155,8 @@ def rope2d(tokens: Tensor, positions: Tensor, base: float = 100.0, f0: float = 1
     D = 4Q; for half X in {0:y, 1:x}, i < Q: theta = pos[b,n,X] * f0 / base**(i/Q);
     (u, v) = (t[2QX+i], t[2QX+Q+i]) -> (u cos - v sin, v cos + u sin).
     Backward is the same map with f0 -> -f0 (curope2d.py:24-28)."""
+    if _FUNCTIONAL:
+        return _rope2d_reference_fallback(tokens, positions.long(), base, f0)
     B, H, N, D = tokens.shape
     assert D % 4 == 0
     Q = D // 4
@@ -118,6 +173,8 @@ def rope2d(tokens: Tensor, positions: Tensor, base: float = 100.0, f0: float = 1
 
 def layer_norm(x: Tensor, w: Tensor, b: Tensor, eps: float = 1e-6) -> Tensor:
     """nn.LayerNorm(C, eps=1e-6), biased variance (encoders/croco.py:32)."""
+    if _FUNCTIONAL:
+        return F.layer_norm(x, (x.shape[-1],), w, b, eps)
     mu = x.mean(dim=-1, keepdim=True)
     var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
     return (x - mu) / torch.sqrt(var + eps) * w + b
@@ -125,6 +182,8 @@ def layer_norm(x: Tensor, w: Tensor, b: Tensor, eps: float = 1e-6) -> Tensor:
 
 def gelu_erf(x: Tensor) -> Tensor:
     """nn.GELU() exact-erf form (libs/croco/blocks.py:67)."""
+    if _FUNCTIONAL:
+        return F.gelu(x)
     return 0.5 * x * (1.0 + torch.erf(x * (1.0 / math.sqrt(2.0))))
 
 
@@ -135,6 +194,8 @@ def linear(x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
 
 def sdpa(q: Tensor, k: Tensor, v: Tensor) -> Tensor:
     """softmax(q k^T d^-0.5) v per (b,h); the reference's naive path, libs/croco/blocks.py:117-120."""
+    if _FUNCTIONAL:
+        return F.scaled_dot_product_attention(q, k, v, scale=q.shape[-1] ** -0.5)
     s = (q @ k.transpose(-2, -1)) * (q.shape[-1] ** -0.5)
     return s.softmax(dim=-1) @ v
 
@@ -506,17 +567,23 @@ def dust3r_forward(
     f1, f2 = feat.chunk(2, dim=0)
     if sym:
         f1, f2 = interleave(f1, f2)
+    # heads + adaptors: fp32 inputs, autocast disabled (factory/dust3r.py:285-309)
     if head == "linear":
         d1, d2 = info_sharing(sd, "info_sharing.", [f1, f2], dec_depth, dec_heads, base)
-        o1 = linear_head(sd, "head1.", d1, patch)
-        o2 = linear_head(sd, "head2.", d2, patch)
+        with torch.autocast(img1.device.type, enabled=False):
+            o1 = linear_head(sd, "head1.", d1.float(), patch)
+            o2 = linear_head(sd, "head2.", d2.float(), patch)
     else:
         (d1, d2), inter = info_sharing(sd, "info_sharing.", [f1, f2], dec_depth, dec_heads, base,
                                        indices=[5, 8], norm_intermediate=False)
-        o1 = dpt_regressor(sd, "dpt_regressor_head1.", dpt_feature(sd, "dpt_feature_head1.", [f1, inter[0][0], inter[1][0], d1]), (H, W))
-        o2 = dpt_regressor(sd, "dpt_regressor_head2.", dpt_feature(sd, "dpt_feature_head2.", [f2, inter[0][1], inter[1][1], d2]), (H, W))
-    p1, c1 = pointmap_conf_adaptor(o1)
-    p2, c2 = pointmap_conf_adaptor(o2)
+        with torch.autocast(img1.device.type, enabled=False):
+            h1 = [t.float() for t in (f1, inter[0][0], inter[1][0], d1)]
+            h2 = [t.float() for t in (f2, inter[0][1], inter[1][1], d2)]
+            o1 = dpt_regressor(sd, "dpt_regressor_head1.", dpt_feature(sd, "dpt_feature_head1.", h1), (H, W))
+            o2 = dpt_regressor(sd, "dpt_regressor_head2.", dpt_feature(sd, "dpt_feature_head2.", h2), (H, W))
+    with torch.autocast(img1.device.type, enabled=False):
+        p1, c1 = pointmap_conf_adaptor(o1)
+        p2, c2 = pointmap_conf_adaptor(o2)
     res1 = {"pts3d": p1.permute(0, 2, 3, 1).contiguous(), "conf": c1.permute(0, 2, 3, 1).contiguous()}
     res2 = {"pts3d_in_other_view": p2.permute(0, 2, 3, 1).contiguous(), "conf": c2.permute(0, 2, 3, 1).contiguous()}
     return res1, res2

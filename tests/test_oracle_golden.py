@@ -330,3 +330,21 @@ def test_cross_attention_softmax_scaling_golden():
     # the flags matter: without them the output differs
     plain = O.info_sharing(sd, "", [f.detach() for f in feats], cfg["depth"], cfg["heads"])
     assert O.parity(plain[0], a["out0"])[1] > 1e-3
+
+
+def test_reference_functionals_mode_matches_spelled_out_oracle():
+    """`O.reference_functionals()` routes LayerNorm / GELU / attention / RoPE through the torch calls the reference itself makes
+    (F.layer_norm, F.gelu, F.scaled_dot_product_attention, the PyTorch RoPE fallback of pos_embed.py:116-155).  In fp32 both
+    spellings must reproduce the reference's golden outputs; the mode exists for the bf16-autocast yardstick and the
+    GPU-eager baseline, where only the fused functionals get autocast's fp32 treatment."""
+    cfg, a = load("dust3r_tiny_linear")
+    sd = weights(cfg)
+    kw = dict(enc_depth=cfg["enc_depth"], enc_heads=cfg["enc_heads"], dec_depth=cfg["dec_depth"], dec_heads=cfg["dec_heads"])
+    with O.reference_functionals():
+        r1, r2 = O.dust3r_forward(sd, a["img1"], a["img2"], **kw)
+    assert O.parity(r1["pts3d"], a["pts3d_1"])[1] <= 2e-5
+    assert O.parity(r2["conf"], a["conf_2"])[1] <= 2e-5
+    p1, _ = O.dust3r_forward(sd, a["img1"], a["img2"], **kw)
+    assert O.parity(r1["pts3d"], p1["pts3d"])[1] <= 2e-5
+    # the mode is scoped
+    assert O._FUNCTIONAL is False

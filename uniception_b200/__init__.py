@@ -11,6 +11,7 @@ the built library raises ImportError -- there is no CPU or library fallback.
 """
 from . import _lib  # noqa: F401  (fails loudly when the CUDA extension is missing)
 from . import checkpoints  # noqa: F401  (original DUSt3R / CroCo checkpoint -> UniCeption-format state dicts)
+from .depth import ViTDPTDepth  # noqa: F401
 from .dust3r import DUSt3R, interleave, is_symmetrized  # noqa: F401
 from .encoders import (  # noqa: F401
     ENCODER_CONFIGS, CroCoEncoder, CroCoIntermediateFeatureReturner, IntermediateFeatureReturner, ManyAR_PatchEmbed, ViTEncoderInput, ViTEncoderOutput,

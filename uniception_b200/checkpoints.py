@@ -93,7 +93,21 @@ def dust3r_state_dict(ckpt: Mapping, pred_head_type: str = "linear") -> SD:
     return out
 
 
+def load_checkpoint_file(path: str):
+    """`torch.load` for UniCeption checkpoint files ({"model": state_dict, plus plain str / number metadata}).  Tensors-only
+    unpickling first (a checkpoint file from an untrusted source must not execute code); files that carry arbitrary pickled
+    objects need the explicit opt-in UC_UNSAFE_CHECKPOINTS=1, which restores the reference's `weights_only=False`."""
+    import os
+
+    try:
+        return torch.load(path, map_location="cpu", weights_only=True)
+    except Exception:
+        if os.environ.get("UC_UNSAFE_CHECKPOINTS") == "1":
+            return torch.load(path, map_location="cpu", weights_only=False)
+        raise
+
+
 def load_uniception_checkpoint(module: torch.nn.Module, path_or_ckpt, strict: bool = True):
     """Load a UniCeption-format checkpoint `{"model": state_dict, ...}` (croco.py:101-111, dust3r.py:206-209)."""
-    ckpt = torch.load(path_or_ckpt, map_location="cpu", weights_only=False) if isinstance(path_or_ckpt, str) else path_or_ckpt
+    ckpt = load_checkpoint_file(path_or_ckpt) if isinstance(path_or_ckpt, str) else path_or_ckpt
     return module.load_state_dict(_model(ckpt), strict=strict)

@@ -50,6 +50,19 @@ class Tape:
         self.fns.clear()
 
 
+def _accumulate_grad(p: nn.Parameter, g: torch.Tensor) -> None:
+    """p.grad += g.  A parameter that lives in a ParamPack (DUSt3R(pred_head_type="dpt")) accumulates into its view of the
+    pack's flat gradient buffer -- after the pack has applied `zero_grad(set_to_none=True)` semantics -- so the value is
+    what the optimizer and dp.GradSync see; a free-standing parameter gets a fresh tensor."""
+    tag = getattr(p, "_uc_pack", None)
+    if tag is not None and tag[0].valid() and tag[0].params.get(tag[1]) is p:
+        tag[0].prepare_grads()
+    if p.grad is None:
+        p.grad = g.contiguous().clone()
+    else:
+        p.grad.add_(g)
+
+
 class ConvW:
     """bf16 GEMM operand + fp32 bias of one conv layer, and the fp32 gradient accumulators in GEMM layout."""
 
@@ -110,9 +123,9 @@ class ConvW:
             g = self.gw.view(s, s, self.co_pad, self.ci_pad)[:, :, :co, :ci].permute(3, 2, 0, 1)
             gb = self.gb.view(s * s, self.co_pad)[:, :co].sum(0)
         if self.weight.requires_grad:
-            self.weight.grad = g.contiguous().clone() if self.weight.grad is None else self.weight.grad.add_(g)
+            _accumulate_grad(self.weight, g)
         if self.bias is not None and self.bias.requires_grad:
-            self.bias.grad = gb.clone() if self.bias.grad is None else self.bias.grad.add_(gb)
+            _accumulate_grad(self.bias, gb)
         self.gw = self.gb = None
 
 
@@ -255,10 +268,10 @@ def crop(tape: Tape, x, B, H, W, Hc, Wc):
 # ------------------------------------------------------------------------------------------------
 # the head
 # ------------------------------------------------------------------------------------------------
-class DPTWeights:
-    """Operand copies of one (DPTFeature, DPTRegressionProcessor) pair, rebuilt per forward from the fp32 masters."""
+class DPTFeatureWeights:
+    """Operand copies of one DPTFeature (prediction_heads/dpt.py:94-177), rebuilt per forward from the fp32 masters."""
 
-    def __init__(self, feat: nn.Module, reg: nn.Module):
+    def __init__(self, feat: nn.Module):
         sc = feat.scratch
         self.pre, self.up, self.rn = [], [], []
         for j in range(4):
@@ -274,6 +287,7 @@ class DPTWeights:
             cin = self.up[j].co_pad if self.up[j] is not None else c1.co_pad
             self.rn.append(ConvW("conv3", sc.layer_rn[j].weight, None, cin_pad=cin))
         f = self.rn[0].co_pad
+        self.feature_dim_pad = f
         self.fuse = []
         for k in (1, 2, 3, 4):
             blk = getattr(sc, f"refinenet{k}")
@@ -284,18 +298,38 @@ class DPTWeights:
                     d[u] = (ConvW("conv3", unit.conv1.weight, unit.conv1.bias, cin_pad=f),
                             ConvW("conv3", unit.conv2.weight, unit.conv2.bias, cin_pad=f))
             self.fuse.append(d)
-        self.r1 = ConvW("conv3", reg.conv1.weight, reg.conv1.bias, cin_pad=f)
-        self.r2 = ConvW("conv3", reg.conv2[0].weight, reg.conv2[0].bias, cin_pad=self.r1.co_pad)
-        self.r3 = ConvW("conv1", reg.conv2[2].weight, reg.conv2[2].bias, cin_pad=self.r2.co_pad)
 
     def all(self):
-        out = self.pre + [u for u in self.up if u is not None] + self.rn + [self.r1, self.r2, self.r3]
+        out = self.pre + [u for u in self.up if u is not None] + self.rn
         for d in self.fuse:
             out.append(d["out"])
             for u in ("resConfUnit1", "resConfUnit2"):
                 if u in d:
                     out += list(d[u])
         return out
+
+
+class DPTRegressorWeights:
+    """Operand copies of one DPTRegressionProcessor (prediction_heads/dpt.py:271-283); cin_pad = padded input channels."""
+
+    def __init__(self, reg: nn.Module, cin_pad: int):
+        self.r1 = ConvW("conv3", reg.conv1.weight, reg.conv1.bias, cin_pad=cin_pad)
+        self.r2 = ConvW("conv3", reg.conv2[0].weight, reg.conv2[0].bias, cin_pad=self.r1.co_pad)
+        self.r3 = ConvW("conv1", reg.conv2[2].weight, reg.conv2[2].bias, cin_pad=self.r2.co_pad)
+
+    def all(self):
+        return [self.r1, self.r2, self.r3]
+
+
+class DPTWeights:
+    """Operand copies of one (DPTFeature, DPTRegressionProcessor) pair."""
+
+    def __init__(self, feat: nn.Module, reg: nn.Module):
+        self.feat = DPTFeatureWeights(feat)
+        self.reg = DPTRegressorWeights(reg, self.feat.feature_dim_pad)
+
+    def all(self):
+        return self.feat.all() + self.reg.all()
 
 
 def _rcu(tape, z, B, H, W, unit, extra_skip=None):
@@ -313,8 +347,9 @@ def _fusion(tape, a, b, B, H, W, d):
     return conv1x1(tape, out, d["out"])
 
 
-def dpt_forward(tape: Tape, Wt: DPTWeights, feats: List[torch.Tensor], B: int, h: int, w: int, out_hw: Tuple[int, int]):
-    """feats: 4 token tensors bf16 [B*h*w, C_j].  Returns y fp32 [B*H*W, 64] (first `out_dim` columns valid)."""
+def dpt_feature_forward(tape: Tape, Wt: DPTFeatureWeights, feats: List[torch.Tensor], B: int, h: int, w: int):
+    """DPTFeature.forward (prediction_heads/dpt.py:180-232).  feats: 4 token tensors bf16 [B*h*w, C_j] (already selected by
+    `hooks`).  Returns (features_upsampled_8x as NHWC bf16 [B*Hf*Wf, feature_dim_pad], Hf, Wf)."""
     maps, sizes = [], []
     for j in range(4):
         a = conv1x1(tape, feats[j], Wt.pre[j])
@@ -333,8 +368,19 @@ def dpt_forward(tape: Tape, Wt: DPTWeights, feats: List[torch.Tensor], B: int, h
     p3 = _fusion(tape, p4, l2, B, sizes[2][0], sizes[2][1], Wt.fuse[2])
     p2 = _fusion(tape, p3, l1, B, sizes[1][0], sizes[1][1], Wt.fuse[1])
     p1 = _fusion(tape, p2, l0, B, sizes[0][0], sizes[0][1], Wt.fuse[0])
-    Hf, Wf = 2 * sizes[0][0], 2 * sizes[0][1]
+    return p1, 2 * sizes[0][0], 2 * sizes[0][1]
+
+
+def dpt_regressor_forward(tape: Tape, Wt: DPTRegressorWeights, p1: torch.Tensor, B: int, Hf: int, Wf: int, out_hw: Tuple[int, int]):
+    """DPTRegressionProcessor.forward (prediction_heads/dpt.py:285-311): 3x3 conv -> bilinear (align_corners) to the exact
+    target size -> 3x3 conv + ReLU -> 1x1.  Returns y fp32 [B*H*W, 64] (first `output_dim` columns valid)."""
     c1 = conv3x3(tape, p1, B, Hf, Wf, Wt.r1)
     u = resize(tape, c1, B, Hf, Wf, out_hw[0], out_hw[1])
     c2 = conv3x3(tape, u, B, out_hw[0], out_hw[1], Wt.r2, relu=True)
     return conv1x1(tape, c2, Wt.r3, out_dtype=torch.float32)
+
+
+def dpt_forward(tape: Tape, Wt: DPTWeights, feats: List[torch.Tensor], B: int, h: int, w: int, out_hw: Tuple[int, int]):
+    """Feature head + regression processor on one tape.  Returns y fp32 [B*H*W, 64] (first `out_dim` columns valid)."""
+    p1, Hf, Wf = dpt_feature_forward(tape, Wt.feat, feats, B, h, w)
+    return dpt_regressor_forward(tape, Wt.reg, p1, B, Hf, Wf, out_hw)

@@ -12,6 +12,7 @@ from typing import List, Tuple
 import torch
 import torch.nn as nn
 
+from .checkpoints import load_checkpoint_file
 from .encoders import CroCoEncoder, feature_take_indices
 from .info_sharing import MultiViewCrossAttentionTransformer, MultiViewCrossAttentionTransformerIFR
 from .params import ParamPack, get_pack
@@ -126,7 +127,7 @@ class DUSt3R(nn.Module):
 
         if self.pretrained_checkpoint_path is not None:
             print(f"Loading pretrained DUSt3R weights from {self.pretrained_checkpoint_path} ...")
-            ckpt = torch.load(self.pretrained_checkpoint_path, weights_only=False)
+            ckpt = load_checkpoint_file(self.pretrained_checkpoint_path)
             print(self.load_state_dict(ckpt["model"]))
 
     def pack(self) -> ParamPack:

@@ -14,6 +14,7 @@ from typing import Callable, List, Optional, Tuple, Union
 import torch
 import torch.nn as nn
 
+from .checkpoints import load_checkpoint_file
 from . import fused
 from .blocks import Block, check_norm_layer
 from .params import ParamPack, get_pack
@@ -195,7 +196,7 @@ class CroCoEncoder(UniCeptionViTEncoderBase):
 
         if pretrained_checkpoint_path:
             print(f"Loading pretrained CroCo checkpoint from {pretrained_checkpoint_path}")
-            ckpt = torch.load(pretrained_checkpoint_path, weights_only=False)
+            ckpt = load_checkpoint_file(pretrained_checkpoint_path)
             print(self.load_state_dict(ckpt["model"]))
             if not override_checkpoint_attributes:
                 assert (

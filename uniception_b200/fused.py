@@ -15,12 +15,8 @@ from .params import ParamPack
 
 
 def _prep_grads(pk: ParamPack) -> None:
-    """`zero_grad(set_to_none=True)` semantics: a dropped .grad means zero."""
-    s = pk._sentinels[0]
-    if s.grad is None or s.grad.data_ptr() != pk.flat_grad.data_ptr():
-        if s.grad is None:
-            pk.flat_grad.zero_()
-        pk.rebind_grads()
+    """`zero_grad(set_to_none=True)` semantics: a dropped .grad means zero (see ParamPack.prepare_grads)."""
+    pk.prepare_grads()
 
 
 class EncoderFn(torch.autograd.Function):

@@ -15,6 +15,7 @@ from typing import Callable, List, Optional, Union
 import torch
 import torch.nn as nn
 
+from .checkpoints import load_checkpoint_file
 from . import fused
 from .blocks import CrossAttentionBlock, Mlp, SelfAttentionBlock, _require, check_norm_layer
 from .encoders import IntermediateFeatureReturner, PositionGetter, feature_take_indices
@@ -143,7 +144,7 @@ class MultiViewCrossAttentionTransformer(UniCeptionInfoSharingBase):
 
         if self.pretrained_checkpoint_path is not None:
             print(f"Loading pretrained multi-view cross-attention transformer weights from {self.pretrained_checkpoint_path} ...")
-            ckpt = torch.load(self.pretrained_checkpoint_path, weights_only=False)
+            ckpt = load_checkpoint_file(self.pretrained_checkpoint_path)
             print(self.load_state_dict(ckpt["model"]))
 
     def initialize_weights(self):
@@ -275,6 +276,7 @@ class MultiViewGlobalAttentionTransformer(UniCeptionInfoSharingBase):
         check_norm_layer(norm_layer)
         if drop_path or proj_drop or attn_drop:
             raise NotImplementedError("uniception_b200: dropout / stochastic-depth block options (SURVEY.md 8f4)")
+        _require(qkv_bias, "qkv_bias=False")  # the engine's Linear kernels always carry a bias (as the cross-attention class)
         self.qk_norm, self.init_values = qk_norm, init_values
         self.softmax_scaling = (use_scalable_softmax, use_entropy_scaling, base_token_count_for_entropy_scaling,
                                 entropy_scaling_growth_factor) if (use_scalable_softmax or use_entropy_scaling) else None
@@ -312,7 +314,7 @@ class MultiViewGlobalAttentionTransformer(UniCeptionInfoSharingBase):
         self.apply(self._init_weights)
         if pretrained_checkpoint_path is not None:
             print(f"Loading pretrained multi-view attention transformer weights from {pretrained_checkpoint_path} ...")
-            ckpt = torch.load(pretrained_checkpoint_path, weights_only=False)
+            ckpt = load_checkpoint_file(pretrained_checkpoint_path)
             print(self.load_state_dict(ckpt["model"]))
 
     _init_weights = MultiViewCrossAttentionTransformer._init_weights

@@ -19,8 +19,12 @@ PROFILE = None  # bench.py: set to a list to record (start_event, end_event, flo
 _DT = {torch.bfloat16: L.UC_DTYPE_BF16, torch.float32: L.UC_DTYPE_F32, torch.float16: L.UC_DTYPE_F16}
 
 
+_dev = None  # device of the tensors of the call in flight (set by _cuda)
+
+
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """The current stream OF THE TENSORS' DEVICE (a model on cuda:1 while cuda:0 is current must not launch on cuda:0)."""
+    return C.c_void_p(torch.cuda.current_stream(_dev).cuda_stream)
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -28,9 +32,22 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 def _cuda(*ts):
+    global _dev
+    dev = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("uniception_b200: tensors must live on a CUDA device (no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"uniception_b200: tensors on different devices ({dev} vs {t.device})")
+    if dev is not None:
+        if dev.index != torch.cuda.current_device():
+            raise RuntimeError(f"uniception_b200: tensors live on {dev} but the current CUDA device is {torch.cuda.current_device()}; "
+                               "wrap the call in torch.cuda.device(...) (kernels launch on the current device)")
+        _dev = dev
 
 
 def gemm(a, b, out, *, a_layout=0, b_layout=0, bias=None, residual=None, aux_out=None, aux_in=None,
@@ -112,6 +129,7 @@ def rope2d_(tokens_bnhd: torch.Tensor, positions: torch.Tensor, base: float, fwd
 
 def rope2d_table(num_pos: int, base: float, f0: float, device, q: int = 16) -> torch.Tensor:
     t = torch.empty(num_pos, q, 2, dtype=torch.float32, device=device)
+    _cuda(t)
     L.check(L.lib.uc_rope2d_table(_ptr(t), num_pos, q, float(base), float(f0), _stream()))
     return t
 

@@ -58,9 +58,11 @@ class ParamPack:
                 view.copy_(p.data)
                 p.data = view
                 p.grad = self.flat_grad[o:o + p.numel()].view(shp)
+                p._uc_pack = (self, n)  # lets code that assigns gradients itself (dpt_engine.ConvW.flush_grads) find the flat view
                 self.params[n] = p
         self.grad_sync = None  # optional dp.GradSync: told which parameter ranges are final during backward
         self._sentinels = [named[0][1], named[len(named) // 2][1], named[-1][1]]
+        self._sentinel_named = [named[0], named[len(named) // 2], named[-1]]
         self._sentinel_ptrs = [p.data_ptr() for p in self._sentinels]
         self.refresh_bf16()
 
@@ -116,18 +118,53 @@ class ParamPack:
         if self.grad_sync is not None:
             self.grad_sync.ready(prefix)
 
+    def grad_view(self, name: str) -> torch.Tensor:
+        """The flat-buffer gradient view of one parameter, in the parameter's own shape."""
+        o, shp = self.index[name]
+        return self.flat_grad[o:o + shp.numel()].view(shp)
+
+    def prepare_grads(self) -> None:
+        """Called at the start of every backward node.  `optimizer.zero_grad()` / `Module.zero_grad()` default to
+        set_to_none=True: a parameter whose `.grad` was dropped restarts from zero -- ONLY its own range of the flat
+        buffer is cleared (one memset when every gradient was dropped), so parameters that are frozen or simply not in
+        the optimizer keep their state.  A `.grad` tensor that somebody else assigned (not a view of the flat buffer) is
+        folded into the view instead of being discarded.  The per-call cost with nothing to do is one attribute read per
+        parameter."""
+        dropped = [n for n, p in self.params.items() if p.grad is None]
+        if dropped:
+            if len(dropped) == len(self.params):
+                self.flat_grad.zero_()
+            else:
+                for n in dropped:
+                    self.grad_view(n).zero_()
+            for n in dropped:
+                self.params[n].grad = self.grad_view(n)
+        if dropped or any(p.grad is not None and p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * self.index[n][0]
+                          for n, p in self._sentinel_named):
+            self.rebind_grads()
+
     def rebind_grads(self) -> None:
-        """Re-attach `.grad` views (e.g. after `zero_grad(set_to_none=True)` dropped them)."""
+        """Re-attach `.grad` views; a foreign `.grad` (assigned by other code) is accumulated into the view first."""
+        base = self.flat_grad.data_ptr()
         for n, p in self.params.items():
-            if p.grad is None or p.grad.data_ptr() != self.grad(n).data_ptr():
-                o, shp = self.index[n]
-                p.grad = self.flat_grad[o:o + shp.numel()].view(shp)
+            want = base + 4 * self.index[n][0]
+            if p.grad is None:
+                p.grad = self.grad_view(n)
+            elif p.grad.data_ptr() != want:
+                view = self.grad_view(n)
+                view.add_(p.grad.to(view.dtype).view(view.shape))
+                p.grad = view
 
 
 def get_pack(module: nn.Module) -> ParamPack:
     """The pack of `module`, (re)built lazily when parameters moved."""
     pk = module.__dict__.get("_uc_pack")
     if pk is None or not pk.valid():
+        old = pk
         pk = ParamPack(module)
+        if old is not None and old.grad_sync is not None:
+            # the parameters moved (.to() / .cuda() / load with assign=True): data parallelism must keep synchronising, on the
+            # NEW flat gradient buffer
+            pk.grad_sync = old.grad_sync.rebuilt_for(pk.flat_grad, pk.index)
         module.__dict__["_uc_pack"] = pk
     return pk

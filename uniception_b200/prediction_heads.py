@@ -16,6 +16,7 @@ from typing import List, Tuple
 import torch
 import torch.nn as nn
 
+from .checkpoints import load_checkpoint_file
 from . import dpt_engine, fused, ops
 from .autograd_ops import LinearFn
 from .params import ParamPack
@@ -74,7 +75,7 @@ class LinearFeature(nn.Module):
                                 stride=1, padding=0, bias=True)
         if self.pretrained_checkpoint_path is not None:
             print(f"Loading pretrained linear dense feature head from {self.pretrained_checkpoint_path}")
-            ckpt = torch.load(self.pretrained_checkpoint_path, weights_only=False)
+            ckpt = load_checkpoint_file(self.pretrained_checkpoint_path)
             print(self.load_state_dict(ckpt["model"]))
 
     def forward(self, feature_input: PredictionHeadInput) -> PixelTaskOutput:
@@ -290,11 +291,30 @@ class DPTFeature(nn.Module):
         self.input_process = nn.ModuleList([nn.Sequential(a, l) for a, l in zip(act, scratch.layer_rn)])
         if pretrained_checkpoint_path is not None:
             print(f"Loading pretrained DPT dense feature head from {pretrained_checkpoint_path}")
-            ckpt = torch.load(pretrained_checkpoint_path, weights_only=False)
+            ckpt = load_checkpoint_file(pretrained_checkpoint_path)
             print(self.load_state_dict(ckpt["model"]))
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("uniception_b200: run DPTFeature through DPTHead(feature, regressor) or DUSt3R(pred_head_type='dpt')")
+    def forward(self, dpt_input: PredictionHeadLayeredInput) -> DPTFeatureInput:
+        """prediction_heads/dpt.py:180-232: 4 hooked BCHW maps -> `features_upsampled_8x` [B, feature_dim, 8h', 8w'] (fp32 NCHW
+        at the module boundary like the reference; NHWC bf16 inside).  `checkpoint_gradient` only changes what the reference
+        keeps for its backward; the 3x3 convs here re-gather their im2col operand in the backward either way."""
+        assert self.input_feature_dims is not None, "Need to call init(input_feature_dims) function first"
+        layered = dpt_input.list_features
+        for hook_idx, hook in enumerate(self.hooks):
+            assert layered[hook].shape[1] == self.input_feature_dims[hook_idx], \
+                f"Input feature dimension mismatch at hook {hook}. Expected BCHW"
+        feats = [layered[hook] for hook in self.hooks]
+        if not feats[0].is_cuda:
+            raise RuntimeError("uniception_b200.DPTFeature runs on CUDA only (no CPU fallback)")
+        B, _, h, w = feats[0].shape
+        toks = [fused.NchwToNlcFn.apply(f) for f in feats]
+        p1 = _DPTFeatureFn.apply(self, B, h, w, *toks, *list(self.parameters()))
+        s0 = self.act_postprocess[0][1].kernel_size[0]  # layer 1 is upsampled by its ConvTranspose, then x2 by refinenet1
+        Hf, Wf = 2 * s0 * h, 2 * s0 * w
+        fd = self.feature_dim
+        x = p1 if p1.shape[1] == fd else p1[:, :fd]
+        out = fused.NlcToNchwFn.apply(x.contiguous(), B, Hf, Wf)
+        return DPTFeatureInput(features_upsampled_8x=out, target_output_shape=dpt_input.target_output_shape)
 
 
 class DPTRegressionProcessor(nn.Module):
@@ -313,11 +333,80 @@ class DPTRegressionProcessor(nn.Module):
                                    nn.Conv2d(hidden_dims[1], output_dim, kernel_size=1, stride=1, padding=0))
         if pretrained_checkpoint_path is not None:
             print(f"Loading pretrained DPT regression processor from {pretrained_checkpoint_path}")
-            ckpt = torch.load(pretrained_checkpoint_path, weights_only=False)
+            ckpt = load_checkpoint_file(pretrained_checkpoint_path)
             print(self.load_state_dict(ckpt["model"]))
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("uniception_b200: run DPTRegressionProcessor through DPTHead(feature, regressor) or DUSt3R(pred_head_type='dpt')")
+    def forward(self, dpt_processor_input: DPTFeatureInput) -> PixelTaskOutput:
+        """prediction_heads/dpt.py:285-311: `features_upsampled_8x` [B, C, Hf, Wf] -> decoded channels [B, output_dim, H, W]."""
+        x = dpt_processor_input.features_upsampled_8x
+        H, W = dpt_processor_input.target_output_shape
+        if not x.is_cuda:
+            raise RuntimeError("uniception_b200.DPTRegressionProcessor runs on CUDA only (no CPU fallback)")
+        B, C, Hf, Wf = x.shape
+        assert C == self.conv1.weight.shape[1], f"Input feature dimension mismatch: {C} vs {self.conv1.weight.shape[1]}"
+        tok = fused.NchwToNlcFn.apply(x)
+        cp = dpt_engine._pad64(C)
+        if cp != C:  # channel counts are padded to the GEMM granularity (zeros)
+            tok = torch.nn.functional.pad(tok, (0, cp - C))
+        y = _DPTRegressorFn.apply(self, B, Hf, Wf, (int(H), int(W)), tok, *list(self.parameters()))
+        od = self.output_dim
+        return PixelTaskOutput(decoded_channels=y[:, :od].reshape(B, H, W, od).permute(0, 3, 1, 2).contiguous())
+
+
+def _tape_backward(ctx, dy, inputs, weights):
+    """Shared backward of the tape-based DPT nodes: seeds the output gradient, replays the tape, moves the GEMM-layout
+    weight gradients into the parameters' .grad and returns the input-token gradients."""
+    tape = ctx.tape
+    g = dy.contiguous()
+    tape.add_grad(ctx.y, g if g.dtype == torch.bfloat16 else g.to(torch.bfloat16))
+    tape.backward()
+    for cw in weights.all():
+        cw.flush_grads()
+    grads = []
+    for t, dt in zip(inputs, ctx.in_dtypes):
+        gt = tape.pop_grad(t)
+        grads.append(None if gt is None else (gt if gt.dtype == dt else gt.to(dt)))
+    return grads
+
+
+class _DPTFeatureFn(torch.autograd.Function):
+    """tokens (4 x bf16 [B*h*w, C_j]) -> features_upsampled_8x, NHWC bf16 [B*Hf*Wf, feature_dim_pad]."""
+
+    @staticmethod
+    def forward(ctx, feat_mod, B, h, w, t0, t1, t2, t3, *params):
+        toks = [t.contiguous() if t.dtype == torch.bfloat16 else t.to(torch.bfloat16).contiguous() for t in (t0, t1, t2, t3)]
+        Wt = dpt_engine.DPTFeatureWeights(feat_mod)
+        tape = dpt_engine.Tape()
+        y, _, _ = dpt_engine.dpt_feature_forward(tape, Wt, toks, B, h, w)
+        ctx.tape, ctx.Wt, ctx.toks, ctx.y = tape, Wt, toks, y
+        ctx.in_dtypes = [t.dtype for t in (t0, t1, t2, t3)]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        grads = _tape_backward(ctx, dy, ctx.toks, ctx.Wt)
+        ctx.tape = ctx.Wt = ctx.toks = ctx.y = None
+        return (None, None, None, None, *grads) + (None,) * (len(ctx.needs_input_grad) - 8)
+
+
+class _DPTRegressorFn(torch.autograd.Function):
+    """NHWC bf16 [B*Hf*Wf, C_pad] -> raw regression output fp32 [B*H*W, 64] (first output_dim columns valid)."""
+
+    @staticmethod
+    def forward(ctx, reg_mod, B, Hf, Wf, out_hw, x, *params):
+        xb = x.contiguous() if x.dtype == torch.bfloat16 else x.to(torch.bfloat16).contiguous()
+        Wt = dpt_engine.DPTRegressorWeights(reg_mod, xb.shape[1])
+        tape = dpt_engine.Tape()
+        y = dpt_engine.dpt_regressor_forward(tape, Wt, xb, B, Hf, Wf, out_hw)
+        ctx.tape, ctx.Wt, ctx.x, ctx.y = tape, Wt, xb, y
+        ctx.in_dtypes = [x.dtype]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        grads = _tape_backward(ctx, dy, [ctx.x], ctx.Wt)
+        ctx.tape = ctx.Wt = ctx.x = ctx.y = None
+        return (None, None, None, None, None, grads[0]) + (None,) * (len(ctx.needs_input_grad) - 6)
 
 
 class _DPTHeadFn(torch.autograd.Function):
