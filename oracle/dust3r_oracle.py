@@ -188,6 +188,8 @@ def gelu_erf(x: Tensor) -> Tensor:
 
 
 def linear(x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
+    if _FUNCTIONAL:  # nn.Linear: under autocast the bias add and the output are in the autocast dtype too
+        return F.linear(x, w, b)
     y = x @ w.t()
     return y if b is None else y + b
 
@@ -297,6 +299,8 @@ def patch_embed(sd: SD, p: str, img: Tensor, patch: int, true_shape: Optional[Te
     wmat = wgt.reshape(wgt.shape[0], -1).t()
 
     def embed(im, hh, ww):
+        if _FUNCTIONAL:  # nn.Conv2d(3, C, k = s = patch) then flatten(2).transpose(1, 2), patch_embed.py:77-79
+            return F.conv2d(im, wgt, sd[p + "proj.bias"], stride=patch).flatten(2).transpose(1, 2)
         cols = im.reshape(im.shape[0], Cin, hh, patch, ww, patch).permute(0, 2, 4, 1, 3, 5).reshape(im.shape[0], hh * ww, Cin * patch * patch)
         return cols @ wmat + sd[p + "proj.bias"]
 

@@ -24,10 +24,13 @@ torch.backends.cudnn.allow_tf32 = False
 
 
 def _autocast_err(fn_fp32_inputs):
-    """relative error of the oracle arithmetic under bf16 autocast vs itself in fp32."""
-    ref = fn_fp32_inputs()
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        low = fn_fp32_inputs()
+    """relative error of the reference arithmetic under bf16 autocast vs itself in fp32.  Inside `O.reference_functionals()` the
+    oracle issues the torch calls the reference issues, which is what makes the autocast run the reference's autocast run
+    (pinned bit for bit by tests/test_oracle_golden.py::test_autocast_yardstick_is_the_reference_under_autocast)."""
+    with O.reference_functionals():
+        ref = fn_fp32_inputs()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            low = fn_fp32_inputs()
     return [O.parity(a.float(), b)[1] for a, b in zip(low, ref)]
 
 
@@ -328,7 +331,7 @@ def test_dust3r_dpt_vs_reference_golden_fwd_bwd():
     # module's resolved state dict (as oracle/make_golden.py does), not the raw seeded one.
     sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
     o1, o2 = _oracle_dpt(sd, img1, img2, cfg)
-    with torch.autocast("cuda", dtype=torch.bfloat16):
+    with O.reference_functionals(), torch.autocast("cuda", dtype=torch.bfloat16):
         l1, _ = _oracle_dpt({k: v.detach() for k, v in sd.items()}, img1, img2, cfg)
     ref_err = O.parity(l1.float(), o1)[1]
     # conf = 1 + exp(raw channel 3): log(conf - 1) recovers the raw head output of the confidence channel
@@ -380,7 +383,7 @@ def test_c5_depth_patch14_vs_reference_golden():
         return inter, O.dpt_regressor(sd, "dpt_regressor_head.", O.dpt_feature(sd, "dpt_feature_head.", inter), hw)
 
     inter, oraw = oracle()
-    with torch.autocast("cuda", dtype=torch.bfloat16):
+    with O.reference_functionals(), torch.autocast("cuda", dtype=torch.bfloat16):
         _, lraw = oracle()
     ref_err = O.parity(lraw.float(), oraw)[1]
     e_hook = O.parity(feats[3], a["hook3"].to(DEV))[1]
