@@ -167,6 +167,8 @@ UC_API int uc_layernorm_bwd(const uc_layernorm_bwd_params* p, uc_stream_t stream
  *   base + (b*N + token) * ld + head*64 + d     (so a packed qkv [B*N, 3C] works with 3 base pointers).
  * RoPE has already been applied to q and k (fused into the producing GEMM's epilogue).
  * lse [B][H][Nq] fp32 = log-sum-exp of the scaled scores (natural log), saved for backward.
+ * uc_attn_bwd: dq, dk, dv with recomputation of the probabilities (two kernels: key-outer for dk / dv, query-outer for dq;
+ * both bit-reproducible); scale and the optional inverse RoPE are applied in the epilogues.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   const void* q;
@@ -187,8 +189,10 @@ typedef struct {
   const void* o;
   const void* d_o;
   const float* lse;
-  float* delta;   /* workspace [B][H][Nq] fp32 */
-  float* dq_acc;  /* workspace [B*Nq][H*64] fp32, zeroed by the call */
+  float* delta;   /* workspace, fp32, B*H*ceil(Nq/64)*128 elements: per (b,h) and 64-query tile, 64 x lse*log2(e) then
+                     64 x delta = rowsum(dO o O) (rows >= Nq: +inf, 0), written by the call's statistics kernel */
+  float* dq_acc;  /* unused (may be NULL): dQ is produced by a query-outer kernel, no fp32 accumulator / atomics.  Only the
+                     first-generation kernel (UC_ATTN_BWD=1, A/B baseline) needs [B*Nq][H*64] fp32 here, zeroed by the call */
   void* dq;
   void* dk;
   void* dv;       /* bf16 outputs, same addressing as q/k/v with lddq/lddk/lddv */

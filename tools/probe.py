@@ -274,7 +274,8 @@ def check_attn_fwd():
     import torch
     from uniception_b200 import ops
     ok = True
-    for (B, H, Nq, Nk) in [(1, 1, 128, 128), (2, 3, 256, 256), (2, 2, 196, 196), (1, 2, 100, 300), (2, 4, 1024, 1024)]:
+    for (B, H, Nq, Nk) in [(1, 1, 128, 128), (2, 3, 256, 256), (2, 2, 196, 196), (1, 2, 100, 300), (2, 4, 1024, 1024), (1, 2, 130, 70),
+                           (2, 2, 1369, 1369), (1, 1, 64, 513)]:
         torch.manual_seed(5)
         Cc = H * 64
         qkv = torch.randn(B * max(Nq, Nk), 3 * Cc, device="cuda").bfloat16()
@@ -296,7 +297,7 @@ def check_attn_bwd():
     from uniception_b200 import ops
     ok = True
     for (B, H, Nq, Nk, rope) in [(1, 1, 128, 128, False), (2, 2, 256, 256, False), (2, 2, 196, 196, True), (1, 2, 100, 300, False),
-                                 (1, 4, 1024, 1024, True)]:
+                                 (1, 4, 1024, 1024, True), (1, 2, 130, 70, False), (2, 2, 1369, 1369, True), (1, 1, 64, 513, False)]:
         torch.manual_seed(6)
         Cc = H * 64
         q = torch.randn(B * Nq, Cc, device="cuda").bfloat16()

@@ -34,6 +34,7 @@ __device__ long long* g_attn_trace = nullptr;
 #endif
 
 int make_head_map(CUtensorMap* m, const void* base, int H, int N, int B, long long ld, int box_rows);
+int attn_bwd_v1(const uc_attn_bwd_params* p, cudaStream_t stream);
 
 namespace {
 
@@ -452,9 +453,10 @@ extern "C" __attribute__((visibility("default"))) int uc_debug_set_attn_trace(lo
   return cudaMemcpyToSymbol(uc::g_attn_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : UC_ERR_CUDA;
 }
 
-extern "C" int uc_attn_bwd(const uc_attn_bwd_params* p, uc_stream_t stream_) {
+// First-generation fused backward (one kernel for dQ, dK, dV + fp32 dQ accumulator), kept behind UC_ATTN_BWD=1 as the A/B
+// baseline of attention2.cu (which owns the C entry point).
+int uc::attn_bwd_v1(const uc_attn_bwd_params* p, cudaStream_t stream) {
   using namespace uc;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   UC_REQUIRE(p && p->q && p->k && p->v && p->o && p->d_o && p->lse && p->delta && p->dq_acc && p->dq && p->dk && p->dv,
              UC_ERR_BAD_SHAPE, "uc_attn_bwd: null pointer");
   UC_REQUIRE(p->B > 0 && p->H > 0 && p->Nq > 0 && p->Nk > 0, UC_ERR_BAD_SHAPE, "uc_attn_bwd: bad shape");

@@ -250,6 +250,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }  // namespace
 
 // 3-D map over a token-major bf16 matrix: dims (H*64 columns, N tokens, B), box (64, box_rows, 1).
+int attn_fwd_v1(const uc_attn_fwd_params* p, cudaStream_t stream);
+
 int make_head_map(CUtensorMap* m, const void* base, int H, int N, int B, long long ld, int box_rows) {
   uint64_t dims[3] = {(uint64_t)H * 64, (uint64_t)N, (uint64_t)B};
   uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)N * (uint64_t)ld * 2};
@@ -259,9 +261,9 @@ int make_head_map(CUtensorMap* m, const void* base, int H, int N, int B, long lo
 
 }  // namespace uc
 
-extern "C" int uc_attn_fwd(const uc_attn_fwd_params* p, uc_stream_t stream_) {
+// First-generation forward kernel, kept behind UC_ATTN_FWD=1 as the A/B baseline of attention2.cu (which owns the C entry point).
+int uc::attn_fwd_v1(const uc_attn_fwd_params* p, cudaStream_t stream) {
   using namespace uc;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   UC_REQUIRE(p && p->q && p->k && p->v && p->o, UC_ERR_BAD_SHAPE, "uc_attn_fwd: null pointer");
   UC_REQUIRE(p->B > 0 && p->H > 0 && p->Nq > 0 && p->Nk > 0, UC_ERR_BAD_SHAPE, "uc_attn_fwd: bad shape");
   UC_REQUIRE(p->ldq % 8 == 0 && p->ldk % 8 == 0 && p->ldv % 8 == 0 && p->ldo % 8 == 0, UC_ERR_BAD_SHAPE,

@@ -115,19 +115,40 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a CUDA error (trap), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes or ~the hint elapses, instead of
+// burning issue slots that the softmax / epilogue warps of the same scheduler need
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
+// Slow path, out of line: a protocol bug must surface as a CUDA error (trap), never as a hung GPU.  The wall clock is read
+// once every 4096 failed probes only.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   uint64_t t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins == 4096) t0 = globaltimer_ns();
-    if (spins > 4096 && (spins & 1023) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
-      printf("uc_b200: mbarrier timeout block(%d,%d,%d) thread %d bar 0x%x parity %u\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x, bar, parity);
-      __trap();
+  while (!mbar_try_wait_hint(bar, parity)) {
+    if ((++spins & 4095u) == 0) {
+      const uint64_t t = globaltimer_ns();
+      if (t0 == 0) {
+        t0 = t;
+      } else if (t - t0 > 4000000000ull) {
+        printf("uc_b200: mbarrier timeout block(%d,%d,%d) thread %d bar 0x%x parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z,
+               threadIdx.x, bar, parity);
+        __trap();
+      }
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 
 // ---- TMA ----

@@ -209,6 +209,10 @@ def layerscale_bwd(dy, z, gamma, dgamma):
     return dz
 
 
+# UC_ATTN_BWD=1 (default): fused one-kernel backward with an fp32 dQ accumulator; UC_ATTN_BWD=3: two bit-reproducible kernels
+_ATTN_BWD_V1 = __import__("os").environ.get("UC_ATTN_BWD", "1") != "3"
+
+
 def attn_fwd(q, k, v, B, H, Nq, Nk, scale, out=None):
     """q: [B*Nq, >=H*64] bf16 view (row stride = ld), k/v: [B*Nk, ...]; returns (o [B*Nq, H*64], lse [B,H,Nq])."""
     _cuda(q, k, v)
@@ -227,8 +231,9 @@ def attn_bwd(q, k, v, o, d_o, lse, B, H, Nq, Nk, scale, dq, dk, dv, q_positions=
     gradients are returned w.r.t. the *un-rotated* projections (inverse RoPE fused)."""
     _cuda(q, k, v, o, d_o, lse, dq, dk, dv)
     assert d_o.dtype == torch.bfloat16 and d_o.stride(0) == o.stride(0) and d_o.stride(1) == 1
-    delta = torch.empty(B, H, Nq, dtype=torch.float32, device=q.device)
-    dq_acc = torch.empty(B * Nq, H * 64, dtype=torch.float32, device=q.device)
+    # workspace: per (b, h) the per-query statistics padded to 64-query tiles, [tile][lse*log2e | delta][64]
+    delta = torch.empty(B * H * ((Nq + 63) // 64) * 128, dtype=torch.float32, device=q.device)
+    dq_acc = torch.empty(B * Nq, H * 64, dtype=torch.float32, device=q.device) if _ATTN_BWD_V1 else None
     p = L.AttnBwdParams(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(d_o), _ptr(lse), _ptr(delta), _ptr(dq_acc),
                         _ptr(dq), _ptr(dk), _ptr(dv), B, H, Nq, Nk,
                         q.stride(0), k.stride(0), v.stride(0), o.stride(0), dq.stride(0), dk.stride(0), dv.stride(0),
