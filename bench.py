@@ -376,8 +376,9 @@ def run_b200(args, wl):
             sys.stdout.flush()
             os.dup2(keep, 1)
             os.close(keep)
-        pk.grad_sync = dp.GradSync(pk.flat_grad, pk.index, max_bucket_elems=args.bucket_mb * 1024 * 1024 // 4,
-                                   compress_bf16=bool(args.dp_bf16))
+        if args.dp_mode != "none":  # "none": diagnostic, ranks run independently (no gradient exchange)
+            pk.grad_sync = dp.GradSync(pk.flat_grad, pk.index, max_bucket_elems=args.bucket_mb * 1024 * 1024 // 4,
+                                       compress_bf16=bool(args.dp_bf16))
     a_host, b_host = _synthetic_batch(B, S, 1234 + rank)
     a_host, b_host = a_host.pin_memory(), b_host.pin_memory()
     a_dev, b_dev = a_host.to(dev), b_host.to(dev)
@@ -393,9 +394,14 @@ def run_b200(args, wl):
             loss = r1["pts3d"].sum() + r1["conf"].sum() + r2["pts3d_in_other_view"].sum() + r2["conf"].sum()
         else:
             loss = model(img1).sum()
-        loss.backward()
-        if pk.grad_sync is not None:
+        if args.dp_mode == "end" and pk.grad_sync is not None:
+            with pk.grad_sync.no_sync():  # diagnostic: nothing overlaps, one all-reduce of the whole buffer after the backward
+                loss.backward()
             pk.grad_sync.finish()
+        else:
+            loss.backward()
+            if pk.grad_sync is not None:
+                pk.grad_sync.finish()
         return loss
 
     graph = None
@@ -470,7 +476,7 @@ def run_b200(args, wl):
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM), CUDA events on the launching stream ----
     ops.PROFILE = []
-    for _ in range(2):
+    for _ in range(0 if args.skip_instrumented else 2):
         step(a_dev, b_dev)  # eager: per-launch CUDA events
     torch.cuda.synchronize()
     gemm_ms = sum(rec[0].elapsed_time(rec[1]) for rec in ops.PROFILE)
@@ -557,6 +563,9 @@ def main():
     ap.add_argument("--graph-multi", type=int, default=1, help="capture the step (incl. NCCL buckets) when N > 1 too")
     ap.add_argument("--bucket-mb", type=int, default=128, help="gradient all-reduce bucket size (N > 1)")
     ap.add_argument("--dp-bf16", type=int, default=0, help="1: all-reduce bf16-compressed gradient buckets (halves NVLink bytes)")
+    ap.add_argument("--dp-mode", default="overlap", choices=["overlap", "end", "none"],
+                    help="overlap (default): buckets all-reduced as the backward retires them; end / none: diagnostics")
+    ap.add_argument("--skip-instrumented", action="store_true", help="skip the per-GEMM CUDA-event pass (roofline block reports 0)")
     ap.add_argument("--gemm-breakdown", action="store_true", help="print per-shape GEMM timings of the instrumented steps to stderr")
     args = ap.parse_args()
     if args.workload is None:

@@ -105,6 +105,11 @@ typedef struct {
 } uc_gemm_params;
 
 UC_API int uc_gemm(const uc_gemm_params* p, uc_stream_t stream);
+/* Tile distribution of the CTA-pair GEMM: 0 (default) static round robin over the persistent clusters; 1 an atomic tile queue, so
+ * that clusters whose SMs are temporarily held by other kernels (the NCCL all-reduce that data parallelism overlaps with the
+ * backward pass -- the reference's users get this from DistributedDataParallel, prediction_heads/dpt.py:82 -- or another
+ * stream's kernel) take fewer tiles instead of adding a wave.  Returns the previous setting.  Process-wide. */
+UC_API int uc_set_gemm_dynamic(int on);
 
 /* ------------------------------------------------------------------------------------------
  * 2-D RoPE.  uc_rope2d == curope.rope_2d (curope.cpp:49-69, kernels.cu:17-108): in place on

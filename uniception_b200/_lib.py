@@ -114,6 +114,7 @@ EXPORTS = {
     "uc_last_error": (C.c_size_t, [C.c_char_p, C.c_size_t]),
     "uc_launch_count": (C.c_uint64, []),
     "uc_gemm": (C.c_int, [C.POINTER(GemmParams), vp]),
+    "uc_set_gemm_dynamic": (C.c_int, [C.c_int]),
     "uc_rope2d": (C.c_int, [C.POINTER(Rope2dParams), vp]),
     "uc_rope2d_table": (C.c_int, [vp, i32, i32, f32, f32, vp]),
     "uc_layernorm_fwd": (C.c_int, [C.POINTER(LayerNormFwdParams), vp]),

@@ -96,7 +96,7 @@ __device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
 // idled half-empty for the difference), so items are handed out by an atomic counter: the TMA warp fetches the next item,
 // publishes it in a 4-slot shared-memory ring (mbarrier = release / acquire) and the MMA / softmax warps follow.  The producer
 // can never be more than two items ahead of the slowest consumer (operand buffers), so four slots need no "empty" barriers.
-// counter[0] = next item, counter[1] = CTAs finished; the last CTA to leave resets both for the slot's next launch.
+// counter[0] = next item, counter[1] = CTAs that drew their sentinel; the last of them resets both for the slot's next launch.
 struct ItemQueue {
   uint32_t bar0;  // 4 "full" mbarriers, 8 bytes apart
   volatile int* slots;
@@ -110,20 +110,24 @@ struct ItemQueue {
     }
     return __shfl_sync(0xffffffffu, it, 0);
   }
+  // producer, when it has drawn its sentinel (item >= n_items): this CTA takes no more items; once every CTA has said so
+  // nobody touches the counters again and the last one resets them for the slot's next launch (off the kernel's exit path)
+  __device__ __forceinline__ void retire(int lane) const {
+    if (lane == 0) {
+      const int done = atomicAdd(counter + 1, 1);
+      if (done == (int)gridDim.x - 1) {
+        counter[0] = 0;
+        counter[1] = 0;
+        __threadfence();
+      }
+    }
+  }
   __device__ __forceinline__ int consume(int n) const {
     mbar_wait(bar0 + 8u * (n & 3), (n >> 2) & 1);
     return slots[n & 3];
   }
   __device__ __forceinline__ void init() const {
     for (int i = 0; i < 4; ++i) mbar_init(bar0 + 8u * i, 1);
-  }
-  __device__ __forceinline__ void finish() const {  // one thread per CTA, after the CTA's last use of the queue
-    const int done = atomicAdd(counter + 1, 1);
-    if (done == (int)gridDim.x - 1) {
-      counter[0] = 0;
-      counter[1] = 0;
-      __threadfence();
-    }
   }
 };
 
@@ -273,7 +277,10 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     int g = 0;  // tile counter of this CTA
     for (int n = 0;; ++n) {
       const int it = queue.produce(n, lane);
-      if (it >= n_items) break;
+      if (it >= n_items) {
+        queue.retire(lane);
+        break;
+      }
       const int bh = it / nq, qt = it % nq;
       const int b = bh / a.H, h = bh % a.H;
       mbar_wait(q_empty(n & 1), ((n >> 1) & 1) ^ 1u);
@@ -484,7 +491,6 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, F3_TM_COLS);
-    if (lane == 0) queue.finish();
   }
 }
 
@@ -632,7 +638,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     int g = 0;
     for (int n = 0;; ++n) {
       const int it = queue.produce(n, lane);
-      if (it >= n_items) break;
+      if (it >= n_items) {
+        queue.retire(lane);
+        break;
+      }
       const int bh = it / nq, qt = it % nq;
       const int b = bh / a.H, h = bh % a.H;
       mbar_wait(qdo_empty, (n & 1) ^ 1u);  // S / dP MMAs of the previous item's last tile have read Q and dO
@@ -764,7 +773,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, DQ_TM_COLS);
-    if (lane == 0) queue.finish();
   }
 }
 
@@ -826,7 +834,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     int g = 0;
     for (int n = 0;; ++n) {
       const int it = queue.produce(n, lane);
-      if (it >= n_items) break;
+      if (it >= n_items) {
+        queue.retire(lane);
+        break;
+      }
       const int bh = it / nk, kt = it % nk;
       const int b = bh / a.H, h = bh % a.H;
       mbar_wait(kv_empty, (n & 1) ^ 1u);  // S^T / dP^T MMAs of the previous item's last sub-tile have read K and V
@@ -953,7 +964,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, KV_TM_COLS);
-    if (lane == 0) queue.finish();
   }
 }
 
@@ -967,21 +977,6 @@ int set_smem(K kernel, uint32_t bytes, const char* what) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   UC_REQUIRE(e == cudaSuccess, UC_ERR_CUDA, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
   return UC_OK;
-}
-
-// Work counters of the persistent kernels: 1024 slots of (next item, CTAs finished), zero at load and reset by the kernels
-// themselves.  Launches take slots round robin: two launches that can overlap in time (different streams, programmatic
-// dependent launch) never share one, and a captured graph replays with the slots it was captured with.
-__device__ int g_attn_work[2048];
-int* work_slot() {
-  static int* base = nullptr;
-  static unsigned seq = 0;
-  if (!base) {
-    void* p = nullptr;
-    if (cudaGetSymbolAddress(&p, g_attn_work) != cudaSuccess) return nullptr;
-    base = static_cast<int*>(p);
-  }
-  return base + 2 * (__atomic_fetch_add(&seq, 1u, __ATOMIC_RELAXED) % 1024u);
 }
 
 dim3 persistent_grid(long long items) {

@@ -32,6 +32,7 @@ int make_tensor_map(CUtensorMap* out, const void* base, CUtensorMapDataType dtyp
                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
 
 int sm_count();
+int* work_slot();  // device pointer to a zeroed (next item, finished) counter pair for one persistent-kernel launch (runtime.cu)
 
 // Programmatic dependent launch (PDL): every hot-path kernel is launched with the programmatic-stream-serialization
 // attribute, triggers its dependents after its own set-up (barrier init, TMEM allocation) and calls pdl_wait() before it
@@ -293,6 +294,16 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
       "r"(rank)
       : "memory");
 }
+// store a 32-bit word at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void st_shared_cluster_u32(uint32_t addr, uint32_t rank, uint32_t v) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "st.shared::cluster.u32 [ra], %2;\n\t}" ::"r"(addr),
+      "r"(rank), "r"(v)
+      : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 // TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit 24 cleared)
 __device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
   asm volatile(

@@ -35,6 +35,7 @@ struct GemmArgs {
   const int* positions;
   const float* rope_table;
   float* colsum;  // optional [n]: += column sums of the bf16 C tile (pair kernel epilogue)
+  int* work;      // pair kernel: (next item, clusters finished) counters of this launch (runtime.cu: work_slot)
 };
 
 template <int BN>
@@ -389,11 +390,27 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   auto ld_bar = [&](int e, int which) { return bar_base + 8u * (2 * STAGES + 6 + 2 * e + which); };  // per epilogue warp: input tile A / B landed
+  // Dynamic tile queue.  Items (tile, k-split) are handed out by an atomic counter instead of a static round robin: a
+  // cluster that starts late -- its SMs were held by another stream's kernel or by an NCCL all-reduce CTA -- simply takes
+  // fewer tiles, where the static split made the whole GEMM wait for a second wave.  The leader CTA's producer warp fetches
+  // the next item and publishes it into an 8-slot ring in BOTH CTAs' shared memory (remote store + remote mbarrier arrive
+  // with release semantics at cluster scope); every other role of both CTAs follows the ring.  The producer is never more than
+  // three items ahead of the slowest role (smem stages, two TMEM accumulators), so eight slots need no "empty" barriers.
+  auto q_bar = [&](int s) { return bar_base + 8u * (40 + s); };
+  const uint32_t q_slot = bar_base + 8u * 48;
+  auto next_item = [&](int n) -> int {  // consumer side (all lanes of the calling warp)
+    // no cluster-scope fence here (ptxas turns one into MEMBAR.ALL.GPU + CCTL.IVALL per call): the slot lives in THIS CTA's
+    // shared memory, the leader's remote store is ordered before its remote arrive (mbarrier.arrive.release.cluster), and the
+    // volatile load below cannot move above the wait
+    mbar_wait(q_bar(n & 7), (n >> 3) & 1);
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(q_slot + 4u * (n & 7)) : "memory");
+    return (int)v;
+  };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
@@ -408,6 +425,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(tempty_bar(a), 2 * NUM_EPI_WARPS);  // leader: epilogue warps of both CTAs
     }
     for (int e = 0; e < NUM_EPI_WARPS; ++e) { mbar_init(ld_bar(e, 0), 1); mbar_init(ld_bar(e, 1), 1); }
+    for (int q = 0; q < 8; ++q) mbar_init(q_bar(q), 1);
     fence_barrier_init();
   }
   cluster_sync_all();  // barrier inits visible to the peer before any remote arrive / TMA credit
@@ -421,6 +439,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   pdl_launch_dependents();  // after the TMEM allocation (common.cuh: PDL rules)
+  // the launch's work counter is private to it (not produced by the predecessor kernel): the leader's first fetch goes out
+  // BEFORE the grid dependency wait, so its round trip hides under the predecessor's tail
+  const int cluster_id = blockIdx.x >> 1;
+  int first_item = cluster_id;  // g.work == nullptr: static round robin (item = cluster + k * clusters), no counters
+  if (g.work && warp == 0 && rank == 0 && lane == 0) first_item = atomicAdd(g.work, 1);
   pdl_wait();
 
   const int total = g.num_m * g.num_n * g.split_k;  // num_m counts 256-row blocks here
@@ -429,7 +452,47 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ===================== TMA producer (both CTAs) =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int item = cluster_id; item < total; item += num_clusters) {
+    // leader: the fetch of item qn+1 is issued before the k-loop of item qn and published a few k-blocks into it, so neither
+    // the atomic's round trip nor the remote store / arrive that tells the peer sits between two tiles' TMA streams
+    auto publish = [&](int qn, int item) {
+      if (lane == 0) {
+        const uint32_t slot = q_slot + 4u * (qn & 7);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(slot), "r"((uint32_t)item) : "memory");
+        st_shared_cluster_u32(slot, 1, (uint32_t)item);
+        mbar_arrive(q_bar(qn & 7));
+        mbar_arrive_cluster(q_bar(qn & 7), 1);
+      }
+      __syncwarp();
+    };
+    int fetched = 0;
+    if (rank == 0) {
+      fetched = __shfl_sync(0xffffffffu, first_item, 0);
+      publish(0, fetched);
+    }
+    for (int qn = 0;; ++qn) {
+      int item;
+      int fetched_next = 0;
+      if (rank == 0) {
+        item = fetched;
+        if (item < total && lane == 0)  // consumed below, after the first k-blocks
+          fetched_next = g.work ? atomicAdd(g.work, 1) : cluster_id + (qn + 1) * num_clusters;
+      } else {
+        item = next_item(qn);
+      }
+      if (item >= total) {
+        // this cluster takes no more items.  Once every cluster has said so nobody touches the counters again: the last one
+        // resets them for the slot's next launch -- here, in the producer warp, while the MMA / epilogue warps still work on
+        // the last tiles, not on the kernel's exit path
+        if (g.work && rank == 0 && lane == 0) {
+          const int done = atomicAdd(g.work + 1, 1);
+          if (done == num_clusters - 1) {
+            g.work[0] = 0;
+            g.work[1] = 0;
+            __threadfence();
+          }
+        }
+        break;
+      }
       const int split = item % g.split_k;
       const int tile = item / g.split_k;
       const int m0 = (g.n_fastest ? (tile / g.num_n) : (tile % g.num_m)) * 256 + 128 * (int)rank;
@@ -457,6 +520,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        if (rank == 0 && kb == min(kb0 + 2, kb1 - 1)) {
+          fetched = __shfl_sync(0xffffffffu, fetched_next, 0);
+          publish(qn + 1, fetched);
+        }
+      }
+      if (rank == 0 && kb0 >= kb1) {  // empty k-range (cannot happen for a scheduled split, kept for symmetry with the consumers)
+        fetched = __shfl_sync(0xffffffffu, fetched_next, 0);
+        publish(qn + 1, fetched);
       }
     }
   } else if (warp == 1) {
@@ -469,7 +540,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = cluster_id; item < total; item += num_clusters) {
+      for (int qn = 0;; ++qn) {
+        const int item = next_item(qn);
+        if (item >= total) break;
         const int split = item % g.split_k;
         const int kb0 = split * g.kb_per_split;
         const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
@@ -536,7 +609,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tma_store_commit();
       }
     };
-    for (int item = cluster_id; item < total; item += num_clusters) {
+    for (int qn = 0;; ++qn) {
+      const int item = next_item(qn);
+      if (item >= total) break;
       const int split = item % g.split_k;
       const int tile = item / g.split_k;
       const int m0 = (g.n_fastest ? (tile / g.num_n) : (tile % g.num_m)) * 256 + 128 * (int)rank;
@@ -749,6 +824,16 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, in
 
 }  // namespace uc
 
+// Tile distribution of the pair GEMM.  0 (default): static round robin -- fastest when the GEMM owns the GPU.  1: atomic tile
+// queue -- a cluster whose SMs are held by somebody else's CTAs (an NCCL all-reduce overlapped with the backward pass, a kernel
+// of another stream) takes fewer tiles instead of forcing a second wave.  dp.GradSync switches it on for world sizes > 1.
+static int g_gemm_dynamic = [] { const char* e = getenv("UC_GEMM_DYNAMIC"); return e ? atoi(e) : 0; }();
+extern "C" int uc_set_gemm_dynamic(int on) {
+  const int prev = g_gemm_dynamic;
+  g_gemm_dynamic = on ? 1 : 0;
+  return prev;
+}
+
 extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
   using namespace uc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -872,6 +957,7 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
   g.aux_in = static_cast<const __nv_bfloat16*>(p->aux_in);
   g.positions = p->positions; g.rope_table = p->rope_table;
   g.colsum = (pair && p->c_dtype == UC_DTYPE_BF16) ? p->c_colsum : nullptr;
+  g.work = nullptr;
 
   const long long total = (long long)num_m * num_n * split_k;
   if (pair) {
@@ -892,6 +978,10 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
       if (r) return r;
     }
     const int clusters = (int)(total < slots ? total : slots);
+    if (g_gemm_dynamic) {
+      g.work = work_slot();
+      UC_REQUIRE(g.work, UC_ERR_CUDA, "uc_gemm: work counters unavailable");
+    }
     return launch2<256>(tmA, tmB, tmC, tmAux, g, 2 * clusters, stream);
   }
   const int grid = (int)(total < sms ? total : sms);

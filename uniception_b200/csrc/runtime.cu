@@ -77,6 +77,25 @@ bool pdl_enabled() {
   return on;
 }
 
+// Work counters of the persistent kernels with dynamic tile / item queues (pair GEMM, attention): 2048 slots of
+// (next item, CTAs or clusters finished), zero at load and reset by the kernels themselves when their last CTA leaves.
+// Launches take slots round robin, so two launches that can overlap in time (different streams, programmatic dependent
+// launch) never share one, and a captured CUDA graph replays with the slots it was captured with.
+__device__ int g_work_slots[4096];
+int* work_slot() {
+  static int* base = nullptr;
+  static unsigned seq = 0;
+  if (!base) {
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, g_work_slots) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    base = static_cast<int*>(p);
+  }
+  return base + 2 * (__atomic_fetch_add(&seq, 1u, __ATOMIC_RELAXED) % 2048u);
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
