@@ -544,8 +544,37 @@ def run_b200(args, wl):
             line["cpu_baseline"] = {"value": r["value"], "unit": wl["unit"], "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        _shutdown_distributed(graph)
+
+
+def _shutdown_distributed(graph) -> None:
+    """Leave a multi-rank run without hanging.  A CUDA graph that captured NCCL all-reduces keeps references into the
+    communicator: ncclCommDestroy underneath `destroy_process_group()` was observed to block forever after such a capture
+    (both ranks had printed / finished; the launcher had to be killed).  So: drain the device, drop the graph, rendezvous,
+    then try the graceful teardown on a helper thread and leave the process regardless after a few seconds -- every result has
+    been printed and flushed by then."""
+    import threading
+
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.synchronize()
+    if graph is not None:
+        try:
+            graph.reset()
+        except Exception:  # pragma: no cover
+            pass
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(timeout=10.0)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def main():

@@ -304,6 +304,11 @@ UC_API int uc_depth_space(const void* src, void* dst, int32_t B, int32_t h, int3
                           uc_stream_t stream);
 UC_API int uc_bilinear_fwd(const void* in, void* out, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, int32_t C,
                            uc_stream_t stream);
+/* the same resampling from an fp32 map (bf16 out): the 1x1 `out_conv` of a fusion block commutes with the interpolation that
+ * precedes it (dpt_block.py:251-255; both are linear and the interpolation weights sum to 1), so the engine runs the conv at
+ * the LOW resolution with fp32 output and resamples that -- a quarter of the conv's FLOPs and one bf16 rounding less */
+UC_API int uc_bilinear_fwd_f32in(const void* in, void* out, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, int32_t C,
+                                 uc_stream_t stream);
 UC_API int uc_bilinear_bwd(const void* dout, void* din, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, int32_t C,
                            uc_stream_t stream);
 UC_API int uc_elementwise(int32_t op, const void* a, const void* b, const void* c, void* out, int64_t n, uc_stream_t stream);

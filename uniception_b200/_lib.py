@@ -132,6 +132,7 @@ EXPORTS = {
     "uc_col2im3x3": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "uc_depth_space": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "uc_bilinear_fwd": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "uc_bilinear_fwd_f32in": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "uc_bilinear_bwd": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "uc_elementwise": (C.c_int, [i32, vp, vp, vp, vp, i64, vp]),
     "uc_headnorm_fwd": (C.c_int, [C.POINTER(HeadNormParams), vp]),

@@ -89,11 +89,21 @@ __global__ void depth_space_kernel(const __nv_bfloat16* __restrict__ src, __nv_b
 }
 
 // bilinear, align_corners=True (F.interpolate, dpt_block.py:251-254, dpt.py:304): src coordinate = dst * (in-1)/(out-1)
-__global__ void bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int Hi, int Wi, int Ho,
+template <bool F32IN>
+__global__ void bilinear_fwd_kernel(const void* __restrict__ in_, __nv_bfloat16* __restrict__ out, int B, int Hi, int Wi, int Ho,
                                     int Wo, int C) {
   const int c8 = C / 8;
   const float sy = Ho > 1 ? float(Hi - 1) / float(Ho - 1) : 0.f, sx = Wo > 1 ? float(Wi - 1) / float(Wo - 1) : 0.f;
   const int64_t total = (int64_t)B * Ho * Wo * c8;
+  auto load8 = [&](int64_t pixel, int cg, float (&v)[8]) {
+    if (F32IN) {
+      const float4* q = reinterpret_cast<const float4*>(static_cast<const float*>(in_) + pixel * C) + 2 * cg;
+      const float4 lo = __ldg(q), hi = __ldg(q + 1);
+      v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+    } else {
+      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(in_) + pixel * C) + cg), v);
+    }
+  };
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int cg = idx % c8;
     const int64_t pix = idx / c8;
@@ -102,12 +112,12 @@ __global__ void bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
     const int y0 = min((int)fy, Hi - 1), x0 = min((int)fx, Wi - 1);
     const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
     const float ly = fy - y0, lx = fx - x0;
-    const __nv_bfloat16* base = in + (int64_t)b * Hi * Wi * C;
+    const int64_t base = (int64_t)b * Hi * Wi;
     float a[8], bq[8], c[8], d[8], r[8];
-    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(base + ((int64_t)y0 * Wi + x0) * C) + cg), a);
-    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(base + ((int64_t)y0 * Wi + x1) * C) + cg), bq);
-    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(base + ((int64_t)y1 * Wi + x0) * C) + cg), c);
-    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(base + ((int64_t)y1 * Wi + x1) * C) + cg), d);
+    load8(base + (int64_t)y0 * Wi + x0, cg, a);
+    load8(base + (int64_t)y0 * Wi + x1, cg, bq);
+    load8(base + (int64_t)y1 * Wi + x0, cg, c);
+    load8(base + (int64_t)y1 * Wi + x1, cg, d);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       r[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * bq[j]) + ly * ((1.f - lx) * c[j] + lx * d[j]);
@@ -202,9 +212,16 @@ extern "C" int uc_depth_space(const void* src, void* dst, int32_t B, int32_t h, 
 
 extern "C" int uc_bilinear_fwd(const void* in, void* out, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, int32_t C, uc_stream_t st) {
   UC_REQUIRE(in && out && B > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C % 8 == 0, UC_ERR_BAD_SHAPE, "uc_bilinear_fwd: bad arguments");
-  bilinear_fwd_kernel<<<grid_for((int64_t)B * Ho * Wo * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(st)>>>(
-      static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), B, Hi, Wi, Ho, Wo, C);
+  bilinear_fwd_kernel<false><<<grid_for((int64_t)B * Ho * Wo * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(st)>>>(
+      in, static_cast<__nv_bfloat16*>(out), B, Hi, Wi, Ho, Wo, C);
   return check_launch("uc_bilinear_fwd");
+}
+
+extern "C" int uc_bilinear_fwd_f32in(const void* in, void* out, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, int32_t C, uc_stream_t st) {
+  UC_REQUIRE(in && out && B > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C % 8 == 0, UC_ERR_BAD_SHAPE, "uc_bilinear_fwd_f32in: bad arguments");
+  bilinear_fwd_kernel<true><<<grid_for((int64_t)B * Ho * Wo * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(st)>>>(
+      in, static_cast<__nv_bfloat16*>(out), B, Hi, Wi, Ho, Wo, C);
+  return check_launch("uc_bilinear_fwd_f32in");
 }
 
 extern "C" int uc_bilinear_bwd(const void* dout, void* din, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, int32_t C, uc_stream_t st) {

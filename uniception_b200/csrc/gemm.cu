@@ -826,7 +826,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, in
 
 // Tile distribution of the pair GEMM.  0 (default): static round robin -- fastest when the GEMM owns the GPU.  1: atomic tile
 // queue -- a cluster whose SMs are held by somebody else's CTAs (an NCCL all-reduce overlapped with the backward pass, a kernel
-// of another stream) takes fewer tiles instead of forcing a second wave.  dp.GradSync switches it on for world sizes > 1.
+// of another stream) takes fewer tiles instead of forcing a second wave.  Measured at N = 2 (profiles/r02c): no gain over the static split, so nothing switches it on by default.
 static int g_gemm_dynamic = [] { const char* e = getenv("UC_GEMM_DYNAMIC"); return e ? atoi(e) : 0; }();
 extern "C" int uc_set_gemm_dynamic(int on) {
   const int prev = g_gemm_dynamic;

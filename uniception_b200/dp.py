@@ -42,16 +42,6 @@ class GradSync:
         AVERAGED gradient (the same trade as DDP's bf16_compress_hook).  Off by default: fp32 matches what the reference's
         users get from DistributedDataParallel."""
         self.flat = flat_grad
-        if flat_grad.is_cuda and dist.is_initialized() and dist.get_world_size(group) > 1:
-            # the all-reduce kernels of the overlapped buckets hold a few SMs while the backward GEMMs run: hand GEMM tiles out
-            # dynamically so that the clusters that lost their SMs do not cost a whole extra wave (include/uc_b200.h)
-            # (UC_GEMM_DYNAMIC in the environment pins the choice for A/B runs)
-            import os
-
-            from . import _lib
-
-            if os.environ.get("UC_GEMM_DYNAMIC") is None:
-                _lib.lib.uc_set_gemm_dynamic(1)
         self.compress = bool(compress_bf16) and flat_grad.is_cuda
         self._bf16 = torch.empty(flat_grad.numel(), dtype=torch.bfloat16, device=flat_grad.device) if self.compress else None
         self.group = group

@@ -343,8 +343,11 @@ def _fusion(tape, a, b, B, H, W, d):
     """FeatureFusionBlock_custom: a [+ RCU1(b)] -> RCU2 -> bilinear x2 (align_corners) -> 1x1 conv."""
     out = a if b is None else _rcu(tape, b, B, H, W, d["resConfUnit1"], extra_skip=a)
     out = _rcu(tape, out, B, H, W, d["resConfUnit2"])
-    out = resize(tape, out, B, H, W, 2 * H, 2 * W)
-    return conv1x1(tape, out, d["out"])
+    # out_conv(interpolate(x)) == interpolate(out_conv(x)): a 1x1 conv is per-pixel affine and the bilinear weights sum to 1
+    # (dpt_block.py:251-255).  The conv runs on the low-resolution map (a quarter of the FLOPs) with fp32 output and the
+    # resampling reads that, so the pair costs ONE bf16 rounding instead of two.
+    out = conv1x1(tape, out, d["out"], out_dtype=torch.float32)
+    return resize(tape, out, B, H, W, 2 * H, 2 * W)
 
 
 def dpt_feature_forward(tape: Tape, Wt: DPTFeatureWeights, feats: List[torch.Tensor], B: int, h: int, w: int):

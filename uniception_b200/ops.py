@@ -357,10 +357,12 @@ def space_to_depth(x: torch.Tensor, B: int, h: int, w: int, s: int) -> torch.Ten
 
 
 def bilinear_fwd(x: torch.Tensor, B: int, Hi: int, Wi: int, Ho: int, Wo: int) -> torch.Tensor:
+    """x bf16 or fp32 NHWC [B*Hi*Wi, C] -> bf16 [B*Ho*Wo, C] (align_corners=True)."""
     _cuda(x)
-    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    assert x.dtype in (torch.bfloat16, torch.float32) and x.is_contiguous()
     out = torch.empty(B * Ho * Wo, x.shape[1], dtype=torch.bfloat16, device=x.device)
-    L.check(L.lib.uc_bilinear_fwd(_ptr(x), _ptr(out), B, Hi, Wi, Ho, Wo, x.shape[1], _stream()))
+    fn = L.lib.uc_bilinear_fwd if x.dtype == torch.bfloat16 else L.lib.uc_bilinear_fwd_f32in
+    L.check(fn(_ptr(x), _ptr(out), B, Hi, Wi, Ho, Wo, x.shape[1], _stream()))
     return out
 
 
