@@ -298,6 +298,31 @@ UC_API int uc_head_post_bwd(const uc_head_post_bwd_params* p, uc_stream_t stream
  *   F.interpolate(bilinear, align_corners=True) : uc_bilinear_fwd / uc_bilinear_bwd
  *   uc_elementwise op 0: a+b  1: relu(a)  2: a*(b>0)  3: a+b+c
  * ------------------------------------------------------------------------------------------ */
+/* 3x3 / stride 1 / pad 1 convolution on NHWC bf16 maps as an implicit GEMM (replaces nn.Conv2d(k=3, padding=1) of
+ * dpt_block.py:133-152 (ResidualConvUnit), prediction_heads/dpt.py:131-140 (layer_rn) and :262-283 (regression head) and their
+ * autograd backward).  No column buffer: per output tile the 9 taps are 9 shifted 4-D TMA boxes of the map (out-of-image
+ * pixels zero-fill = the padding) accumulated in TMEM by the CTA-pair tcgen05 kernel of uc_gemm; outputs leave through 4-D TMA
+ * stores clipped at the image border.  Weight layout [cout, 9 * cin], k = (r * 3 + t) * cin + ci  (= conv.weight.permute(0,2,3,1)).
+ *   mode 0  y  = conv(x, w) [+ bias] [ReLU | + residual]                 x [B*H*W, cin]  -> y  [B*H*W, cout]
+ *   mode 1  dx = conv(dy, flipped w^T) [* (relu_out > 0)]                dy [B*H*W, cout] -> dx [B*H*W, cin]
+ *   mode 2  dw += dy^T * patches(x)   (fp32, accumulated, split over the pixels with TMA reduce-add)   dw [cout, 9 * cin]
+ * Channel counts are multiples of 64 (the engine pads); stride-2 convolutions keep the uc_im2col3x3 path. */
+typedef struct {
+  int32_t mode;
+  int32_t B, H, W;
+  int32_t cin, cout;
+  const void* x;        /* mode 0, 2 */
+  const void* w;        /* mode 0, 1: bf16 [cout, 9 * cin] */
+  void* y;              /* mode 0 */
+  const void* dy;       /* mode 1, 2 */
+  void* dx;             /* mode 1 */
+  float* dw;            /* mode 2: fp32 [cout, 9 * cin], accumulated */
+  const float* bias;    /* mode 0, optional [cout] */
+  const void* residual; /* mode 0, optional bf16 [B*H*W, cout] */
+  const void* relu_out; /* mode 1, optional bf16 [B*H*W, cin]: the ReLU output whose input gradient dx is */
+  int32_t relu;         /* mode 0: fused ReLU */
+} uc_conv3x3_params;
+UC_API int uc_conv3x3(const uc_conv3x3_params* p, uc_stream_t stream);
 UC_API int uc_im2col3x3(const void* x, void* cols, int32_t B, int32_t H, int32_t W, int32_t C, int32_t stride, uc_stream_t stream);
 UC_API int uc_col2im3x3(const void* dcols, void* dx, int32_t B, int32_t H, int32_t W, int32_t C, int32_t stride, uc_stream_t stream);
 UC_API int uc_depth_space(const void* src, void* dst, int32_t B, int32_t h, int32_t w, int32_t C, int32_t s, int32_t to_space,

@@ -108,6 +108,14 @@ class HeadNormParams(C.Structure):
     ]
 
 
+class Conv3x3Params(C.Structure):
+    _fields_ = [
+        ("mode", i32), ("B", i32), ("H", i32), ("W", i32), ("cin", i32), ("cout", i32),
+        ("x", vp), ("w", vp), ("y", vp), ("dy", vp), ("dx", vp), ("dw", vp), ("bias", vp), ("residual", vp), ("relu_out", vp),
+        ("relu", i32),
+    ]
+
+
 # every symbol include/uc_b200.h declares (checked by tests/test_cabi.py)
 EXPORTS = {
     "uc_version": (C.c_int, []),
@@ -128,6 +136,7 @@ EXPORTS = {
     "uc_nchw_to_nlc": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
     "uc_head_post_fwd": (C.c_int, [C.POINTER(HeadPostFwdParams), vp]),
     "uc_head_post_bwd": (C.c_int, [C.POINTER(HeadPostBwdParams), vp]),
+    "uc_conv3x3": (C.c_int, [C.POINTER(Conv3x3Params), vp]),
     "uc_im2col3x3": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "uc_col2im3x3": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "uc_depth_space": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),

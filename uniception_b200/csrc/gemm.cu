@@ -36,6 +36,16 @@ struct GemmArgs {
   const float* rope_table;
   float* colsum;  // optional [n]: += column sums of the bf16 C tile (pair kernel epilogue)
   int* work;      // pair kernel: (next item, clusters finished) counters of this launch (runtime.cu: work_slot)
+  // implicit-GEMM 3x3 convolution (uc_conv3x3; pair kernel instantiated with CONV != 0), NHWC maps, stride 1, pad 1:
+  //   CONV 1 (fwd / dgrad): the A tile of a CTA is a TW x TH pixel window (TW * TH = 128) of one image, fetched per k-block by a
+  //     4-D TMA box at the tap's offset (out-of-image pixels zero-fill = the padding); C / aux tiles leave / arrive the same way.
+  //   CONV 2 (wgrad): K runs over pixels; a k-block is a TW x TH window (TW * TH = 64) of dy (A, unshifted) and of x (B, shifted
+  //     by the tap of each 64-column block of the [cout, 9 cin] weight gradient).
+  int cv_H, cv_W, cv_tw_log2, cv_tiles_x, cv_tiles_y;
+  int cv_kb_per_tap;    // CONV 1: channel blocks (of 64) per tap in A
+  int cv_b_tap_stride;  // CONV 1: 0 = B is K-major with k = tap * C + c (fwd); > 0 = B is MN-major and tap t reads the column
+                        // block (8 - t) * stride (dgrad: the spatially flipped filter)
+  int cv_cin;           // CONV 2: channels of x (columns per tap)
 };
 
 template <int BN>
@@ -81,7 +91,7 @@ __device__ __forceinline__ void epilogue_math(const GemmArgs& g, int row, int n,
   const int epi = g.epilogue & MASK;  // MASK: flags this instantiation can see (everything else is compiled out)
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-  if (epi & UC_EPI_BIAS) {
+  if ((epi & UC_EPI_BIAS) && n < g.n) {  // (n >= g.n: partial last column tile of a convolution, clipped by the TMA store)
     const float4* b4 = reinterpret_cast<const float4*>(g.bias + n);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -373,7 +383,7 @@ struct Cfg2 {  // BN = 256: 256 x 256 tiles (the only instantiation); BN = 128 c
 
 // MASK / F32: epilogue flags and output type this instantiation handles.  One generic kernel with run-time flags is
 // 12 K SASS instructions (~200 KB): the epilogue warps then stall on instruction fetch (ncu: 1.0 "no_instruction" per issue).
-template <int MASK, bool F32, int BN>
+template <int MASK, bool F32, int BN, int CONV = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, const GemmArgs g) {
@@ -499,23 +509,64 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int n0 = (g.n_fastest ? (tile % g.num_n) : (tile / g.num_m)) * BN + (BN / 2) * (int)rank;
       const int kb0 = split * g.kb_per_split;
       const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
+      int cx0 = 0, cy0 = 0, cimg = 0;  // CONV 1: this CTA's pixel window
+      if (CONV == 1) {
+        const int tm = g.n_fastest ? (tile / g.num_n) : (tile % g.num_m);
+        const int per_img = g.cv_tiles_x * g.cv_tiles_y;
+        cimg = tm / per_img;
+        const int r = tm - cimg * per_img;
+        const int ty = r / g.cv_tiles_x;
+        cx0 = (r - ty * g.cv_tiles_x) << g.cv_tw_log2;
+        cy0 = (2 * ty + (int)rank) * (128 >> g.cv_tw_log2);
+      }
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + stage * G2_STAGE_BYTES;
         const uint32_t sb = sa + G2_A_BYTES;
         if (elect_one()) {
           if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * G2_STAGE_BYTES);
-          if (!g.a_mn) {
+          if (CONV == 1) {
+            const int tap = kb / g.cv_kb_per_tap;
+            const int c0 = (kb - tap * g.cv_kb_per_tap) * 64;
+            const int dy = tap / 3, dx = tap - 3 * dy;
+            tma2_load_4d(sa, &tmA, full_bar(stage), c0, cx0 + dx - 1, cy0 + dy - 1, cimg);
+            if (!g.b_mn) {
+              tma2_load_2d(sb, &tmB, full_bar(stage), kb * BK, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 2 / 64; ++j)
+                tma2_load_2d(sb + j * 8192, &tmB, full_bar(stage), n0 + j * 64 + (8 - tap) * g.cv_b_tap_stride, c0);
+            }
+          } else if (CONV == 2) {
+            const int per_img = g.cv_tiles_x * g.cv_tiles_y;
+            const int img = kb / per_img;
+            const int r = kb - img * per_img;
+            const int ty = r / g.cv_tiles_x;
+            const int x0 = (r - ty * g.cv_tiles_x) << g.cv_tw_log2;
+            const int y0 = ty * (64 >> g.cv_tw_log2);
+            tma2_load_4d(sa, &tmA, full_bar(stage), m0, x0, y0, img);
+            tma2_load_4d(sa + 8192, &tmA, full_bar(stage), m0 + 64, x0, y0, img);
+#pragma unroll
+            for (int j = 0; j < BN / 2 / 64; ++j) {
+              const int n = n0 + j * 64;
+              const int tap = min(n / g.cv_cin, 8);  // columns >= 9 cin: partial last tile, clipped by the TMA reduce
+              const int ci = n - (n / g.cv_cin) * g.cv_cin;
+              const int dy = tap / 3, dx = tap - 3 * dy;
+              tma2_load_4d(sb + j * 8192, &tmB, full_bar(stage), ci, x0 + dx - 1, y0 + dy - 1, img);
+            }
+          } else if (!g.a_mn) {
             tma2_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
           } else {
             tma2_load_2d(sa, &tmA, full_bar(stage), m0, kb * BK);
             tma2_load_2d(sa + 8192, &tmA, full_bar(stage), m0 + 64, kb * BK);
           }
-          if (!g.b_mn) {
-            tma2_load_2d(sb, &tmB, full_bar(stage), kb * BK, n0);
-          } else {
+          if (CONV == 0) {
+            if (!g.b_mn) {
+              tma2_load_2d(sb, &tmB, full_bar(stage), kb * BK, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 2 / 64; ++j) tma2_load_2d(sb + j * 8192, &tmB, full_bar(stage), n0 + j * 64, kb * BK);
+              for (int j = 0; j < BN / 2 / 64; ++j) tma2_load_2d(sb + j * 8192, &tmB, full_bar(stage), n0 + j * 64, kb * BK);
+            }
           }
         }
         __syncwarp();
@@ -620,8 +671,32 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
       if (kb0 >= kb1) continue;
       const int row0 = m0 + lane_group * 32;
-      const int row = row0 + lane;
-      const bool row_ok = row < g.m;
+      int row = row0 + lane;
+      bool row_ok = row < g.m;
+      int cxs = 0, cys = 0, cimg = 0;  // CONV 1: pixel coordinates of this warp's 32-row group (its C / aux boxes)
+      if (CONV == 1) {
+        const int tm = g.n_fastest ? (tile / g.num_n) : (tile % g.num_m);
+        const int per_img = g.cv_tiles_x * g.cv_tiles_y;
+        cimg = tm / per_img;
+        const int r = tm - cimg * per_img;
+        const int ty = r / g.cv_tiles_x;
+        const int x0 = (r - ty * g.cv_tiles_x) << g.cv_tw_log2;
+        const int y0 = (2 * ty + (int)rank) * (128 >> g.cv_tw_log2);
+        const int tw_mask = (1 << g.cv_tw_log2) - 1;
+        const int rl0 = lane_group * 32, rl = rl0 + lane;
+        cxs = x0 + (rl0 & tw_mask);
+        cys = y0 + (rl0 >> g.cv_tw_log2);
+        row_ok = (x0 + (rl & tw_mask)) < g.cv_W && (y0 + (rl >> g.cv_tw_log2)) < g.cv_H;
+        row = 0;  // no row-addressed global access in this mode (aux tiles are staged, bias is per column)
+      }
+      auto load_aux = [&](uint32_t buf, uint32_t bar, int col) {
+        if (CONV == 1) tma_load_4d(buf, &tmAux, bar, col, cxs, cys, cimg);
+        else tma_load_2d(buf, &tmAux, bar, col, row0);
+      };
+      auto store_c = [&](uint32_t buf, int col) {
+        if (CONV == 1) tma_store_4d(&tmC, buf, col, cxs, cys, cimg);
+        else tma_store_2d(&tmC, buf, col, row0);
+      };
       const int nw = n0 + col_half * (BN / 2);  // first column of this warp's half of the tile
       if (!f32 && has_in) {
         // input tile of unit 0 ([32 rows x 64 cols] bf16 of aux_in / residual) requested BEFORE waiting for the accumulator
@@ -629,7 +704,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (NCH == 4) tma_store_wait_read1();  // the previous tile's unit-0 store has finished reading buf0
           else tma_store_wait_read0();
           mbar_arrive_expect_tx(ld_bar(e, 0), 4096);
-          tma_load_2d(buf0, &tmAux, ld_bar(e, 0), nw, row0);
+          load_aux(buf0, ld_bar(e, 0), nw);
         }
         __syncwarp();
       }
@@ -690,7 +765,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (NCH == 4 && lane == 0) {
                   tma_store_wait_read0();  // the previous tile's unit-1 store has finished reading buf1
                   mbar_arrive_expect_tx(ld_bar(e, 1), 4096);
-                  tma_load_2d(buf1, &tmAux, ld_bar(e, 1), nw + 64, row0);
+                  load_aux(buf1, ld_bar(e, 1), nw + 64);
                 }
                 mbar_wait(ld_bar(e, 0), ph_a);
                 ph_a ^= 1u;
@@ -737,7 +812,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             __syncwarp();
             if (lane == 0) {
               if (has_aux) tma_store_2d(&tmAux, buf1, n - 32, row0);
-              tma_store_2d(&tmC, outb, n - 32, row0);
+              store_c(outb, n - 32);
               tma_store_commit();
             }
             if (g.colsum) {
@@ -776,16 +851,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
-template <int MASK, bool F32, int BN>
+template <int MASK, bool F32, int BN, int CONV = 0>
 int launch2_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux, const GemmArgs& g,
                  int grid, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<MASK, F32, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<MASK, F32, BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::SMEM);
     UC_REQUIRE(e == cudaSuccess, UC_ERR_CUDA, "uc_gemm: cudaFuncSetAttribute(gemm2) failed: %s", cudaGetErrorString(e));
     configured = true;
   }
-  cudaError_t le = launch_pdl(gemm2_kernel<MASK, F32, BN>, dim3(grid), dim3(GEMM_THREADS), Cfg2<BN>::SMEM, stream, tmA, tmB, tmC, tmAux, g);
+  cudaError_t le = launch_pdl(gemm2_kernel<MASK, F32, BN, CONV>, dim3(grid), dim3(GEMM_THREADS), Cfg2<BN>::SMEM, stream, tmA, tmB, tmC, tmAux, g);
   UC_REQUIRE(le == cudaSuccess, UC_ERR_CUDA, "uc_gemm(cta_pair): launch failed: %s", cudaGetErrorString(le));
   return check_launch("uc_gemm(cta_pair)");
 }
@@ -958,6 +1033,7 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
   g.positions = p->positions; g.rope_table = p->rope_table;
   g.colsum = (pair && p->c_dtype == UC_DTYPE_BF16) ? p->c_colsum : nullptr;
   g.work = nullptr;
+  g.cv_H = g.cv_W = g.cv_tw_log2 = g.cv_tiles_x = g.cv_tiles_y = g.cv_kb_per_tap = g.cv_b_tap_stride = g.cv_cin = 0;
 
   const long long total = (long long)num_m * num_n * split_k;
   if (pair) {
@@ -990,4 +1066,138 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
   if (r == 0 && p->c_colsum)  // single-CTA kernels have no staged tile: one extra pass over C
     r = uc_colsum(p->c, UC_DTYPE_BF16, p->ldc, p->m, p->n, p->c_colsum, stream_);
   return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// uc_conv3x3: 3x3 / stride 1 / pad 1 convolution on NHWC bf16 maps as an IMPLICIT GEMM on the CTA-pair kernel above -- no
+// im2col buffer exists: the 9 taps are 9 shifted 4-D TMA boxes of the activation map accumulating into the same TMEM tile.
+// ------------------------------------------------------------------------------------------------
+namespace {
+// window width (power of two, lo..hi) of area `area` pixels that wastes the fewest pixels on an H x W map;
+// rows_per_tile = how many window heights one scheduling unit spans (2 for the CTA pair's 256-row tile)
+int best_window_log2(int H, int W, int area, int rows_mult, int lo, int hi) {
+  int best = lo;
+  long long best_cost = -1;
+  for (int l = lo; l <= hi; ++l) {
+    const int tw = 1 << l, th = (area / tw) * rows_mult;
+    if (area % tw) continue;
+    const long long cost = (long long)((W + tw - 1) / tw) * tw * ((H + th - 1) / th) * th;
+    if (best_cost < 0 || cost < best_cost || (cost == best_cost && tw <= 32)) { best_cost = cost; best = l; }
+  }
+  return best;
+}
+int act_map(CUtensorMap* tm, const void* base, int B, int H, int W, int C, int bw, int bh) {
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  uint32_t box[4] = {64u, (uint32_t)bw, (uint32_t)bh, 1u};
+  return uc::make_tensor_map(tm, base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+}  // namespace
+
+extern "C" int uc_conv3x3(const uc_conv3x3_params* p, uc_stream_t stream_) {
+  using namespace uc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  UC_REQUIRE(p, UC_ERR_BAD_SHAPE, "uc_conv3x3: null params");
+  UC_REQUIRE(p->mode >= 0 && p->mode <= 2, UC_ERR_BAD_SHAPE, "uc_conv3x3: mode %d", p->mode);
+  UC_REQUIRE(p->B > 0 && p->H > 0 && p->W > 0, UC_ERR_BAD_SHAPE, "uc_conv3x3: bad map size B=%d H=%d W=%d", p->B, p->H, p->W);
+  UC_REQUIRE(p->cin > 0 && p->cout > 0 && p->cin % 64 == 0 && p->cout % 64 == 0, UC_ERR_BAD_SHAPE,
+             "uc_conv3x3: channel counts must be multiples of 64 (cin=%d cout=%d)", p->cin, p->cout);
+  UC_REQUIRE(p->w || p->mode == 2, UC_ERR_BAD_SHAPE, "uc_conv3x3: null weight");
+  const int sms = sm_count();
+  const int slots = sms / 2;
+  GemmArgs g{};
+  g.cv_H = p->H; g.cv_W = p->W;
+  g.bias = nullptr; g.residual = nullptr; g.aux_out = nullptr; g.aux_in = nullptr; g.positions = nullptr; g.rope_table = nullptr;
+  g.colsum = nullptr; g.work = nullptr; g.rope_cols = 0;
+  CUtensorMap tmA, tmB, tmC, tmAux;
+  int r;
+  if (p->mode == 2) {
+    // dw[co, tap * cin + ci] += sum_pixels dy[pixel, co] * x[pixel + tap offset, ci]   (fp32, split over the pixels)
+    UC_REQUIRE(p->x && p->dy && p->dw, UC_ERR_BAD_SHAPE, "uc_conv3x3(wgrad): x, dy and dw are required");
+    const int l2 = best_window_log2(p->H, p->W, 64, 1, 1, 6);
+    const int tw = 1 << l2, th = 64 / tw;
+    g.cv_tw_log2 = l2; g.cv_tiles_x = (p->W + tw - 1) / tw; g.cv_tiles_y = (p->H + th - 1) / th; g.cv_cin = p->cin;
+    g.m = p->cout; g.n = 9 * p->cin;
+    g.num_kb = p->B * g.cv_tiles_x * g.cv_tiles_y;
+    g.k = g.num_kb * 64;
+    g.a_mn = 1; g.b_mn = 1;
+    g.num_m = (g.m + 255) / 256; g.num_n = (g.n + 255) / 256;
+    const long long tiles = (long long)g.num_m * g.num_n;
+    int split_k = 1;
+    {
+      const int max_split = g.num_kb / 4 < 1 ? 1 : g.num_kb / 4;
+      double best_u = -1.0;
+      for (int sk = 1; sk <= max_split && sk <= 64; ++sk) {
+        const long long items = tiles * sk;
+        const long long waves = (items + slots - 1) / slots;
+        const double u = double(items) / double(waves * slots) - 0.002 * sk;
+        if (u > best_u) { best_u = u; split_k = sk; }
+        if (items >= 4LL * slots) break;
+      }
+    }
+    int kb_per = (g.num_kb + split_k - 1) / split_k;
+    split_k = (g.num_kb + kb_per - 1) / kb_per;
+    g.split_k = split_k; g.kb_per_split = kb_per;
+    g.n_fastest = 0;
+    g.epilogue = UC_EPI_ATOMIC; g.c_f32 = 1; g.ldc = 9LL * p->cin; g.c = p->dw;
+    if ((r = act_map(&tmA, p->dy, p->B, p->H, p->W, p->cout, tw, th))) return r;
+    if ((r = act_map(&tmB, p->x, p->B, p->H, p->W, p->cin, tw, th))) return r;
+    uint64_t dims[2] = {(uint64_t)g.n, (uint64_t)g.m};
+    uint64_t strides[1] = {(uint64_t)g.ldc * 4};
+    uint32_t box[2] = {32u, 32u};
+    if ((r = make_tensor_map(&tmC, p->dw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return r;
+    tmAux = tmC;
+    const long long total = tiles * split_k;
+    const int clusters = (int)(total < slots ? total : slots);
+    return launch2_inst<UC_EPI_ATOMIC, true, 256, 2>(tmA, tmB, tmC, tmAux, g, 2 * clusters, stream);
+  }
+  // fwd: y = conv(x, w) [+ bias] [relu | + residual]            A = x  (cin),  n = cout, B = w  K-major [cout, 9 cin]
+  // dgrad: dx = conv(dy, flipped w^T) [* (relu_out > 0)]        A = dy (cout), n = cin,  B = w  MN-major view [cout, 9 cin]
+  const bool fwd = p->mode == 0;
+  const void* a_ptr = fwd ? p->x : p->dy;
+  void* c_ptr = fwd ? p->y : p->dx;
+  UC_REQUIRE(a_ptr && c_ptr, UC_ERR_BAD_SHAPE, "uc_conv3x3: null activation pointer");
+  const int ca = fwd ? p->cin : p->cout;  // channels of the A map
+  const int n = fwd ? p->cout : p->cin;
+  const int l2 = best_window_log2(p->H, p->W, 128, 2, 3, 7);
+  const int tw = 1 << l2, th = 128 / tw;
+  g.cv_tw_log2 = l2; g.cv_tiles_x = (p->W + tw - 1) / tw; g.cv_tiles_y = (p->H + 2 * th - 1) / (2 * th);
+  g.cv_kb_per_tap = ca / 64;
+  g.cv_b_tap_stride = fwd ? 0 : p->cin;
+  g.m = p->B * p->H * p->W; g.n = n; g.k = 9 * ca;
+  g.a_mn = 0; g.b_mn = fwd ? 0 : 1;
+  const int bn = (n % 256 == 0 || n > 384) ? 256 : 128;
+  g.num_m = p->B * g.cv_tiles_x * g.cv_tiles_y;
+  g.num_n = (n + bn - 1) / bn;
+  g.num_kb = 9 * g.cv_kb_per_tap; g.split_k = 1; g.kb_per_split = g.num_kb;
+  g.n_fastest = 1;
+  int epi = 0;
+  if (fwd) {
+    UC_REQUIRE(!(p->relu && p->residual), UC_ERR_UNSUPPORTED, "uc_conv3x3: fused ReLU and residual are mutually exclusive");
+    if (p->bias) { epi |= UC_EPI_BIAS; g.bias = p->bias; }
+    if (p->relu) epi |= UC_EPI_RELU;
+    if (p->residual) { epi |= UC_EPI_RESIDUAL; g.residual = static_cast<const __nv_bfloat16*>(p->residual); }
+  } else if (p->relu_out) {
+    epi |= UC_EPI_RELU_BWD; g.aux_in = static_cast<const __nv_bfloat16*>(p->relu_out);
+  }
+  g.epilogue = epi; g.c_f32 = 0; g.ldc = n; g.c = c_ptr;
+  if ((r = act_map(&tmA, a_ptr, p->B, p->H, p->W, ca, tw, th))) return r;
+  {
+    uint64_t dims[2], strides[1] = {(uint64_t)9 * p->cin * 2};
+    uint32_t box[2];
+    if (fwd) { dims[0] = 9ull * p->cin; dims[1] = p->cout; box[0] = BK; box[1] = bn / 2; }
+    else { dims[0] = 9ull * p->cin; dims[1] = p->cout; box[0] = 64; box[1] = BK; }
+    if ((r = make_tensor_map(&tmB, p->w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return r;
+  }
+  // C / aux tiles: one epilogue warp's 32 rows = 32 pixels of a row (tw >= 32) or 32 / tw rows of tw pixels
+  const int bw = tw >= 32 ? 32 : tw, bh = 32 / bw;
+  if ((r = act_map(&tmC, c_ptr, p->B, p->H, p->W, n, bw, bh))) return r;
+  tmAux = tmC;
+  const void* aux_ptr = fwd ? p->residual : p->relu_out;
+  if (aux_ptr && (r = act_map(&tmAux, aux_ptr, p->B, p->H, p->W, n, bw, bh))) return r;
+  const long long total = (long long)g.num_m * g.num_n;
+  const int clusters = (int)(total < slots ? total : slots);
+  constexpr int kConvMask = UC_EPI_BIAS | UC_EPI_RESIDUAL | UC_EPI_RELU | UC_EPI_RELU_BWD;
+  if (bn == 256) return launch2_inst<kConvMask, false, 256, 1>(tmA, tmB, tmC, tmAux, g, 2 * clusters, stream);
+  return launch2_inst<kConvMask, false, 128, 1>(tmA, tmB, tmC, tmAux, g, 2 * clusters, stream);
 }

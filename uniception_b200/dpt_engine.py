@@ -12,6 +12,8 @@ next multiple of 64 in the bf16 operand copies, so the GEMM tile constraints hol
 """
 from __future__ import annotations
 
+import os
+
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -168,9 +170,33 @@ def conv1x1(tape: Tape, x, cw: ConvW, out_dtype=torch.bfloat16, need_dx=True):
     return y
 
 
+IMPLICIT_CONV = os.environ.get("UC_CONV_IM2COL", "0") != "1"  # UC_CONV_IM2COL=1: the materialised-column path (A/B, debugging)
+
+
 def conv3x3(tape: Tape, x, B, H, W, cw: ConvW, relu=False, residual=None):
-    """3x3, pad 1, stride cw.stride.  Optional fused ReLU or fused `+ residual` (one of the two)."""
+    """3x3, pad 1, stride cw.stride.  Optional fused ReLU or fused `+ residual` (one of the two).
+    Stride 1: implicit GEMM (uc_conv3x3: shifted TMA boxes, no column buffer) forward, dgrad and wgrad.
+    Stride 2 (one small layer of the head, dpt.py:118-126): uc_im2col3x3 -> uc_gemm."""
     st = cw.stride
+    if st == 1 and IMPLICIT_CONV:
+        y = ops.conv3x3_fwd(x, cw.w16, B, H, W, bias=cw.b32, relu=relu, residual=residual)
+
+        def bwd_implicit():
+            g = tape.pop_grad(y)
+            if g is None:
+                return
+            if residual is not None:
+                tape.add_grad(residual, g)
+            if relu:
+                g = ops.elementwise(2, g, y)  # g * (y > 0)
+            gw, gb = cw.grad_buffers()
+            ops.conv3x3_wgrad_(x, g, gw, B, H, W)
+            if cw.b32 is not None:
+                ops.colsum_(g, gb)
+            tape.add_grad(x, ops.conv3x3_dgrad(g, cw.w16, B, H, W))
+
+        tape.record(bwd_implicit)
+        return y
     cols = ops.im2col3x3(x, B, H, W, st)
     y = _gemm_fwd(cols, cw, relu=relu, residual=residual)
     del cols  # re-gathered in backward: trades one memory-bound pass for not holding 9x the activation

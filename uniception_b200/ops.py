@@ -317,6 +317,47 @@ def conv_out_hw(H: int, W: int, stride: int):
     return (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
 
 
+def _p(t):
+    return _ptr(t) if t is not None else None
+
+
+def conv3x3_fwd(x: torch.Tensor, w16: torch.Tensor, B: int, H: int, W: int, bias=None, relu: bool = False, residual=None) -> torch.Tensor:
+    """Implicit-GEMM 3x3 / stride 1 / pad 1 convolution (uc_conv3x3 mode 0).  x bf16 [B*H*W, cin], w16 bf16 [cout, 9*cin]
+    (tap-major), optional fp32 bias, fused ReLU or `+ residual` (bf16 [B*H*W, cout]).  Returns bf16 [B*H*W, cout]."""
+    _cuda(x, w16)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.shape[0] == B * H * W and w16.is_contiguous()
+    cin, cout = x.shape[1], w16.shape[0]
+    assert w16.shape[1] == 9 * cin
+    y = torch.empty(B * H * W, cout, dtype=torch.bfloat16, device=x.device)
+    p = L.Conv3x3Params(0, B, H, W, cin, cout, _ptr(x), _ptr(w16), _ptr(y), None, None, None, _p(bias), _p(residual), None, int(relu))
+    L.check(L.lib.uc_conv3x3(C.byref(p), _stream()))
+    return y
+
+
+def conv3x3_dgrad(dy: torch.Tensor, w16: torch.Tensor, B: int, H: int, W: int, relu_out=None) -> torch.Tensor:
+    """dx of the same convolution (uc_conv3x3 mode 1); relu_out: dx *= (relu_out > 0) (the conv's input was a ReLU output)."""
+    _cuda(dy, w16)
+    assert dy.dtype == torch.bfloat16 and dy.is_contiguous() and dy.shape[0] == B * H * W
+    cout = w16.shape[0]
+    cin = w16.shape[1] // 9
+    assert dy.shape[1] == cout
+    dx = torch.empty(B * H * W, cin, dtype=torch.bfloat16, device=dy.device)
+    p = L.Conv3x3Params(1, B, H, W, cin, cout, None, _ptr(w16), None, _ptr(dy), _ptr(dx), None, None, None, _p(relu_out), 0)
+    L.check(L.lib.uc_conv3x3(C.byref(p), _stream()))
+    return dx
+
+
+def conv3x3_wgrad_(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, B: int, H: int, W: int) -> None:
+    """dw (fp32 [cout, 9*cin]) += the weight gradient of the same convolution (uc_conv3x3 mode 2)."""
+    _cuda(x, dy, dw)
+    assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and dw.dtype == torch.float32
+    assert x.is_contiguous() and dy.is_contiguous() and dw.is_contiguous()
+    cin, cout = x.shape[1], dy.shape[1]
+    assert tuple(dw.shape) == (cout, 9 * cin)
+    p = L.Conv3x3Params(2, B, H, W, cin, cout, _ptr(x), None, None, _ptr(dy), None, _ptr(dw), None, None, None, 0)
+    L.check(L.lib.uc_conv3x3(C.byref(p), _stream()))
+
+
 def im2col3x3(x: torch.Tensor, B: int, H: int, W: int, stride: int = 1) -> torch.Tensor:
     """x [B*H*W, C] bf16 -> cols [B*Ho*Wo, 9*C] (tap-major, pad 1)."""
     _cuda(x)
