@@ -495,6 +495,297 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 // ================================================================================================================
+// forward, ping-pong: ONE CTA per SM works on TWO 128-row query tiles of the same (batch, head) at once
+// ================================================================================================================
+// attn_fwd3_kernel leaves the exp pipe ~40 % idle (profiles/r02b_attention_design_log.txt): its softmax warps read every score
+// tile twice from TMEM (row maximum, then exponentials; four dependent TMEM round trips per tile), the next QK^T cannot start
+// before the second read, and its two CTAs per SM fetch K and V separately.  Here:
+//   * a softmax thread loads its 64 scores of a tile into registers ONCE and releases the S buffer at that point, so
+//     QK^T(j+1) of its group runs underneath the whole softmax of tile j;
+//   * one CTA per SM hosts two such groups (A and B: 8 warps each, two threads per query row) on two query tiles of the same
+//     (batch, head); K / V tiles are fetched once and serve both; one MMA warp issues for both groups in a fixed order
+//     QK_A(j+1) QK_B(j+1) PV_A(j) PV_B(j), each MMA gated by the barrier of the group it serves.
+// TMEM (all 512 columns): S_A | S_B (128 fp32 each) | P_A | P_B (128 bf16 = 64 columns each) | O_A | O_B (64 each).
+constexpr int F4_THREADS = 64 + 16 * 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 group A, 10..17 group B
+constexpr int F4_KST = 3;                 // K and V stages
+constexpr uint32_t F4_OFF_K = 4 * F3_TILE, F4_OFF_V = F4_OFF_K + F4_KST * F3_TILE, F4_OFF_X = F4_OFF_V + F4_KST * F3_TILE,
+                   F4_OFF_BAR = F4_OFF_X + 8192;
+constexpr uint32_t F4_SMEM = F4_OFF_BAR + 512 + 1024;
+constexpr uint32_t F4_TM_COLS = 512;
+
+template <int NPOLY>
+__global__ void __launch_bounds__(F4_THREADS, 1)
+attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const FwdArgs a, int* work) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  auto sQ = [&](int st, int grp) { return smem_base + (2 * st + grp) * F3_TILE; };
+  auto sK = [&](int st) { return smem_base + F4_OFF_K + st * F3_TILE; };
+  auto sV = [&](int st) { return smem_base + F4_OFF_V + st * F3_TILE; };
+  float* xch = reinterpret_cast<float*>(smem_gen + F4_OFF_X);  // per group 768 floats: maxima [parity 2][half 2][128], sums [half 2][128]
+  const uint32_t bar = smem_base + F4_OFF_BAR;
+  auto q_full = [&](int st) { return bar + 8u * st; };
+  auto q_empty = [&](int st) { return bar + 8u * (2 + st); };
+  auto k_full = [&](int st) { return bar + 8u * (4 + st); };
+  auto k_empty = [&](int st) { return bar + 8u * (8 + st); };
+  auto v_full = [&](int st) { return bar + 8u * (12 + st); };
+  auto v_empty = [&](int st) { return bar + 8u * (16 + st); };
+  auto s_full = [&](int grp) { return bar + 8u * (20 + grp); };
+  auto p_ready = [&](int grp) { return bar + 8u * (22 + grp); };
+  auto o_done = [&](int grp) { return bar + 8u * (24 + grp); };
+  auto s_free = [&](int grp) { return bar + 8u * (26 + grp); };
+  const uint32_t tmem_slot = bar + 8u * 28;
+  const ItemQueue queue{bar + 8u * 30, reinterpret_cast<volatile int*>(smem_gen + F4_OFF_BAR + 8 * 34), work};
+  auto tm_s = [](int grp) { return uint32_t(128 * grp); };
+  auto tm_p = [](int grp) { return uint32_t(256 + 64 * grp); };
+  auto tm_o = [](int grp) { return uint32_t(384 + 64 * grp); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = (a.Nk + 127) / 128;    // key tiles per item
+  const int nq = (a.Nq + 127) / 128;   // query tiles per (batch, head)
+  const int nq2 = (nq + 1) / 2;        // items (pairs of query tiles) per (batch, head)
+  const int n_items = nq2 * a.B * a.H;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int s = 0; s < 2; ++s) { mbar_init(q_full(s), 1); mbar_init(q_empty(s), 1); }
+    for (int s = 0; s < F4_KST; ++s) {
+      mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1);
+      mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
+    }
+    for (int grp = 0; grp < 2; ++grp) {
+      mbar_init(s_full(grp), 1);
+      mbar_init(p_ready(grp), 8);
+      mbar_init(o_done(grp), 1);
+      mbar_init(s_free(grp), 8);
+    }
+    queue.init();
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, F4_TM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_launch_dependents();  // after the TMEM allocation (common.cuh: PDL rules)
+  pdl_wait();
+
+  if (warp == 0) {
+    // ---- TMA producer ----
+    int g = 0;  // tile counter of this CTA
+    for (int n = 0;; ++n) {
+      const int it = queue.produce(n, lane);
+      if (it >= n_items) {
+        queue.retire(lane);
+        break;
+      }
+      const int bh = it / nq2, qt2 = it % nq2;
+      const int b = bh / a.H, h = bh % a.H;
+      const int qa = 2 * qt2, qb = min(2 * qt2 + 1, nq - 1);  // odd tile count: group B repeats the last tile and stores nothing
+      mbar_wait(q_empty(n & 1), ((n >> 1) & 1) ^ 1u);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full(n & 1), 2 * F3_TILE);
+        tma_load_3d(sQ(n & 1, 0), &tmQ, q_full(n & 1), h * 64, qa * 128, b);
+        tma_load_3d(sQ(n & 1, 1), &tmQ, q_full(n & 1), h * 64, qb * 128, b);
+      }
+      __syncwarp();
+      for (int j = 0; j < T; ++j, ++g) {
+        const int st = g % F4_KST;
+        const uint32_t ph = ((g / F4_KST) & 1) ^ 1u;
+        mbar_wait(k_empty(st), ph);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(k_full(st), F3_TILE);
+          tma_load_3d(sK(st), &tmK, k_full(st), h * 64, j * 128, b);
+        }
+        __syncwarp();
+        mbar_wait(v_empty(st), ph);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(v_full(st), F3_TILE);
+          tma_load_3d(sV(st), &tmV, v_full(st), h * 64, j * 128, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: the issue order below is the ping-pong schedule ----
+    const uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
+    const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
+    auto issue_qk = [&](int grp, int n, int j, int g) {  // S_grp = Q_grp(item n) K(tile g)^T
+      const int st = g % F4_KST;
+      if (grp == 0) {  // group B's MMAs follow group A's in program order: same operands, already waited for
+        if (j == 0) mbar_wait(q_full(n & 1), (n >> 1) & 1);
+        mbar_wait(k_full(st), (g / F4_KST) & 1);
+      }
+      tc_fence_after();
+      const uint64_t qd = umma_desc_kmajor(sQ(n & 1, grp)), kd = umma_desc_kmajor(sK(st));
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tmem_base + tm_s(grp), qd + uint64_t(k * 2), kd + uint64_t(k * 2), idesc_qk, k > 0);
+        umma_commit(s_full(grp));
+        if (grp == 1) {
+          umma_commit(k_empty(st));
+          if (j == T - 1) umma_commit(q_empty(n & 1));
+        }
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int grp, int j, int g) {  // O_grp += P_grp(g) V(g)
+      const int st = g % F4_KST;
+      mbar_wait(p_ready(grp), g & 1);
+      if (grp == 0) mbar_wait(v_full(st), (g / F4_KST) & 1);
+      tc_fence_after();
+      const uint64_t vd = umma_desc_mnmajor(sV(st), 8192);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ts(tmem_base + tm_o(grp), tmem_base + tm_p(grp) + k * 8, vd + uint64_t(k * 128), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        if (grp == 1) umma_commit(v_empty(st));
+        umma_commit(o_done(grp));
+      }
+      __syncwarp();
+    };
+    int g = 0;
+    if (queue.consume(0) < n_items) {
+      issue_qk(0, 0, 0, 0);
+      issue_qk(1, 0, 0, 0);
+      for (int n = 0;; ++n) {
+        bool more = true;
+        for (int j = 0; j < T; ++j, ++g) {
+          const bool last = j == T - 1;
+          if (last) more = queue.consume(n + 1) < n_items;
+          if (!last || more) {  // look-ahead: QK^T of the next tile as soon as the group has its scores in registers
+#pragma unroll
+            for (int grp = 0; grp < 2; ++grp) {
+              mbar_wait(s_free(grp), g & 1);
+              if (!last) issue_qk(grp, n, j + 1, g + 1);
+              else issue_qk(grp, n + 1, 0, g + 1);
+            }
+          }
+          issue_pv(0, j, g);
+          issue_pv(1, j, g);
+        }
+        if (!more) break;
+      }
+    }
+  } else {
+    // ---- softmax: group = query tile, two threads per query row (half = 64-column half of the key tile) ----
+    const int sw = warp - 2;
+    const int grp = sw >> 3;
+    const int half = (sw >> 2) & 1;
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int r = quad * 32 + lane;  // row inside the tile
+    const int bar_id = 1 + grp * 4 + quad;  // named barrier of the 64 threads that share 32 rows
+    const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr + tm_s(grp) + 64 * half, tP = tmem_base + lane_addr + tm_p(grp) + 32 * half,
+                   tO = tmem_base + lane_addr + tm_o(grp) + 32 * half;
+    float* xmax = xch + grp * 768;  // [2 parity][2 half][128] half-row maxima
+    float* xsum = xmax + 512;       // [2 half][128] half-row sums
+    int g = 0;
+    for (int n = 0;; ++n) {
+      const int it = queue.consume(n);
+      if (it >= n_items) break;
+      const int bh = it / nq2, qt = 2 * (it % nq2) + grp;
+      const int b = bh / a.H, h = bh % a.H;
+      float m_run = -INFINITY, l0 = 0.f, l1 = 0.f;  // l0 + l1: this thread's half of the row sum
+      for (int j = 0; j < T; ++j, ++g) {
+        mbar_wait(s_full(grp), g & 1);
+        tc_fence_after();
+        const int valid = a.Nk - j * 128 - 64 * half;  // score columns of this half that are real keys (< 64: ragged tail)
+        uint32_t s0[32], s1[32];
+        tmem_ld32(tS, s0);
+        tmem_ld32(tS + 32, s1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free(grp));  // the scores are in registers: QK^T(g+1) may overwrite S
+        if (valid < 64) {
+          mask32(s0, valid);
+          mask32(s1, valid - 32);
+        }
+        float m_tile = fmaxf(max32(s0), max32(s1));
+        xmax[((g & 1) * 2 + half) * 128 + r] = m_tile;
+        bar_sync_named(bar_id, 64);
+        m_tile = fmaxf(m_tile, xmax[((g & 1) * 2 + (half ^ 1)) * 128 + r]);
+        // lazy rescaling (both threads of a row see the same numbers and decide alike)
+        const bool grow = (m_tile - m_run) * a.scale_log2 > kLazyThreshold;  // true on an item's first tile (m_run = -inf)
+        const float m_new = grow ? m_tile : m_run;
+        const float alpha = grow ? ex2((m_run - m_new) * a.scale_log2) : 1.0f;
+        const float neg_m = -m_new * a.scale_log2;
+        if (grow) {
+          l0 *= alpha;
+          l1 *= alpha;
+        }
+        m_run = m_new;
+        uint32_t pk[16];
+        exp32<NPOLY>(s0, a.scale_log2, neg_m, pk, l0, l1);
+        if (g > 0) {  // PV(g-1) of this group has retired: its P region may be overwritten and O is stable
+          mbar_wait(o_done(grp), (g - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st16(tP, pk);
+        exp32<NPOLY>(s1, a.scale_log2, neg_m, pk, l0, l1);
+        tmem_st16(tP + 16, pk);
+        if (j > 0 && __any_sync(0xffffffffu, grow)) {  // rescale this thread's 32 output columns
+          uint32_t o[32];
+          tmem_ld32(tO, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(tO, o);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready(grp));
+      }
+      // ---- item epilogue: O / l -> global (each thread its 32 columns), LSE ----
+      const float l_half = l0 + l1;
+      xsum[half * 128 + r] = l_half;
+      mbar_wait(o_done(grp), (g - 1) & 1);
+      tc_fence_after();
+      bar_sync_named(bar_id, 64);
+      const float l_row = l_half + xsum[(half ^ 1) * 128 + r];
+      const float inv_l = 1.0f / l_row;
+      const int row = qt * 128 + r;
+      const bool row_ok = row < a.Nq;
+      {
+        uint32_t o[32];
+        tmem_ld32(tO, o);
+        tmem_ld_wait();
+        if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(a.o + ((long long)b * a.Nq + row) * a.ldo + h * 64 + 32 * half);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 t;
+            t.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
+            t.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
+            t.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
+            t.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
+            dst[i] = t;
+          }
+        }
+      }
+      if (half == 0 && row_ok && a.lse) a.lse[((long long)b * a.H + h) * a.Nq + row] = m_run * a.scale + logf(l_row);
+      bar_sync_named(bar_id, 64);  // the partner has read this item's row sum before the next item's is written
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, F4_TM_COLS);
+  }
+}
+
+// ================================================================================================================
 // backward: statistics
 // ================================================================================================================
 // stats[bh][tile][0][i] = -lse[q] * log2(e), stats[bh][tile][1][i] = -sum_d dO[q,d] * O[q,d], q = tile*64 + i; rows >= Nq hold
@@ -1001,8 +1292,13 @@ extern "C" int uc_attn_fwd(const uc_attn_fwd_params* p, uc_stream_t stream_) {
   UC_REQUIRE(((uintptr_t)p->q % 16 == 0) && ((uintptr_t)p->k % 16 == 0) && ((uintptr_t)p->v % 16 == 0) &&
                  ((uintptr_t)p->o % 16 == 0),
              UC_ERR_BAD_SHAPE, "uc_attn_fwd: pointers must be 16-byte aligned");
-  static const int impl = env_int("UC_ATTN_FWD", 3);  // 1: first-generation kernel (A/B baseline), 3: persistent kernel of this file
-  if (impl == 1) return attn_fwd_v1(p, stream);
+  // 1: first-generation kernel, 3: persistent kernel with two independent CTAs per SM (both kept as A/B baselines),
+  // 4 (default): ping-pong kernel, one CTA per SM working on two query tiles
+  static const int impl_env = env_int("UC_ATTN_FWD", 0);
+  if (impl_env == 1) return attn_fwd_v1(p, stream);
+  // default: the ping-pong kernel when the query tiles pair up exactly, else (odd tile count, e.g. 1369 tokens = 11 tiles: its
+  // group B would repeat a tile for nothing) the two-CTAs-per-SM kernel.  Measured: profiles/r02e_attention_fwd4.log
+  const int impl = impl_env ? impl_env : ((((p->Nq + 127) / 128) & 1) ? 3 : 4);
   CUtensorMap tmQ, tmK, tmV;
   int r;
   if ((r = make_head_map(&tmQ, p->q, p->H, p->Nq, p->B, p->ldq, 128))) return r;
@@ -1024,9 +1320,26 @@ extern "C" int uc_attn_fwd(const uc_attn_fwd_params* p, uc_stream_t stream_) {
   a.scale_log2 = p->scale * kLog2e;
   const long long items = (long long)((p->Nq + 127) / 128) * p->B * p->H;
   static const int npoly = env_int("UC_ATTN_POLY", 4);  // column pairs (of 16 per 32-column chunk) exponentiated on the FMA pipe
-  const dim3 grid = persistent_grid(items);
   int* work = work_slot();
   UC_REQUIRE(work, UC_ERR_CUDA, "uc_attn_fwd: work counters unavailable");
+  if (impl == 4) {
+    static bool configured4 = false;
+    if (!configured4) {
+      if ((r = set_smem(attn_fwd4_kernel<0>, F4_SMEM, "uc_attn_fwd"))) return r;
+      if ((r = set_smem(attn_fwd4_kernel<4>, F4_SMEM, "uc_attn_fwd"))) return r;
+      if ((r = set_smem(attn_fwd4_kernel<8>, F4_SMEM, "uc_attn_fwd"))) return r;
+      configured4 = true;
+    }
+    const long long items2 = (long long)(((p->Nq + 127) / 128 + 1) / 2) * p->B * p->H;
+    const long long sms = sm_count();
+    const dim3 grid4((unsigned)(items2 < sms ? items2 : sms));
+    cudaError_t le4 = npoly >= 8   ? launch_pdl(attn_fwd4_kernel<8>, grid4, dim3(F4_THREADS), F4_SMEM, stream, tmQ, tmK, tmV, a, work)
+                      : npoly >= 4 ? launch_pdl(attn_fwd4_kernel<4>, grid4, dim3(F4_THREADS), F4_SMEM, stream, tmQ, tmK, tmV, a, work)
+                                   : launch_pdl(attn_fwd4_kernel<0>, grid4, dim3(F4_THREADS), F4_SMEM, stream, tmQ, tmK, tmV, a, work);
+    UC_REQUIRE(le4 == cudaSuccess, UC_ERR_CUDA, "uc_attn_fwd: launch failed: %s", cudaGetErrorString(le4));
+    return check_launch("uc_attn_fwd");
+  }
+  const dim3 grid = persistent_grid(items);
   cudaError_t le = npoly >= 8   ? launch_pdl(attn_fwd3_kernel<8>, grid, dim3(A3_THREADS), F3_SMEM, stream, tmQ, tmK, tmV, a, work)
                    : npoly >= 4 ? launch_pdl(attn_fwd3_kernel<4>, grid, dim3(A3_THREADS), F3_SMEM, stream, tmQ, tmK, tmV, a, work)
                                 : launch_pdl(attn_fwd3_kernel<0>, grid, dim3(A3_THREADS), F3_SMEM, stream, tmQ, tmK, tmV, a, work);

@@ -31,6 +31,9 @@ class Tape:
         self.fns: List[Callable[[], None]] = []
         self.grads: Dict[int, torch.Tensor] = {}
         self.keep: List[torch.Tensor] = []
+        # ids of fused-ReLU conv outputs whose single consumer applies the ReLU mask in its own dgrad epilogue
+        # (UC_EPI_RELU_BWD): their producers receive the gradient already masked
+        self.premasked: set = set()
 
     def add_grad(self, t: torch.Tensor, g: torch.Tensor) -> None:
         k = id(t)
@@ -140,8 +143,8 @@ def _gemm_fwd(x, cw: ConvW, out_dtype=torch.bfloat16, relu=False, residual=None)
     return out
 
 
-def _gemm_bwd(tape: Tape, dy, x_in, cw: ConvW, need_dx=True):
-    """dy [rows, n_out] bf16.  Accumulates weight/bias grads; returns d x_in."""
+def _gemm_bwd(tape: Tape, dy, x_in, cw: ConvW, need_dx=True, relu_mask=None):
+    """dy [rows, n_out] bf16.  Accumulates weight/bias grads; returns d x_in (times (relu_mask > 0) when given)."""
     gw, gb = cw.grad_buffers()
     ops.gemm(dy, x_in, gw, a_layout=1, b_layout=1, atomic=True)
     if cw.b32 is not None:
@@ -149,12 +152,19 @@ def _gemm_bwd(tape: Tape, dy, x_in, cw: ConvW, need_dx=True):
     if not need_dx:
         return None
     dx = torch.empty(dy.shape[0], cw.w16.shape[1], dtype=torch.bfloat16, device=dy.device)
-    ops.gemm(dy, cw.w16, dx, b_layout=1)
+    if relu_mask is not None:
+        ops.gemm(dy, cw.w16, dx, b_layout=1, relu_bwd=True, aux_in=relu_mask)
+    else:
+        ops.gemm(dy, cw.w16, dx, b_layout=1)
     return dx
 
 
-def conv1x1(tape: Tape, x, cw: ConvW, out_dtype=torch.bfloat16, need_dx=True):
+def conv1x1(tape: Tape, x, cw: ConvW, out_dtype=torch.bfloat16, need_dx=True, x_premask=False):
+    """x_premask: x is the output of a fused-ReLU conv and this is its only consumer -- the ReLU mask is applied by this
+    conv's dgrad epilogue instead of a separate pass in the producer's backward."""
     y = _gemm_fwd(x, cw, out_dtype)
+    if x_premask:
+        tape.premasked.add(id(x))
 
     def bwd():
         g = tape.pop_grad(y)
@@ -162,7 +172,7 @@ def conv1x1(tape: Tape, x, cw: ConvW, out_dtype=torch.bfloat16, need_dx=True):
             return
         if g.dtype != torch.bfloat16:
             g = g.to(torch.bfloat16)
-        dx = _gemm_bwd(tape, g.contiguous(), x, cw, need_dx)
+        dx = _gemm_bwd(tape, g.contiguous(), x, cw, need_dx, relu_mask=x if x_premask else None)
         if dx is not None:
             tape.add_grad(x, dx)
 
@@ -173,13 +183,18 @@ def conv1x1(tape: Tape, x, cw: ConvW, out_dtype=torch.bfloat16, need_dx=True):
 IMPLICIT_CONV = os.environ.get("UC_CONV_IM2COL", "0") != "1"  # UC_CONV_IM2COL=1: the materialised-column path (A/B, debugging)
 
 
-def conv3x3(tape: Tape, x, B, H, W, cw: ConvW, relu=False, residual=None):
+def conv3x3(tape: Tape, x, B, H, W, cw: ConvW, relu=False, residual=None, x_relu_src=None, x_premask=False):
     """3x3, pad 1, stride cw.stride.  Optional fused ReLU or fused `+ residual` (one of the two).
     Stride 1: implicit GEMM (uc_conv3x3: shifted TMA boxes, no column buffer) forward, dgrad and wgrad.
-    Stride 2 (one small layer of the head, dpt.py:118-126): uc_im2col3x3 -> uc_gemm."""
+    Stride 2 (one small layer of the head, dpt.py:118-126): uc_im2col3x3 -> uc_gemm.
+    ReLU backward rides the dgrad epilogue (UC_EPI_RELU_BWD) when x is a ReLU output with this conv as its ONLY consumer:
+    x_relu_src = z with x = relu(z) from `relu()`: the masked dx is delivered to z directly; x_premask: x came out of a conv
+    with a fused ReLU, which then receives its gradient already masked."""
     st = cw.stride
     if st == 1 and IMPLICIT_CONV:
         y = ops.conv3x3_fwd(x, cw.w16, B, H, W, bias=cw.b32, relu=relu, residual=residual)
+        if x_premask:
+            tape.premasked.add(id(x))
 
         def bwd_implicit():
             g = tape.pop_grad(y)
@@ -187,13 +202,18 @@ def conv3x3(tape: Tape, x, B, H, W, cw: ConvW, relu=False, residual=None):
                 return
             if residual is not None:
                 tape.add_grad(residual, g)
-            if relu:
+            if relu and id(y) not in tape.premasked:
                 g = ops.elementwise(2, g, y)  # g * (y > 0)
             gw, gb = cw.grad_buffers()
             ops.conv3x3_wgrad_(x, g, gw, B, H, W)
             if cw.b32 is not None:
                 ops.colsum_(g, gb)
-            tape.add_grad(x, ops.conv3x3_dgrad(g, cw.w16, B, H, W))
+            if x_relu_src is not None:
+                tape.add_grad(x_relu_src, ops.conv3x3_dgrad(g, cw.w16, B, H, W, relu_out=x))
+            elif x_premask:
+                tape.add_grad(x, ops.conv3x3_dgrad(g, cw.w16, B, H, W, relu_out=x))
+            else:
+                tape.add_grad(x, ops.conv3x3_dgrad(g, cw.w16, B, H, W))
 
         tape.record(bwd_implicit)
         return y
@@ -361,8 +381,9 @@ class DPTWeights:
 def _rcu(tape, z, B, H, W, unit, extra_skip=None):
     """z + conv2(relu(conv1(relu(z)))) [+ extra_skip]; ReLU of conv1 fused in its epilogue, skip fused in conv2's."""
     skip = z if extra_skip is None else add(tape, z, extra_skip)
-    t = conv3x3(tape, relu(tape, z), B, H, W, unit[0], relu=True)
-    return conv3x3(tape, t, B, H, W, unit[1], residual=skip)
+    fused = IMPLICIT_CONV and unit[0].stride == 1 and unit[1].stride == 1
+    t = conv3x3(tape, relu(tape, z), B, H, W, unit[0], relu=True, x_relu_src=z if fused else None)
+    return conv3x3(tape, t, B, H, W, unit[1], residual=skip, x_premask=fused)
 
 
 def _fusion(tape, a, b, B, H, W, d):
@@ -406,7 +427,7 @@ def dpt_regressor_forward(tape: Tape, Wt: DPTRegressorWeights, p1: torch.Tensor,
     c1 = conv3x3(tape, p1, B, Hf, Wf, Wt.r1)
     u = resize(tape, c1, B, Hf, Wf, out_hw[0], out_hw[1])
     c2 = conv3x3(tape, u, B, out_hw[0], out_hw[1], Wt.r2, relu=True)
-    return conv1x1(tape, c2, Wt.r3, out_dtype=torch.float32)
+    return conv1x1(tape, c2, Wt.r3, out_dtype=torch.float32, x_premask=IMPLICIT_CONV)
 
 
 def dpt_forward(tape: Tape, Wt: DPTWeights, feats: List[torch.Tensor], B: int, h: int, w: int, out_hw: Tuple[int, int]):

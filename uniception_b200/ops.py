@@ -321,6 +321,19 @@ def _p(t):
     return _ptr(t) if t is not None else None
 
 
+def _conv_call(p, B, H, W, cin, cout, mode):
+    """uc_conv3x3, timed with CUDA events when bench.py's per-launch GEMM profile is on (the convolution runs on the same
+    tcgen05 kernel as uc_gemm; algorithmic FLOPs = 2 * pixels * 9 * cin * cout)."""
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L.lib.uc_conv3x3(C.byref(p), _stream()))
+        e1.record()
+        PROFILE.append((e0, e1, 2.0 * B * H * W * 9 * cin * cout, ("conv3x3", mode, B * H * W, cin, cout, 0)))
+        return
+    L.check(L.lib.uc_conv3x3(C.byref(p), _stream()))
+
+
 def conv3x3_fwd(x: torch.Tensor, w16: torch.Tensor, B: int, H: int, W: int, bias=None, relu: bool = False, residual=None) -> torch.Tensor:
     """Implicit-GEMM 3x3 / stride 1 / pad 1 convolution (uc_conv3x3 mode 0).  x bf16 [B*H*W, cin], w16 bf16 [cout, 9*cin]
     (tap-major), optional fp32 bias, fused ReLU or `+ residual` (bf16 [B*H*W, cout]).  Returns bf16 [B*H*W, cout]."""
@@ -330,7 +343,7 @@ def conv3x3_fwd(x: torch.Tensor, w16: torch.Tensor, B: int, H: int, W: int, bias
     assert w16.shape[1] == 9 * cin
     y = torch.empty(B * H * W, cout, dtype=torch.bfloat16, device=x.device)
     p = L.Conv3x3Params(0, B, H, W, cin, cout, _ptr(x), _ptr(w16), _ptr(y), None, None, None, _p(bias), _p(residual), None, int(relu))
-    L.check(L.lib.uc_conv3x3(C.byref(p), _stream()))
+    _conv_call(p, B, H, W, cin, cout, 0)
     return y
 
 
@@ -343,7 +356,7 @@ def conv3x3_dgrad(dy: torch.Tensor, w16: torch.Tensor, B: int, H: int, W: int, r
     assert dy.shape[1] == cout
     dx = torch.empty(B * H * W, cin, dtype=torch.bfloat16, device=dy.device)
     p = L.Conv3x3Params(1, B, H, W, cin, cout, None, _ptr(w16), None, _ptr(dy), _ptr(dx), None, None, None, _p(relu_out), 0)
-    L.check(L.lib.uc_conv3x3(C.byref(p), _stream()))
+    _conv_call(p, B, H, W, cin, cout, 1)
     return dx
 
 
@@ -355,7 +368,7 @@ def conv3x3_wgrad_(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, B: int, 
     cin, cout = x.shape[1], dy.shape[1]
     assert tuple(dw.shape) == (cout, 9 * cin)
     p = L.Conv3x3Params(2, B, H, W, cin, cout, _ptr(x), None, None, _ptr(dy), None, _ptr(dw), None, None, None, 0)
-    L.check(L.lib.uc_conv3x3(C.byref(p), _stream()))
+    _conv_call(p, B, H, W, cin, cout, 2)
 
 
 def im2col3x3(x: torch.Tensor, B: int, H: int, W: int, stride: int = 1) -> torch.Tensor:
