@@ -298,6 +298,21 @@ UC_API int uc_head_post_bwd(const uc_head_post_bwd_params* p, uc_stream_t stream
  *   F.interpolate(bilinear, align_corners=True) : uc_bilinear_fwd / uc_bilinear_bwd
  *   uc_elementwise op 0: a+b  1: relu(a)  2: a*(b>0)  3: a+b+c
  * ------------------------------------------------------------------------------------------ */
+/* Patch embedding without a column buffer == PatchEmbedDust3R.proj + flatten(2).transpose(1, 2)
+ * (libs/croco/patch_embed.py:47, :77-80): Conv2d(3, n, kernel = stride = patch) + bias on the fp32 NCHW image, tokens out
+ * (bf16 [B * (H/patch) * (W/patch), n], row = (b, patch y, patch x)).  The A operand is fetched by 5-D TMA boxes
+ * (dx, dy, patch x, patch y, 3 b + channel) straight from the image and multiplied in TF32 with the fp32 weight
+ * [n, 3 * patch * patch] (= proj.weight.flatten(1)); patch 16 or 32, W % 4 == 0, n % 128 == 0.  Other patch sizes (14:
+ * 56-byte patch rows cannot be TMA boxes) and the ManyAR transposed samples use uc_patchify + uc_gemm. */
+typedef struct {
+  const float* img;  /* fp32 [B, 3, H, W] */
+  const float* w;    /* fp32 [n, 3 * patch * patch] */
+  const float* bias; /* fp32 [n] or NULL */
+  void* out;         /* bf16 [B * (H / patch) * (W / patch), n] */
+  int32_t B, H, W, patch, n;
+} uc_patch_embed_params;
+UC_API int uc_patch_embed(const uc_patch_embed_params* p, uc_stream_t stream);
+
 /* 3x3 / stride 1 / pad 1 convolution on NHWC bf16 maps as an implicit GEMM (replaces nn.Conv2d(k=3, padding=1) of
  * dpt_block.py:133-152 (ResidualConvUnit), prediction_heads/dpt.py:131-140 (layer_rn) and :262-283 (regression head) and their
  * autograd backward).  No column buffer: per output tile the 9 taps are 9 shifted 4-D TMA boxes of the map (out-of-image

@@ -40,7 +40,8 @@ def test_ctypes_struct_sizes_match_header_layout():
                "uc_layernorm_fwd_params": _lib.LayerNormFwdParams, "uc_layernorm_bwd_params": _lib.LayerNormBwdParams,
                "uc_attn_fwd_params": _lib.AttnFwdParams, "uc_attn_bwd_params": _lib.AttnBwdParams,
                "uc_head_post_fwd_params": _lib.HeadPostFwdParams, "uc_head_post_bwd_params": _lib.HeadPostBwdParams,
-               "uc_headnorm_params": _lib.HeadNormParams, "uc_conv3x3_params": _lib.Conv3x3Params}
+               "uc_headnorm_params": _lib.HeadNormParams, "uc_conv3x3_params": _lib.Conv3x3Params,
+               "uc_patch_embed_params": _lib.PatchEmbedParams}
     prog = '#include <stdio.h>\n#include "uc_b200.h"\nint main(){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in structs) + "return 0;}"
     with tempfile.TemporaryDirectory() as d:

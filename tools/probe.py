@@ -466,6 +466,48 @@ def check_dpt_ops():
     return ok
 
 
+def check_conv3x3():
+    """uc_conv3x3 (implicit-GEMM 3x3 conv: forward, dgrad with and without the fused ReLU mask, wgrad) vs torch fp32 conv2d on
+    the same bf16-rounded operands; ragged map sizes, partial column tiles (192 / 384 channels), every window shape."""
+    import conv_probe
+
+    ok = True
+    for args, kw in [((2, 12, 10, 64, 128), {}), ((1, 37, 37, 256, 256), dict(relu=True)), ((2, 74, 74, 256, 256), dict(residual=True)),
+                     ((1, 64, 64, 192, 256), {}), ((1, 33, 40, 128, 128), {}), ((1, 16, 16, 768, 256), {}),
+                     ((1, 148, 148, 256, 128), dict(relu=True)), ((1, 130, 518, 128, 128), {}), ((3, 5, 7, 384, 256), {})]:
+        ok &= conv_probe.check(*args, **kw)
+    return ok
+
+
+def check_patch_embed():
+    """uc_patch_embed (5-D TMA boxes of the fp32 image, TF32 MMAs on the fp32 weight) vs F.conv2d in fp32 and vs the
+    uc_patchify + uc_gemm path; square, ragged and non-power-of-two patch grids, patch 16 / 32."""
+    import torch
+    import torch.nn.functional as F
+    from uniception_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    ok = True
+    for (B, H, W, ps, n) in [(2, 512, 512, 16, 1024), (3, 224, 224, 16, 768), (1, 48, 32, 16, 128), (2, 160, 288, 16, 256),
+                             (2, 128, 64, 32, 128)]:
+        g = torch.Generator(device="cuda").manual_seed(H + W + n)
+        img = torch.randn(B, 3, H, W, device="cuda", generator=g).clamp_(-1, 1)
+        w = torch.randn(n, 3, ps, ps, device="cuda", generator=g) / (3 * ps * ps) ** 0.5
+        b = torch.randn(n, device="cuda", generator=g)
+        ref = F.conv2d(img, w, b, stride=ps).flatten(2).transpose(1, 2).reshape(-1, n)
+        assert ops.patch_embed_ok(img, ps, n)
+        out = ops.patch_embed(img, w.view(n, -1).contiguous(), b, ps)
+        ok &= _report(f"patch_embed B{B} {H}x{W} p{ps} n{n} (TF32 operands, bf16 out)", out.float(), ref, 3e-3)
+        if ps == 16:
+            cols = ops.patchify(img, ps)
+            old = torch.empty(cols.shape[0], n, dtype=torch.bfloat16, device="cuda")
+            ops.gemm(cols, w.view(n, -1).bfloat16().contiguous(), old, bias=b)
+            e_old = float((old.float() - ref).norm() / ref.norm())
+            e_new = float((out.float() - ref).norm() / ref.norm())
+            print(f"      rel-L2 vs fp32: im2col-free TF32 path {e_new:.3e}, patchify + bf16 GEMM path {e_old:.3e}")
+            ok &= e_new <= e_old * 1.02
+    return ok
+
+
 def check_attn_once():
     """one fwd + bwd launch at the encoder's C3 shape (for ncu)"""
     import torch
@@ -483,7 +525,7 @@ def check_attn_once():
     return True
 
 
-CHECKS = ["gemm_tn", "gemm_dgrad", "gemm_wgrad", "gemm_epilogues", "elementwise", "attn_fwd", "attn_bwd", "dpt_ops", "perf"]
+CHECKS = ["gemm_tn", "gemm_dgrad", "gemm_wgrad", "gemm_epilogues", "elementwise", "attn_fwd", "attn_bwd", "dpt_ops", "conv3x3", "patch_embed", "perf"]
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] != "all":

@@ -108,6 +108,10 @@ class HeadNormParams(C.Structure):
     ]
 
 
+class PatchEmbedParams(C.Structure):
+    _fields_ = [("img", vp), ("w", vp), ("bias", vp), ("out", vp), ("B", i32), ("H", i32), ("W", i32), ("patch", i32), ("n", i32)]
+
+
 class Conv3x3Params(C.Structure):
     _fields_ = [
         ("mode", i32), ("B", i32), ("H", i32), ("W", i32), ("cin", i32), ("cout", i32),
@@ -136,6 +140,7 @@ EXPORTS = {
     "uc_nchw_to_nlc": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
     "uc_head_post_fwd": (C.c_int, [C.POINTER(HeadPostFwdParams), vp]),
     "uc_head_post_bwd": (C.c_int, [C.POINTER(HeadPostBwdParams), vp]),
+    "uc_patch_embed": (C.c_int, [C.POINTER(PatchEmbedParams), vp]),
     "uc_conv3x3": (C.c_int, [C.POINTER(Conv3x3Params), vp]),
     "uc_im2col3x3": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "uc_col2im3x3": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp]),

@@ -330,6 +330,13 @@ __device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* m,
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma2_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+      "[%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
 }
@@ -344,6 +351,15 @@ __device__ __forceinline__ void umma2_ss(uint32_t d_tmem, uint64_t a_desc, uint6
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the same with fp32 operands read as TF32 (UMMA_K = 8 elements = 32 bytes: the same descriptor step as 16 bf16)
+__device__ __forceinline__ void umma2_ss_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -366,10 +382,20 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr) {
 __device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t saddr, uint32_t mn_block_bytes) {
   return kDescSw128 | uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(mn_block_bytes >> 4) << 16) | (uint64_t(1024 >> 4) << 32);
 }
+// K-major tile [rows][64 B] with the 64-byte swizzle: 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw64(uint32_t saddr) {
+  return (uint64_t(1) << 46) | (uint64_t(4) << 61) /*SWIZZLE_64B*/ | uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(1) << 16) |
+         (uint64_t(512 >> 4) << 32);
+}
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, M x N tile.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a_mn_major) << 15) | (uint32_t(b_mn_major) << 16) |
          (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+// fp32 operands consumed as TF32 (a_format = b_format = 2), fp32 accumulate, both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 
 // ---- small numeric helpers ----

@@ -41,11 +41,14 @@ struct GemmArgs {
   //     4-D TMA box at the tap's offset (out-of-image pixels zero-fill = the padding); C / aux tiles leave / arrive the same way.
   //   CONV 2 (wgrad): K runs over pixels; a k-block is a TW x TH window (TW * TH = 64) of dy (A, unshifted) and of x (B, shifted
   //     by the tap of each 64-column block of the [cout, 9 cin] weight gradient).
+  //   CONV 3 (patch embedding, uc_patch_embed): the "map" is the patch grid; A comes straight from the fp32 NCHW image through a
+  //     5-D TMA box (dx, dy, patch x, patch y, batch*3 + channel) -- a k-block is 32 fp32 = 32 / p rows of one patch of one
+  //     channel -- and the MMAs run in TF32 on the fp32 master weights; C leaves like CONV 1.  No column buffer.
   int cv_H, cv_W, cv_tw_log2, cv_tiles_x, cv_tiles_y;
-  int cv_kb_per_tap;    // CONV 1: channel blocks (of 64) per tap in A
+  int cv_kb_per_tap;    // CONV 1: channel blocks (of 64) per tap in A; CONV 3: k-blocks per image channel (p * p / 32)
   int cv_b_tap_stride;  // CONV 1: 0 = B is K-major with k = tap * C + c (fwd); > 0 = B is MN-major and tap t reads the column
                         // block (8 - t) * stride (dgrad: the spatially flipped filter)
-  int cv_cin;           // CONV 2: channels of x (columns per tap)
+  int cv_cin;           // CONV 2: channels of x (columns per tap); CONV 3: patch rows per k-block (32 / p)
 };
 
 template <int BN>
@@ -509,8 +512,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int n0 = (g.n_fastest ? (tile % g.num_n) : (tile / g.num_m)) * BN + (BN / 2) * (int)rank;
       const int kb0 = split * g.kb_per_split;
       const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
-      int cx0 = 0, cy0 = 0, cimg = 0;  // CONV 1: this CTA's pixel window
-      if (CONV == 1) {
+      int cx0 = 0, cy0 = 0, cimg = 0;  // CONV 1 / 3: this CTA's pixel (patch) window
+      if (CONV == 1 || CONV == 3) {
         const int tm = g.n_fastest ? (tile / g.num_n) : (tile % g.num_m);
         const int per_img = g.cv_tiles_x * g.cv_tiles_y;
         cimg = tm / per_img;
@@ -537,6 +540,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               for (int j = 0; j < BN / 2 / 64; ++j)
                 tma2_load_2d(sb + j * 8192, &tmB, full_bar(stage), n0 + j * 64 + (8 - tap) * g.cv_b_tap_stride, c0);
             }
+          } else if (CONV == 3) {
+            const int ch = kb / g.cv_kb_per_tap;
+            const int dy0 = (kb - ch * g.cv_kb_per_tap) * g.cv_cin;
+            // one box per patch row: [128 patches x p fp32]; 32 / p of them (64-byte rows: 64-byte swizzle) make the k-block
+            for (int rr = 0; rr < g.cv_cin; ++rr)
+              tma2_load_5d(sa + rr * (G2_A_BYTES / g.cv_cin), &tmA, full_bar(stage), 0, dy0 + rr, cx0, cy0, 3 * cimg + ch);
+            tma2_load_2d(sb, &tmB, full_bar(stage), kb * 32, n0);
           } else if (CONV == 2) {
             const int per_img = g.cv_tiles_x * g.cv_tiles_y;
             const int img = kb / per_img;
@@ -584,7 +594,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (rank == 0) {
-      const uint32_t idesc = umma_idesc_bf16(256, BN, g.a_mn, g.b_mn);
+      const uint32_t idesc = CONV == 3 ? umma_idesc_tf32(256, BN) : umma_idesc_bf16(256, BN, g.a_mn, g.b_mn);
       const uint32_t a_step = g.a_mn ? (2048u >> 4) : (32u >> 4);
       const uint32_t b_step = g.b_mn ? (2048u >> 4) : (32u >> 4);
       int stage = 0;
@@ -610,8 +620,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint64_t bdesc = g.b_mn ? umma_desc_mnmajor(sb, 8192) : umma_desc_kmajor(sb);
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma2_ss(d_tmem, adesc + uint64_t(k * a_step), bdesc + uint64_t(k * b_step), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              if (CONV == 3) {
+                // A: one 128-byte-swizzled tile (patch 32) or two 64-byte-swizzled half tiles of 8 KB (patch 16), 8 tf32 per step
+                const uint64_t ad = g.cv_cin == 2 ? umma_desc_kmajor_sw64(sa + (k >> 1) * 8192) + uint64_t((k & 1) * 2) : adesc + uint64_t(k * 2);
+                umma2_ss_tf32(d_tmem, ad, bdesc + uint64_t(k * b_step), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              } else {
+                umma2_ss(d_tmem, adesc + uint64_t(k * a_step), bdesc + uint64_t(k * b_step), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              }
+            }
             umma2_commit_mc(empty_bar(stage));
           }
           __syncwarp();
@@ -673,8 +690,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int row0 = m0 + lane_group * 32;
       int row = row0 + lane;
       bool row_ok = row < g.m;
-      int cxs = 0, cys = 0, cimg = 0;  // CONV 1: pixel coordinates of this warp's 32-row group (its C / aux boxes)
-      if (CONV == 1) {
+      int cxs = 0, cys = 0, cimg = 0;  // CONV 1 / 3: pixel coordinates of this warp's 32-row group (its C / aux boxes)
+      if (CONV == 1 || CONV == 3) {
         const int tm = g.n_fastest ? (tile / g.num_n) : (tile % g.num_m);
         const int per_img = g.cv_tiles_x * g.cv_tiles_y;
         cimg = tm / per_img;
@@ -690,11 +707,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         row = 0;  // no row-addressed global access in this mode (aux tiles are staged, bias is per column)
       }
       auto load_aux = [&](uint32_t buf, uint32_t bar, int col) {
-        if (CONV == 1) tma_load_4d(buf, &tmAux, bar, col, cxs, cys, cimg);
+        if (CONV == 1 || CONV == 3) tma_load_4d(buf, &tmAux, bar, col, cxs, cys, cimg);
         else tma_load_2d(buf, &tmAux, bar, col, row0);
       };
       auto store_c = [&](uint32_t buf, int col) {
-        if (CONV == 1) tma_store_4d(&tmC, buf, col, cxs, cys, cimg);
+        if (CONV == 1 || CONV == 3) tma_store_4d(&tmC, buf, col, cxs, cys, cimg);
         else tma_store_2d(&tmC, buf, col, row0);
       };
       const int nw = n0 + col_half * (BN / 2);  // first column of this warp's half of the tile
@@ -1200,4 +1217,62 @@ extern "C" int uc_conv3x3(const uc_conv3x3_params* p, uc_stream_t stream_) {
   constexpr int kConvMask = UC_EPI_BIAS | UC_EPI_RESIDUAL | UC_EPI_RELU | UC_EPI_RELU_BWD;
   if (bn == 256) return launch2_inst<kConvMask, false, 256, 1>(tmA, tmB, tmC, tmAux, g, 2 * clusters, stream);
   return launch2_inst<kConvMask, false, 128, 1>(tmA, tmB, tmC, tmAux, g, 2 * clusters, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// uc_patch_embed: Conv2d(3, C, kernel = stride = p) + bias on the fp32 NCHW image, tokens out (bf16 [B * Hp * Wp, C]),
+// without materialising the patch columns: 5-D TMA boxes of the image feed TF32 MMAs on the fp32 master weights.
+// ------------------------------------------------------------------------------------------------
+extern "C" int uc_patch_embed(const uc_patch_embed_params* p, uc_stream_t stream_) {
+  using namespace uc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  UC_REQUIRE(p && p->img && p->w && p->out, UC_ERR_BAD_SHAPE, "uc_patch_embed: null pointer");
+  UC_REQUIRE(p->patch == 16 || p->patch == 32, UC_ERR_UNSUPPORTED,
+             "uc_patch_embed: patch %d (a patch row must be a 64- or 128-byte TMA box row: 16 or 32; use uc_patchify + uc_gemm)", p->patch);
+  UC_REQUIRE(p->B > 0 && p->H > 0 && p->W > 0 && p->H % p->patch == 0 && p->W % p->patch == 0, UC_ERR_BAD_SHAPE,
+             "uc_patch_embed: image %dx%d is not a multiple of the patch size %d", p->H, p->W, p->patch);
+  UC_REQUIRE(p->n > 0 && p->n % 128 == 0, UC_ERR_BAD_SHAPE, "uc_patch_embed: n=%d must be a multiple of 128", p->n);
+  UC_REQUIRE(((uintptr_t)p->img % 16 == 0) && ((uintptr_t)p->w % 16 == 0) && ((uintptr_t)p->out % 16 == 0), UC_ERR_BAD_SHAPE,
+             "uc_patch_embed: pointers must be 16-byte aligned");
+  const int ps = p->patch, Hp = p->H / ps, Wp = p->W / ps;
+  const int sms = sm_count();
+  const int slots = sms / 2;
+  GemmArgs g{};
+  g.cv_H = Hp; g.cv_W = Wp;
+  const int l2 = best_window_log2(Hp, Wp, 128, 2, 3, 7);
+  const int tw = 1 << l2, th = 128 / tw;
+  g.cv_tw_log2 = l2; g.cv_tiles_x = (Wp + tw - 1) / tw; g.cv_tiles_y = (Hp + 2 * th - 1) / (2 * th);
+  g.cv_kb_per_tap = ps * ps / 32; g.cv_cin = 32 / ps; g.cv_b_tap_stride = 0;
+  g.m = p->B * Hp * Wp; g.n = p->n; g.k = 3 * ps * ps;
+  g.a_mn = 0; g.b_mn = 0;
+  const int bn = (p->n % 256 == 0) ? 256 : 128;
+  g.num_m = p->B * g.cv_tiles_x * g.cv_tiles_y;
+  g.num_n = p->n / bn;
+  g.num_kb = 3 * g.cv_kb_per_tap; g.split_k = 1; g.kb_per_split = g.num_kb;
+  g.n_fastest = 1;
+  g.epilogue = p->bias ? UC_EPI_BIAS : 0; g.bias = p->bias;
+  g.c_f32 = 0; g.ldc = p->n; g.c = p->out;
+  CUtensorMap tmA, tmB, tmC, tmAux;
+  int r;
+  {
+    uint64_t dims[5] = {(uint64_t)ps, (uint64_t)ps, (uint64_t)Wp, (uint64_t)Hp, (uint64_t)3 * p->B};
+    uint64_t strides[4] = {(uint64_t)p->W * 4, (uint64_t)ps * 4, (uint64_t)ps * p->W * 4, (uint64_t)p->H * p->W * 4};
+    uint32_t box[5] = {(uint32_t)ps, 1u, (uint32_t)tw, (uint32_t)th, 1u};  // [128 patches x one patch row]
+    if ((r = make_tensor_map(&tmA, p->img, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, dims, strides, box,
+                             ps == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)))
+      return r;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)3 * ps * ps, (uint64_t)p->n};
+    uint64_t strides[1] = {(uint64_t)3 * ps * ps * 4};
+    uint32_t box[2] = {32u, (uint32_t)bn / 2};
+    if ((r = make_tensor_map(&tmB, p->w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return r;
+  }
+  const int bw = tw >= 32 ? 32 : tw, bh = 32 / bw;
+  if ((r = act_map(&tmC, p->out, p->B, Hp, Wp, p->n, bw, bh))) return r;
+  tmAux = tmC;
+  const long long total = (long long)g.num_m * g.num_n;
+  const int clusters = (int)(total < slots ? total : slots);
+  if (bn == 256) return launch2_inst<UC_EPI_BIAS, false, 256, 3>(tmA, tmB, tmC, tmAux, g, 2 * clusters, stream);
+  return launch2_inst<UC_EPI_BIAS, false, 128, 3>(tmA, tmB, tmC, tmAux, g, 2 * clusters, stream);
 }

@@ -72,6 +72,9 @@ class Rope:
 # ------------------------------------------------------------------------------------------------
 # linear helpers
 # ------------------------------------------------------------------------------------------------
+PATCH_EMBED_TMA = os.environ.get("UC_PATCH_EMBED_TMA", "1") != "0"  # 0: uc_patchify + uc_gemm forward (A/B, debugging)
+
+
 def _empty(rows, cols, like, dtype=torch.bfloat16):
     return torch.empty(rows, cols, dtype=dtype, device=like.device)
 
@@ -305,7 +308,14 @@ def encoder_fwd(pk: ParamPack, p: str, img: torch.Tensor, depth: int, heads: int
     if portrait is not None and not any(portrait):
         portrait = None
     rope = Rope(B, h, w, rope_base, rope_f0, img.device, portrait) if rope_base is not None else None
-    if portrait is None:
+    wname = p + "patch_embed.proj.weight"
+    direct = (portrait is None and PATCH_EMBED_TMA and ops.patch_embed_ok(img, patch, pk.w32(wname).shape[0]))
+    if direct:
+        # im2col-free: 5-D TMA boxes of the fp32 image feed TF32 MMAs on the fp32 master weight (uc_patch_embed); nothing but the
+        # image is kept for the backward pass, which gathers the bf16 columns it needs for the weight gradient itself
+        x = ops.patch_embed(img, pk.w32(wname).view(pk.w32(wname).shape[0], -1), pk.w32(p + "patch_embed.proj.bias"), patch)
+        saved = {"cols": None, "img": img, "patch": patch, "blocks": [], "B": B, "N": N, "rope": rope, "inter": []}
+    elif portrait is None:
         cols = ops.patchify(img, patch)
     else:  # mixed batch: gather each orientation group separately, then restore the sample order (index ops, bit-exact)
         pidx = [i for i, f in enumerate(portrait) if f]
@@ -316,14 +326,15 @@ def encoder_fwd(pk: ParamPack, p: str, img: torch.Tensor, depth: int, heads: int
         if lidx:
             cols[lidx] = ops.patchify(img[lidx].contiguous(), patch).view(len(lidx), N, -1)
         cols = cols.view(B * N, -1)
-    wpe = pk.w16(p + "patch_embed.proj.weight")
-    if wpe.shape[1] != cols.shape[1]:  # patch sizes whose 3*p*p is not a multiple of 8 (p = 14): zero-padded operand copy
-        wpad = torch.zeros(wpe.shape[0], cols.shape[1], dtype=wpe.dtype, device=wpe.device)
-        wpad[:, :wpe.shape[1]] = wpe
-        wpe = wpad
-    x = _empty(cols.shape[0], wpe.shape[0], cols)
-    ops.gemm(cols, wpe, x, bias=pk.w32(p + "patch_embed.proj.bias"))
-    saved = {"cols": cols, "blocks": [], "B": B, "N": N, "rope": rope, "inter": []}
+    if not direct:
+        wpe = pk.w16(wname)
+        if wpe.shape[1] != cols.shape[1]:  # patch sizes whose 3*p*p is not a multiple of 8 (p = 14): zero-padded operand copy
+            wpad = torch.zeros(wpe.shape[0], cols.shape[1], dtype=wpe.dtype, device=wpe.device)
+            wpad[:, :wpe.shape[1]] = wpe
+            wpe = wpad
+        x = _empty(cols.shape[0], wpe.shape[0], cols)
+        ops.gemm(cols, wpe, x, bias=pk.w32(p + "patch_embed.proj.bias"))
+        saved = {"cols": cols, "blocks": [], "B": B, "N": N, "rope": rope, "inter": []}
     inter = []
     for i in range(depth):
         bs: list = []
@@ -381,6 +392,8 @@ def encoder_bwd(pk: ParamPack, p: str, saved, d_out: Optional[torch.Tensor], dep
     if dx is not None and pk.requires_grad(p + "patch_embed.proj.weight"):
         gw = pk.grad(p + "patch_embed.proj.weight")
         cols = saved["cols"]
+        if cols is None:  # forward ran im2col-free: gather the bf16 columns now, for the weight gradient only
+            cols = ops.patchify(saved["img"], saved["patch"])
         if gw.shape[1] == cols.shape[1]:
             ops.gemm(dx, cols, gw, a_layout=1, b_layout=1, atomic=True)
         else:  # padded pitch (p = 14): accumulate into a padded fp32 scratch, then add the valid columns

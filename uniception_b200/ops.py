@@ -321,6 +321,31 @@ def _p(t):
     return _ptr(t) if t is not None else None
 
 
+def patch_embed_ok(img: torch.Tensor, patch: int, n: int) -> bool:
+    """Shapes uc_patch_embed accepts (TMA box constraints, include/uc_b200.h); everything else takes patchify + gemm."""
+    return patch in (16, 32) and img.shape[-1] % 4 == 0 and n % 128 == 0 and img.shape[1] == 3
+
+
+def patch_embed(img: torch.Tensor, w32: torch.Tensor, bias: Optional[torch.Tensor], patch: int) -> torch.Tensor:
+    """im2col-free patch embedding (uc_patch_embed): img fp32 [B,3,H,W], w32 fp32 [n, 3*patch*patch] -> bf16 [B*Hp*Wp, n]."""
+    _cuda(img, w32)
+    assert img.dtype == torch.float32 and img.is_contiguous() and w32.dtype == torch.float32 and w32.is_contiguous()
+    B, _, H, W = img.shape
+    n = w32.shape[0]
+    assert w32.shape[1] == 3 * patch * patch
+    out = torch.empty(B * (H // patch) * (W // patch), n, dtype=torch.bfloat16, device=img.device)
+    p = L.PatchEmbedParams(_ptr(img), _ptr(w32), _p(bias), _ptr(out), B, H, W, patch, n)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L.lib.uc_patch_embed(C.byref(p), _stream()))
+        e1.record()
+        PROFILE.append((e0, e1, 2.0 * out.shape[0] * n * 3 * patch * patch, ("patch_embed", out.shape[0], n, 3 * patch * patch, 0, 0)))
+        return out
+    L.check(L.lib.uc_patch_embed(C.byref(p), _stream()))
+    return out
+
+
 def _conv_call(p, B, H, W, cin, cout, mode):
     """uc_conv3x3, timed with CUDA events when bench.py's per-launch GEMM profile is on (the convolution runs on the same
     tcgen05 kernel as uc_gemm; algorithmic FLOPs = 2 * pixels * 9 * cin * cout)."""
