@@ -250,6 +250,14 @@ UC_API int uc_layerscale_fwd(const void* z, const void* res, const float* gamma,
 UC_API int uc_layerscale_bwd(const void* dy, const void* z, const float* gamma, void* dz, float* dgamma, int32_t rows, int32_t cols,
                              uc_stream_t stream);
 
+/* Row softmax of a score matrix produced by uc_gemm and its backward: the un-fused attention of head dims other than 64
+ * (DiffAttention family: 128-wide self-attention heads, 64-wide q/k against 128-wide v; utils/transformer_blocks.py:686-945,
+ * info_sharing/diff_cross_attention_transformer.py:110-113).  Columns >= valid (key padding up to the GEMM's multiple of 64)
+ * are written as zeros.   fwd: P = softmax(scale * S[:, :valid]);   bwd: dS = scale * P o (dP - rowsum(P o dP)). */
+UC_API int uc_softmax_rows_fwd(const float* s, void* p_bf16, int32_t rows, int32_t valid, int32_t ld, float scale, uc_stream_t stream);
+UC_API int uc_softmax_rows_bwd(const void* p_bf16, const float* dp, void* ds_bf16, int32_t rows, int32_t valid, int32_t ld, float scale,
+                               uc_stream_t stream);
+
 /* column sums of a [rows][cols] matrix (bias gradients), ACCUMULATED into fp32 out[cols] */
 UC_API int uc_colsum(const void* x, int32_t x_dtype, int64_t ld, int32_t rows, int32_t cols, float* out, uc_stream_t stream);
 

@@ -286,6 +286,116 @@ def decoder_block(sd: SD, p: str, x: Tensor, y: Tensor, xpos, ypos, heads: int, 
     return x
 
 
+# --------------------------------------------------------------------------------------
+# DiffAttention family (utils/transformer_blocks.py:658-1031, info_sharing/diff_cross_attention_transformer.py:22-588)
+# --------------------------------------------------------------------------------------
+def lambda_init(depth: int) -> float:
+    """utils/transformer_blocks.py:682-683."""
+    return 0.8 - 0.6 * math.exp(-0.3 * depth)
+
+
+def _diff_combine(sd: SD, p: str, attn1: Tensor, attn2: Tensor, depth: int) -> Tensor:
+    """attn1 - lambda_full * attn2 -> RMSNorm(2 d, eps 1e-5, affine) -> x (1 - lambda_init)
+    (utils/transformer_blocks.py:779-787 / :924-931; RMSNorm :658-679 normalises in fp32 and casts back)."""
+    l1 = torch.exp(torch.sum(sd[p + "lambda_q1"] * sd[p + "lambda_k1"], dim=-1).float()).type_as(attn1)
+    l2 = torch.exp(torch.sum(sd[p + "lambda_q2"] * sd[p + "lambda_k2"], dim=-1).float()).type_as(attn1)
+    li = lambda_init(depth)
+    a = attn1 - (l1 - l2 + li) * attn2
+    af = a.float()
+    a = (af * torch.rsqrt(af.pow(2).mean(-1, keepdim=True) + 1e-5)).type_as(a) * sd[p + "subln.weight"]
+    return a * (1 - li)
+
+
+def diff_attention(sd: SD, p: str, x: Tensor, pos: Optional[Tensor], heads: int, depth: int, base: float) -> Tensor:
+    """`DiffAttention.forward` (utils/transformer_blocks.py:743-795).  heads = the layer's num_heads H: q / k are split into
+    2 H heads of d = C / H / 2, v into H heads of 2 d; the [B, H, N, 2 d] result is reshaped to [B, N, C] WITHOUT a
+    head / token transpose (:789), as the reference does."""
+    B, N, C = x.shape
+    d = C // heads // 2
+    qkv = linear(x, sd[p + "qkv.weight"], sd.get(p + "qkv.bias")).reshape(B, N, 3, heads, 2 * d)
+    q, k, v = torch.chunk(qkv, 3, dim=2)
+    q = q.reshape(B, N, 2 * heads, d).permute(0, 2, 1, 3)
+    k = k.reshape(B, N, 2 * heads, d).permute(0, 2, 1, 3)
+    v = v.reshape(B, N, heads, 2 * d).permute(0, 2, 1, 3)
+    q, k = qk_norm(sd, p, q, k)
+    if pos is not None:
+        q, k = rope2d(q, pos, base), rope2d(k, pos, base)
+    q1, q2 = q.chunk(2, dim=1)
+    k1, k2 = k.chunk(2, dim=1)
+    scale = d ** -0.5
+    a1 = ((q1 @ k1.transpose(-2, -1)) * scale).softmax(dim=-1) @ v
+    a2 = ((q2 @ k2.transpose(-2, -1)) * scale).softmax(dim=-1) @ v
+    a = _diff_combine(sd, p, a1, a2, depth).reshape(B, N, heads * 2 * d)
+    return linear(a, sd[p + "proj.weight"], sd[p + "proj.bias"])
+
+
+def diff_cross_attention(sd: SD, p: str, xq: Tensor, y: Tensor, qpos, kpos, heads: int, depth: int, base: float) -> Tensor:
+    """`DiffCrossAttention.forward` (utils/transformer_blocks.py:881-938): as above with separate q / k / v projections and
+    the [B, H, Nq, 2 d] -> [B, Nq, H, 2 d] transpose before the combination (:921-922)."""
+    B, Nq, C = xq.shape
+    Nk = y.shape[1]
+    d = C // heads // 2
+    q = linear(xq, sd[p + "projq.weight"], sd.get(p + "projq.bias")).reshape(B, Nq, 2 * heads, d).permute(0, 2, 1, 3)
+    k = linear(y, sd[p + "projk.weight"], sd.get(p + "projk.bias")).reshape(B, Nk, 2 * heads, d).permute(0, 2, 1, 3)
+    v = linear(y, sd[p + "projv.weight"], sd.get(p + "projv.bias")).reshape(B, Nk, heads, 2 * d).permute(0, 2, 1, 3)
+    q, k = qk_norm(sd, p, q, k)
+    if qpos is not None:
+        q, k = rope2d(q, qpos, base), rope2d(k, kpos, base)
+    q1, q2 = q.chunk(2, dim=1)
+    k1, k2 = k.chunk(2, dim=1)
+    scale = d ** -0.5
+    a1 = (((q1 @ k1.transpose(-2, -1)) * scale).softmax(dim=-1) @ v).transpose(1, 2)
+    a2 = (((q2 @ k2.transpose(-2, -1)) * scale).softmax(dim=-1) @ v).transpose(1, 2)
+    a = _diff_combine(sd, p, a1, a2, depth).reshape(B, Nq, heads * 2 * d)
+    return linear(a, sd[p + "proj.weight"], sd[p + "proj.bias"])
+
+
+def diff_decoder_block(sd: SD, p: str, x: Tensor, y: Tensor, xpos, ypos, heads: int, depth: int, base: float) -> Tensor:
+    """`DiffCrossAttentionBlock` (utils/transformer_blocks.py:989-1031 on CrossAttentionBlock.forward :620-647): plain
+    self-attention with `heads` heads (head_dim = C / heads), differential cross-attention, MLP."""
+    x = x + layer_scale(sd, p + "ls1.gamma", self_attention(sd, p + "attn.", layer_norm(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"]),
+                                                           xpos, heads, base))
+    y_ = layer_norm(y, sd[p + "norm_y.weight"], sd[p + "norm_y.bias"]) if (p + "norm_y.weight") in sd else y
+    x = x + layer_scale(sd, p + "ls2.gamma", diff_cross_attention(
+        sd, p + "cross_attn.", layer_norm(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"]), y_, xpos, ypos, heads, depth, base))
+    x = x + layer_scale(sd, p + "ls3.gamma", mlp(sd, p + "mlp.", layer_norm(x, sd[p + "norm3.weight"], sd[p + "norm3.bias"])))
+    return x
+
+
+def diff_info_sharing(sd: SD, p: str, feats: List[Tensor], depth: int, heads: int, base: Optional[float] = 100.0, indices=None,
+                      norm_intermediate: bool = True):
+    """`DifferentialMultiViewCrossAttentionTransformer.forward` (diff_cross_attention_transformer.py:175-259; IFR :390-507).
+    heads = the TRANSFORMER's num_heads; its blocks are built with heads // 2 (:110-113).  base None: no positional encoding."""
+    nv = len(feats)
+    B, _, h, w = feats[0].shape
+    toks = [f.permute(0, 2, 3, 1).reshape(B, h * w, f.shape[1]) for f in feats]
+    pos = [patch_positions(B, h, w, f.device) if base is not None else None for f in feats]
+    if (p + "proj_embed.weight") in sd:
+        toks = [linear(t, sd[p + "proj_embed.weight"], sd[p + "proj_embed.bias"]) for t in toks]
+    take = feature_take_indices(depth, indices)[0] if indices is not None else []
+    inter = []
+    nw, nb = sd[p + "norm.weight"], sd[p + "norm.bias"]
+    for k in range(depth):
+        new = []
+        for v in range(nv):
+            others = torch.cat([toks[i] for i in range(nv) if i != v], dim=1)
+            opos = torch.cat([pos[i] for i in range(nv) if i != v], dim=1) if base is not None else None
+            new.append(diff_decoder_block(sd, f"{p}multi_view_branches.{v}.{k}.", toks[v], others, pos[v], opos, heads // 2, k,
+                                          base if base is not None else 100.0))
+        toks = new
+        if k in take:
+            inter.append([layer_norm(t, nw, nb) if norm_intermediate else t for t in toks])
+    dim = toks[0].shape[-1]
+
+    def to_bchw(t):
+        return t.reshape(B, h, w, dim).permute(0, 3, 1, 2).contiguous()
+
+    out = [to_bchw(layer_norm(t, nw, nb)) for t in toks]
+    if indices is not None:
+        return out, [[to_bchw(t) for t in lvl] for lvl in inter]
+    return out
+
+
 def patch_embed(sd: SD, p: str, img: Tensor, patch: int, true_shape: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     """Conv2d(3,C,k=s=patch)+bias, flatten(2).transpose(1,2) (libs/croco/patch_embed.py:68-82),
     restated as unfold + matmul (kernel == stride so patches do not overlap).
@@ -615,6 +725,10 @@ def seeded_state_dict(shapes: Dict[str, Sequence[int]], seed: int, dtype=torch.f
             v = 1.0 + 0.1 * rs.standard_normal(shp)
         elif k.endswith("gamma"):  # LayerScale: O(1) so that the scaled branch matters in the parity metric
             v = 1.0 + 0.3 * rs.standard_normal(shp)
+        elif k.endswith("subln.weight"):  # RMS sub-layer norm of the Diff layers
+            v = 1.0 + 0.1 * rs.standard_normal(shp)
+        elif ".lambda_" in k:  # DiffAttention lambdas: large enough that exp(sum(lq * lk)) moves away from 1
+            v = 0.3 * rs.standard_normal(shp)
         else:
             v = 0.02 * rs.standard_normal(shp)
         sd[k] = torch.from_numpy(np.ascontiguousarray(v)).to(dtype)

@@ -521,6 +521,58 @@ def golden_cross_attention_scaled(name, seed, B=2, hw=(3, 4), C_in=192, dim=128,
                      shapes={k: list(v) for k, v in shapes.items()}), arrays)
 
 
+def golden_diff_cross_attention(name, seed, B=2, hw=(3, 4), C_in=192, dim=256, depth=2, heads=4, V=2, rope=True, indices=None):
+    """`DifferentialMultiViewCrossAttentionTransformer(IFR)` (diff_cross_attention_transformer.py:22-588):
+    dim 256 / 4 heads -> blocks with 2 heads: 128-wide self-attention heads, differential cross-attention with 64-wide q / k
+    against 128-wide v (the head geometry of the default dim 768 / 12 heads).  Loss weights every output."""
+    from uniception.models.info_sharing.base import MultiViewTransformerInput
+    from uniception.models.info_sharing.diff_cross_attention_transformer import (
+        DifferentialMultiViewCrossAttentionTransformer, DifferentialMultiViewCrossAttentionTransformerIFR)
+    from uniception.models.libs.croco.pos_embed import RoPE2D
+
+    kw = dict(name="mvd", input_embed_dim=C_in, num_views=V, depth=depth, dim=dim, num_heads=heads,
+              custom_positional_encoding=RoPE2D(freq=100.0) if rope else None)
+    if indices is None:
+        m = DifferentialMultiViewCrossAttentionTransformer(**kw)
+    else:
+        m = DifferentialMultiViewCrossAttentionTransformerIFR(indices=indices, **kw)
+    sd, shapes = _load_seeded(m, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    feats = [torch.randn(B, C_in, *hw, generator=g).requires_grad_(True) for _ in range(V)]
+    res = m(MultiViewTransformerInput(features=feats))
+    out, inter = (res[0].features, [lv.features for lv in res[1]]) if indices is not None else (res.features, [])
+
+    def loss(o, it):
+        return sum(t.sum() for t in o) + sum((k + 1.5) * sum(t.sum() for t in lv) for k, lv in enumerate(it))
+
+    loss(out, inter).backward()
+    params = dict(m.named_parameters())
+    osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    of = [f.detach().clone().requires_grad_(True) for f in feats]
+    ores = O.diff_info_sharing(osd, "", of, depth, heads, base=100.0 if rope else None, indices=indices)
+    oo, oi = (ores[0], ores[1]) if indices is not None else (ores, [])
+    for v in range(V):
+        _check(f"{name} view{v}", oo[v], out[v])
+    for k, lv in enumerate(oi):
+        for v in range(V):
+            _check(f"{name} level{k} view{v}", lv[v], inter[k][v])
+    loss(oo, oi).backward()
+    arrays = {f"feat{v}": feats[v].detach() for v in range(V)}
+    arrays.update({f"out{v}": out[v] for v in range(V)})
+    for k, lv in enumerate(inter):
+        arrays.update({f"inter{k}_{v}": lv[v] for v in range(V)})
+    arrays["grad_in0"] = feats[0].grad
+    for key in ("multi_view_branches.1.0.cross_attn.projq.weight", "multi_view_branches.0.1.attn.qkv.weight",
+                "multi_view_branches.0.0.cross_attn.lambda_q1", "multi_view_branches.1.1.cross_attn.lambda_k2",
+                "multi_view_branches.0.1.cross_attn.subln.weight", "multi_view_branches.1.0.cross_attn.projv.bias",
+                "multi_view_branches.0.0.mlp.fc1.weight", "proj_embed.weight"):
+        _check(f"{name} grad {key}", osd[key].grad, params[key].grad, 1e-4)
+        arrays["grad_" + key.replace(".", "_")] = params[key].grad
+    _save(name, dict(seed=seed, B=B, hw=list(hw), C_in=C_in, dim=dim, depth=depth, heads=heads, V=V, rope=bool(rope),
+                     indices=list(indices) if indices is not None else None,
+                     shapes={k: list(v) for k, v in shapes.items()}), arrays)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -553,6 +605,8 @@ def main():
                                        indices=[1, 3])
     golden_self_attention_info_sharing("alternating_attn_tiny_ifr", "MultiViewAlternatingAttentionTransformerIFR", seed=57, rope=True,
                                        V=3, indices=[0, 2], norm_intermediate=False)
+    golden_diff_cross_attention("diff_cross_attn_tiny", seed=71)
+    golden_diff_cross_attention("diff_cross_attn_tiny_ifr", seed=72, V=3, hw=(2, 5), indices=[0, 1], rope=False)
 
 
 if __name__ == "__main__":

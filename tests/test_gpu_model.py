@@ -629,3 +629,47 @@ def test_cross_attention_softmax_scaling_vs_reference_golden():
     assert O.parity(m.multi_view_branches[1][0].cross_attn.projq.weight.grad, a["grad_projq"].to(DEV))[1] <= 5e-2
     assert O.parity(m.multi_view_branches[0][1].attn.qkv.weight.grad, a["grad_qkv"].to(DEV))[1] <= 5e-2
     assert O.parity(feats[0].grad, a["grad_in0"].to(DEV))[1] <= 5e-2
+
+
+@pytest.mark.parametrize("name", ["diff_cross_attn_tiny", "diff_cross_attn_tiny_ifr"])
+def test_diff_cross_attention_vs_reference_golden(name):
+    """the DiffAttention family (`DifferentialMultiViewCrossAttentionTransformer(IFR)`) on the un-fused attention
+    path -- uc_gemm scores, uc_softmax_rows, uc_gemm PV and the four gradient products -- with 128-wide self-attention heads and
+    64-wide q / k against 128-wide v; forward vs the reference's golden, gradients of every kind of parameter the family adds."""
+    cfg, a = load(name)
+    V = cfg["V"]
+    kw = dict(name="mvd", input_embed_dim=cfg["C_in"], num_views=V, depth=cfg["depth"], dim=cfg["dim"], num_heads=cfg["heads"],
+              custom_positional_encoding=U.RoPE2D(freq=100.0) if cfg["rope"] else None)
+    if cfg["indices"] is None:
+        m = U.DifferentialMultiViewCrossAttentionTransformer(**kw)
+    else:
+        m = U.DifferentialMultiViewCrossAttentionTransformerIFR(indices=cfg["indices"], **kw)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v) for k, v in cfg["shapes"].items()}
+    m.load_state_dict(weights(cfg))
+    m = m.to(DEV)
+    feats = [a[f"feat{v}"].to(DEV).requires_grad_(True) for v in range(V)]
+    res = m(U.MultiViewTransformerInput(features=feats))
+    out, inter = (res[0].features, [lv.features for lv in res[1]]) if cfg["indices"] is not None else (res.features, [])
+    sd = {k: v.to(DEV) for k, v in weights(cfg).items()}
+    fin = [f.detach() for f in feats]
+
+    def oracle():
+        r = O.diff_info_sharing(sd, "", fin, cfg["depth"], cfg["heads"], base=100.0 if cfg["rope"] else None, indices=cfg["indices"])
+        return (list(r[0]) + [t for lv in r[1] for t in lv]) if cfg["indices"] is not None else list(r)
+
+    ref_err = max(_autocast_err(oracle))
+    errs = [O.parity(out[v], a[f"out{v}"].to(DEV))[1] for v in range(V)]
+    errs += [O.parity(lv[v], a[f"inter{k}_{v}"].to(DEV))[1] for k, lv in enumerate(inter) for v in range(V)]
+    print(f"{name}: ours vs reference golden rel {max(errs):.3e} (autocast-bf16 oracle: {ref_err:.3e})")
+    assert max(errs) <= 1.5 * ref_err + 2e-3, (errs, ref_err)
+    loss = sum(t.sum() for t in out) + sum((k + 1.5) * sum(t.sum() for t in lv) for k, lv in enumerate(inter))
+    loss.backward()
+    params = dict(m.named_parameters())
+    for key in ("multi_view_branches.1.0.cross_attn.projq.weight", "multi_view_branches.0.1.attn.qkv.weight",
+                "multi_view_branches.0.0.cross_attn.lambda_q1", "multi_view_branches.1.1.cross_attn.lambda_k2",
+                "multi_view_branches.0.1.cross_attn.subln.weight", "multi_view_branches.1.0.cross_attn.projv.bias",
+                "multi_view_branches.0.0.mlp.fc1.weight", "proj_embed.weight"):
+        e = O.parity(params[key].grad, a["grad_" + key.replace(".", "_")].to(DEV))[1]
+        print(f"   grad {key}: rel {e:.3e}")
+        assert e <= 5e-2, (key, e)
+    assert O.parity(feats[0].grad, a["grad_in0"].to(DEV))[1] <= 5e-2

@@ -332,6 +332,37 @@ def test_cross_attention_softmax_scaling_golden():
     assert O.parity(plain[0], a["out0"])[1] > 1e-3
 
 
+_DIFF_GRADS = ("multi_view_branches.1.0.cross_attn.projq.weight", "multi_view_branches.0.1.attn.qkv.weight",
+               "multi_view_branches.0.0.cross_attn.lambda_q1", "multi_view_branches.1.1.cross_attn.lambda_k2",
+               "multi_view_branches.0.1.cross_attn.subln.weight", "multi_view_branches.1.0.cross_attn.projv.bias",
+               "multi_view_branches.0.0.mlp.fc1.weight", "proj_embed.weight")
+
+
+def _diff_loss(out, inter):
+    return sum(t.sum() for t in out) + sum((k + 1.5) * sum(t.sum() for t in lv) for k, lv in enumerate(inter))
+
+
+@pytest.mark.parametrize("name", ["diff_cross_attn_tiny", "diff_cross_attn_tiny_ifr"])
+def test_diff_cross_attention_golden(name):
+    """`DifferentialMultiViewCrossAttentionTransformer(IFR)` -- 128-wide self-attention heads, differential
+    cross-attention (64-wide q / k against 128-wide v), lambda parameters and RMS sub-norm; forward and gradients."""
+    cfg, a = load(name)
+    sd = {k: v.requires_grad_(True) for k, v in weights(cfg).items()}
+    V = cfg["V"]
+    feats = [a[f"feat{v}"].clone().requires_grad_(v == 0) for v in range(V)]
+    res = O.diff_info_sharing(sd, "", feats, cfg["depth"], cfg["heads"], base=100.0 if cfg["rope"] else None, indices=cfg["indices"])
+    out, inter = (res[0], res[1]) if cfg["indices"] is not None else (res, [])
+    for v in range(V):
+        _close(out[v], a[f"out{v}"])
+    for k, lv in enumerate(inter):
+        for v in range(V):
+            _close(lv[v], a[f"inter{k}_{v}"])
+    _diff_loss(out, inter).backward()
+    for key in _DIFF_GRADS:
+        _close(sd[key].grad, a["grad_" + key.replace(".", "_")], 1e-4)
+    _close(feats[0].grad, a["grad_in0"], 1e-4)
+
+
 def test_reference_functionals_mode_matches_spelled_out_oracle():
     """`O.reference_functionals()` routes LayerNorm / GELU / attention / RoPE through the torch calls the reference itself makes
     (F.layer_norm, F.gelu, F.scaled_dot_product_attention, the PyTorch RoPE fallback of pos_embed.py:116-155).  In fp32 both

@@ -26,8 +26,9 @@ def test_b200_lookup_needs_no_reference():
     assert registry.info_sharing_class("global_attention", ifr=True) is U.MultiViewGlobalAttentionTransformerIFR
     with pytest.raises(ValueError):
         registry.encoder_class("dinov2")  # not part of the B200 path
+    assert registry.info_sharing_class("diff_cross_attention") is U.DifferentialMultiViewCrossAttentionTransformer
     with pytest.raises(ValueError):
-        registry.info_sharing_class("diff_cross_attention")
+        registry.info_sharing_class("no_such_attention")
     with pytest.raises(ValueError):
         registry.encoder_class("croco", implementation="tpu")
     enc = registry.build_encoder("croco", name="e", data_norm_type="dust3r", enc_embed_dim=128, enc_depth=1, enc_num_heads=2)
@@ -41,7 +42,7 @@ def test_install_swaps_the_reference_registries_and_restores_them():
     import uniception.models.info_sharing as RI
 
     ref_croco, ref_cross = RE.ENCODER_CONFIGS["croco"]["class"], RI.INFO_SHARING_CLASSES["cross_attention"]
-    ref_diff, ref_dino = RI.INFO_SHARING_CLASSES["diff_cross_attention"], RE.ENCODER_CONFIGS["dinov2"]["class"]
+    ref_dino = RE.ENCODER_CONFIGS["dinov2"]["class"]
     assert registry.current() == "reference"
     with registry.implementation("b200"):
         assert registry.current() == "b200"
@@ -54,8 +55,9 @@ def test_install_swaps_the_reference_registries_and_restores_them():
         assert RE.ENCODER_CONFIGS["croco"]["supported_models"] == ["CroCov2", "DUSt3R", "MASt3R"]  # metadata kept
         assert RI.INFO_SHARING_CLASSES["cross_attention"][0] is U.MultiViewCrossAttentionTransformer
         assert RI.INFO_SHARING_CLASSES["alternating_attention"][1] is U.MultiViewAlternatingAttentionTransformerIFR
+        assert RI.INFO_SHARING_CLASSES["diff_cross_attention"][0] is U.DifferentialMultiViewCrossAttentionTransformer
         # untouched names keep the reference's classes
-        assert RI.INFO_SHARING_CLASSES["diff_cross_attention"] is ref_diff and RE.ENCODER_CONFIGS["dinov2"]["class"] is ref_dino
+        assert RE.ENCODER_CONFIGS["dinov2"]["class"] is ref_dino
         # explicit per-module choice still reaches the reference while the hook is on
         assert registry.encoder_class("croco", implementation="reference") is ref_croco
         assert registry.info_sharing_class("cross_attention", implementation="reference") is ref_cross[0]

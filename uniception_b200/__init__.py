@@ -29,4 +29,8 @@ from .prediction_heads import (  # noqa: F401
 from .rope import RoPE2D, cuRoPE2D  # noqa: F401
 
 __version__ = "0.1.0"
+from .diff_attention import (  # noqa: E402
+    DiffAttention, DiffCrossAttention, DiffCrossAttentionBlock, DiffSelfAttentionBlock, DifferentialMultiViewCrossAttentionTransformer,
+    DifferentialMultiViewCrossAttentionTransformerIFR, RMSNorm,
+)
 from . import registry  # noqa: E402,F401  (implementation switch / hook into the reference's registries; imports nothing from the reference)

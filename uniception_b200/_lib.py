@@ -140,6 +140,8 @@ EXPORTS = {
     "uc_nchw_to_nlc": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
     "uc_head_post_fwd": (C.c_int, [C.POINTER(HeadPostFwdParams), vp]),
     "uc_head_post_bwd": (C.c_int, [C.POINTER(HeadPostBwdParams), vp]),
+    "uc_softmax_rows_fwd": (C.c_int, [vp, vp, i32, i32, i32, f32, vp]),
+    "uc_softmax_rows_bwd": (C.c_int, [vp, vp, vp, i32, i32, i32, f32, vp]),
     "uc_patch_embed": (C.c_int, [C.POINTER(PatchEmbedParams), vp]),
     "uc_conv3x3": (C.c_int, [C.POINTER(Conv3x3Params), vp]),
     "uc_im2col3x3": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp]),

@@ -6,8 +6,6 @@ masters with a version-keyed bf16 operand cache, parameter gradients are returne
 """
 from __future__ import annotations
 
-import weakref
-
 import torch
 import torch.nn as nn
 
@@ -15,16 +13,17 @@ from . import engine as E
 from . import ops
 from .rope import fusable_rope
 
-_w16_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
-
-
 def w16(param: torch.Tensor) -> torch.Tensor:
-    """bf16 operand copy of an fp32 parameter, refreshed when the parameter changes."""
-    key = (param.data_ptr(), param._version)
-    hit = _w16_cache.get(param)
+    """bf16 operand copy of an fp32 parameter, refreshed when the parameter changes.  The copy is cached ON the parameter
+    object (a WeakKeyDictionary keyed by tensors compares keys with `==` on hash collisions, which is elementwise)."""
+    key = (param.data_ptr(), param._version, str(param.device))
+    hit = getattr(param, "_uc_w16", None)
     if hit is None or hit[0] != key:
         hit = (key, ops.cast_bf16(param.detach().contiguous()).view(param.shape[0], -1))
-        _w16_cache[param] = hit
+        try:
+            param._uc_w16 = hit
+        except AttributeError:  # pragma: no cover  (plain tensors without a __dict__)
+            pass
     return hit[1]
 
 
@@ -211,6 +210,66 @@ class AttentionFn(torch.autograd.Function):
                      dkv_src[:, v_off:v_off + C], q_positions=qpos32 if tab is not None else None,
                      k_positions=kpos32 if tab is not None else None, rope_table=tab)
         return (dq_src.view(qs), None if same else dkv_src.view(kvs)) + (None,) * 11
+
+
+class GeneralAttentionFn(torch.autograd.Function):
+    """softmax(q k^T * scale) v for head dims the fused kernels do not cover (any multiples of 64; q/k width != v width
+    allowed): the attention of the DiffAttention family (utils/transformer_blocks.py:686-945) -- 128-wide self-attention heads and
+    64-wide q/k against 128-wide v at the default dim 768 / 12 heads.  UN-FUSED: per (batch, head) the scores are a uc_gemm
+    (fp32 out), the softmax a row kernel (uc_softmax_rows_*), P V / the four gradient products uc_gemms again; P (bf16) is
+    kept for the backward.  Keys are zero-padded to a multiple of 64 (GEMM n / k constraint), masked in the softmax.
+    q4 [B,H,Nq,dqk], k4 [B,H,Nk,dqk], v4 [B,H,Nk,dv] -> [B,H,Nq,dv] bf16."""
+
+    @staticmethod
+    def forward(ctx, q4, k4, v4, scale):
+        B, H, Nq, dqk = q4.shape
+        Nk, dv = k4.shape[2], v4.shape[3]
+        assert dqk % 64 == 0 and dv % 64 == 0, "head dims must be multiples of 64"
+        if not q4.is_cuda:
+            raise RuntimeError("uniception_b200: tensors must live on a CUDA device (no CPU fallback)")
+        Nkp = (Nk + 63) // 64 * 64
+        dev = q4.device
+        q = q4.to(torch.bfloat16).contiguous()
+        k = torch.zeros(B, H, Nkp, dqk, dtype=torch.bfloat16, device=dev)
+        v = torch.zeros(B, H, Nkp, dv, dtype=torch.bfloat16, device=dev)
+        k[:, :, :Nk] = k4
+        v[:, :, :Nk] = v4
+        P = torch.empty(B, H, Nq, Nkp, dtype=torch.bfloat16, device=dev)
+        o = torch.empty(B, H, Nq, dv, dtype=torch.bfloat16, device=dev)
+        s = torch.empty(Nq, Nkp, dtype=torch.float32, device=dev)
+        for b in range(B):
+            for h in range(H):
+                ops.gemm(q[b, h], k[b, h], s)
+                ops.softmax_rows_fwd(s, Nk, scale, out=P[b, h])
+                ops.gemm(P[b, h], v[b, h], o[b, h], b_layout=1)
+        ctx.save_for_backward(q, k, v, P)
+        ctx.meta = (Nk, float(scale), q4.dtype, k4.dtype, v4.dtype)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q, k, v, P = ctx.saved_tensors
+        Nk, scale, tq, tk, tv = ctx.meta
+        B, H, Nq, dqk = q.shape
+        Nkp, dv = k.shape[2], v.shape[3]
+        dev = q.device
+        do = d_o.to(torch.bfloat16).contiguous()
+        dq = torch.empty_like(q)
+        dk = torch.empty_like(k)
+        dvp = torch.empty_like(v)
+        dp = torch.empty(Nq, Nkp, dtype=torch.float32, device=dev)
+        for b in range(B):
+            for h in range(H):
+                ops.gemm(P[b, h], do[b, h], dvp[b, h], a_layout=1, b_layout=1)  # dV = P^T dO
+                ops.gemm(do[b, h], v[b, h], dp)                                  # dP = dO V^T
+                ds = ops.softmax_rows_bwd(P[b, h], dp, Nk, scale)
+                ops.gemm(ds, k[b, h], dq[b, h], b_layout=1)                      # dQ = dS K
+                ops.gemm(ds, q[b, h], dk[b, h], a_layout=1, b_layout=1)          # dK = dS^T Q
+        return dq.to(tq), dk[:, :, :Nk].to(tk), dvp[:, :, :Nk].to(tv), None
+
+
+def general_attention(q4, k4, v4, scale):
+    return GeneralAttentionFn.apply(q4, k4, v4, scale)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -4,8 +4,9 @@
 `CrossAttention`, `CrossAttentionBlock` mirror utils/transformer_blocks.py:260-386, :517-647.
 `SelfAttentionBlock`, `LayerScale` mirror utils/transformer_blocks.py:389-514.
 Built natively: the DUSt3R option set plus qk_norm, LayerScale (init_values) and the softmax-scaling flags; dropout,
-stochastic depth, non-GELU activations, head_dim != 64, latent_attn_dim and DiffAttention raise NotImplementedError at
-construction instead of silently running something else.
+stochastic depth and non-GELU activations raise NotImplementedError at construction instead of silently running something else.
+Head dims other than 64 (multiples of 64) take the un-fused GEMM + row-softmax attention; the DiffAttention family lives in
+diff_attention.py.
 
 The fused whole-module engines (encoders.py / info_sharing.py) never call these modules' forward:
 they read the parameters through a ParamPack.  The `forward` methods here exist so the blocks are
@@ -80,7 +81,10 @@ class Attention(nn.Module):
             assert dim % num_heads == 0, "dim should be divisible by num_heads"
         self.latent_attn = latent_attn_dim is not None
         width = latent_attn_dim if self.latent_attn else dim
-        _require(width // num_heads == 64, f"head_dim {width // num_heads} (only 64)")
+        # head_dim 64: the fused tcgen05 attention kernels.  Other multiples of 64 (128 inside the DiffAttention family's
+        # blocks): the un-fused GEMM + row-softmax path (autograd_ops.GeneralAttentionFn), without qk_norm
+        _require((width // num_heads) % 64 == 0, f"head_dim {width // num_heads} (multiples of 64 only)")
+        _require(width // num_heads == 64 or not qk_norm, "qk_norm with head_dim != 64")
         _require(attn_drop == 0.0 and proj_drop == 0.0, "attention dropout")
         # softmax scaling by the token count (utils/transformer_blocks.py:231-241) folds into the kernels' scale
         self.softmax_scaling = (use_scalable_softmax, use_entropy_scaling, base_token_count_for_entropy_scaling,
@@ -101,7 +105,15 @@ class Attention(nn.Module):
         if self.rope is not None:
             assert xpos is not None, "Positions of tokens (xpos) are a required input when using custom positional encoding"
         qkv = A.linear(x, self.qkv.weight, self.qkv.bias)
-        scale = attn_scale(self.softmax_scaling, N)
+        scale = attn_scale(self.softmax_scaling, N, self.head_dim)
+        if self.head_dim != 64:
+            qkv5 = qkv.reshape(B, N, 3, self.num_heads, self.head_dim).permute(2, 0, 3, 1, 4)
+            q, k, v = qkv5[0], qkv5[1], qkv5[2]
+            if self.rope is not None:  # the plugin may rotate in place (cuRoPE2D): give it private contiguous copies
+                q = self.rope(q.clone(memory_format=torch.contiguous_format), xpos)
+                k = self.rope(k.clone(memory_format=torch.contiguous_format), xpos)
+            o = A.general_attention(q, k, v, scale).transpose(1, 2).reshape(B, N, C)
+            return A.linear(o, self.proj.weight, self.proj.bias, residual=residual)
         if isinstance(self.q_norm, nn.LayerNorm):
             qn = A.head_norm(qkv, 0, C, self.q_norm)
             kv = torch.cat((A.head_norm(qkv, C, C, self.k_norm), qkv[..., 2 * C:]), dim=-1)
@@ -139,7 +151,8 @@ class CrossAttention(nn.Module):
                  use_entropy_scaling=False, base_token_count_for_entropy_scaling=444, entropy_scaling_growth_factor=1.4, **_ignored):
         super().__init__()
         assert dim % num_heads == 0, "dim should be divisible by num_heads"
-        _require(dim // num_heads == 64, f"head_dim {dim // num_heads} (only 64)")
+        _require((dim // num_heads) % 64 == 0, f"head_dim {dim // num_heads} (multiples of 64 only)")
+        _require(dim // num_heads == 64 or not qk_norm, "qk_norm with head_dim != 64")
         _require(attn_drop == 0.0 and proj_drop == 0.0, "attention dropout")
         self.softmax_scaling = (use_scalable_softmax, use_entropy_scaling, base_token_count_for_entropy_scaling,
                                 entropy_scaling_growth_factor) if (use_scalable_softmax or use_entropy_scaling) else None
@@ -160,6 +173,15 @@ class CrossAttention(nn.Module):
         q = A.linear(query, self.projq.weight, self.projq.bias)
         k = A.linear(key, self.projk.weight, self.projk.bias)
         v = A.linear(value, self.projv.weight, self.projv.bias)
+        if self.head_dim != 64:
+            q4 = q.reshape(B, Nq, self.num_heads, self.head_dim).permute(0, 2, 1, 3)
+            k4 = k.reshape(B, Nk, self.num_heads, self.head_dim).permute(0, 2, 1, 3)
+            v4 = v.reshape(B, Nk, self.num_heads, self.head_dim).permute(0, 2, 1, 3)
+            if self.custom_positional_encoding is not None:
+                q4 = self.custom_positional_encoding(q4.clone(memory_format=torch.contiguous_format), qpos)
+                k4 = self.custom_positional_encoding(k4.clone(memory_format=torch.contiguous_format), kpos)
+            o = A.general_attention(q4, k4, v4, attn_scale(self.softmax_scaling, Nq, self.head_dim)).transpose(1, 2).reshape(B, Nq, C)
+            return A.linear(o, self.proj.weight, self.proj.bias, residual=residual)
         if isinstance(self.q_norm, nn.LayerNorm):
             q, k = A.head_norm(q, 0, C, self.q_norm), A.head_norm(k, 0, C, self.k_norm)
         kv = torch.cat((k, v), dim=-1)

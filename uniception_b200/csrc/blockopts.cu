@@ -2,6 +2,8 @@
 // :222, :306-307, :347) fused with the 2-D RoPE that follows it, and LayerScale (:389-412).  HBM-bound: 16-byte accesses,
 // 8-lane groups per 64-wide head, statistics in fp32; per-column reductions are combined in the block before the global
 // atomics.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace uc {
@@ -271,4 +273,73 @@ extern "C" int uc_layerscale_bwd(const void* dy, const void* z, const float* gam
   layerscale_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(z), gamma, static_cast<__nv_bfloat16*>(dz), dgamma, rows, cols);
   return check_launch("uc_layerscale_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row softmax for the un-fused attention of head dims other than 64 (the DiffAttention family,
+// utils/transformer_blocks.py:686-945: scores and their gradients are [queries, keys] matrices produced by uc_gemm).
+// One warp per row, fp32 statistics; columns >= valid (padding up to a multiple of 64 keys) come out as exact zeros.
+//   fwd:  P  = softmax(scale * S[:, :valid])                              S fp32 -> P bf16
+//   bwd:  dS = scale * P o (dP - rowsum(P o dP))                          P bf16, dP fp32 -> dS bf16
+// ------------------------------------------------------------------------------------------------
+namespace uc {
+namespace {
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__global__ void softmax_rows_fwd_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P, int rows, int valid, int ld, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
+    const float* s = S + (size_t)row * ld;
+    __nv_bfloat16* p = P + (size_t)row * ld;
+    float m = -INFINITY;
+    for (int c = lane; c < valid; c += 32) m = fmaxf(m, s[c]);
+    m = warp_max(m) * scale;
+    float l = 0.f;
+    for (int c = lane; c < valid; c += 32) l += __expf(s[c] * scale - m);
+    l = warp_sum(l);
+    const float inv = 1.f / l;
+    for (int c = lane; c < ld; c += 32) p[c] = __float2bfloat16_rn(c < valid ? __expf(s[c] * scale - m) * inv : 0.f);
+  }
+}
+__global__ void softmax_rows_bwd_kernel(const __nv_bfloat16* __restrict__ P, const float* __restrict__ dP, __nv_bfloat16* __restrict__ dS,
+                                        int rows, int valid, int ld, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
+    const __nv_bfloat16* p = P + (size_t)row * ld;
+    const float* dp = dP + (size_t)row * ld;
+    __nv_bfloat16* ds = dS + (size_t)row * ld;
+    float dot = 0.f;
+    for (int c = lane; c < valid; c += 32) dot += __bfloat162float(p[c]) * dp[c];
+    dot = warp_sum(dot);
+    for (int c = lane; c < ld; c += 32) ds[c] = __float2bfloat16_rn(c < valid ? scale * __bfloat162float(p[c]) * (dp[c] - dot) : 0.f);
+  }
+}
+}  // namespace
+}  // namespace uc
+
+extern "C" int uc_softmax_rows_fwd(const float* s, void* p, int32_t rows, int32_t valid, int32_t ld, float scale, uc_stream_t st) {
+  using namespace uc;
+  UC_REQUIRE(s && p && rows > 0 && valid > 0 && ld >= valid, UC_ERR_BAD_SHAPE, "uc_softmax_rows_fwd: bad arguments");
+  const int blocks = (int)std::min<long long>(((long long)rows * 32 + 255) / 256, (long long)sm_count() * 8);
+  softmax_rows_fwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(st)>>>(s, static_cast<__nv_bfloat16*>(p), rows, valid, ld, scale);
+  return check_launch("uc_softmax_rows_fwd");
+}
+
+extern "C" int uc_softmax_rows_bwd(const void* p, const float* dp, void* ds, int32_t rows, int32_t valid, int32_t ld, float scale, uc_stream_t st) {
+  using namespace uc;
+  UC_REQUIRE(p && dp && ds && rows > 0 && valid > 0 && ld >= valid, UC_ERR_BAD_SHAPE, "uc_softmax_rows_bwd: bad arguments");
+  const int blocks = (int)std::min<long long>(((long long)rows * 32 + 255) / 256, (long long)sm_count() * 8);
+  softmax_rows_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(st)>>>(static_cast<const __nv_bfloat16*>(p), dp,
+                                                                             static_cast<__nv_bfloat16*>(ds), rows, valid, ld, scale);
+  return check_launch("uc_softmax_rows_bwd");
 }

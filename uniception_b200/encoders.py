@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from .checkpoints import load_checkpoint_file
 from . import fused
-from .blocks import Block, check_norm_layer
+from .blocks import Block, _require, check_norm_layer
 from .params import ParamPack, get_pack
 from .rope import RoPE2D, fusable_rope
 
@@ -185,6 +185,7 @@ class CroCoEncoder(UniCeptionViTEncoderBase):
         else:
             raise NotImplementedError("Unknown pos_embed " + pos_embed)
 
+        _require(enc_embed_dim // enc_num_heads == 64, f"head_dim {enc_embed_dim // enc_num_heads} in the fused encoder (only 64)")
         pe_cls = ManyAR_PatchEmbed if patch_embed_cls == "ManyAR_PatchEmbed" else PatchEmbedDust3R
         self.patch_embed = pe_cls(img_size, patch_size, 3, enc_embed_dim)
         self.enc_blocks = nn.ModuleList(

@@ -114,6 +114,7 @@ class MultiViewCrossAttentionTransformer(UniCeptionInfoSharingBase):
         self.gradient_checkpointing = gradient_checkpointing
         check_norm_layer(norm_layer)
         _require(qkv_bias, "qkv_bias=False")
+        _require(dim // num_heads == 64, f"head_dim {dim // num_heads} in the fused decoder (only 64)")
         _require(not gradient_checkpointing,
                  "gradient_checkpointing (raises AttributeError in the reference too, cross_attention_transformer.py:163-165)")
         _require(custom_positional_encoding is None or fusable_rope(custom_positional_encoding) is not None,
@@ -277,6 +278,7 @@ class MultiViewGlobalAttentionTransformer(UniCeptionInfoSharingBase):
         if drop_path or proj_drop or attn_drop:
             raise NotImplementedError("uniception_b200: dropout / stochastic-depth block options (SURVEY.md 8f4)")
         _require(qkv_bias, "qkv_bias=False")  # the engine's Linear kernels always carry a bias (as the cross-attention class)
+        _require(dim // num_heads == 64, f"head_dim {dim // num_heads} in the fused transformer (only 64)")
         self.qk_norm, self.init_values = qk_norm, init_values
         self.softmax_scaling = (use_scalable_softmax, use_entropy_scaling, base_token_count_for_entropy_scaling,
                                 entropy_scaling_growth_factor) if (use_scalable_softmax or use_entropy_scaling) else None

@@ -321,6 +321,25 @@ def _p(t):
     return _ptr(t) if t is not None else None
 
 
+def softmax_rows_fwd(s: torch.Tensor, valid: int, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """s fp32 [rows, ld] -> bf16 [rows, ld]: softmax(scale * s[:, :valid]) with zeros in the padding columns."""
+    _cuda(s)
+    assert s.dtype == torch.float32 and s.is_contiguous() and s.dim() == 2
+    p = torch.empty(s.shape, dtype=torch.bfloat16, device=s.device) if out is None else out
+    assert p.dtype == torch.bfloat16 and p.is_contiguous() and p.shape == s.shape
+    L.check(L.lib.uc_softmax_rows_fwd(_ptr(s), _ptr(p), s.shape[0], valid, s.shape[1], float(scale), _stream()))
+    return p
+
+
+def softmax_rows_bwd(p: torch.Tensor, dp: torch.Tensor, valid: int, scale: float) -> torch.Tensor:
+    """dS (bf16) = scale * P o (dP - rowsum(P o dP)); P bf16, dP fp32, both [rows, ld]."""
+    _cuda(p, dp)
+    assert p.dtype == torch.bfloat16 and dp.dtype == torch.float32 and p.is_contiguous() and dp.is_contiguous() and p.shape == dp.shape
+    ds = torch.empty(p.shape, dtype=torch.bfloat16, device=p.device)
+    L.check(L.lib.uc_softmax_rows_bwd(_ptr(p), _ptr(dp), _ptr(ds), p.shape[0], valid, p.shape[1], float(scale), _stream()))
+    return ds
+
+
 def patch_embed_ok(img: torch.Tensor, patch: int, n: int) -> bool:
     """Shapes uc_patch_embed accepts (TMA box constraints, include/uc_b200.h); everything else takes patchify + gemm."""
     return patch in (16, 32) and img.shape[-1] % 4 == 0 and n % 128 == 0 and img.shape[1] == 3

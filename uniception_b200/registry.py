@@ -12,8 +12,8 @@ behind those names:
                             registry.install("reference")   # restores the reference's classes (== uninstall())
     or `with registry.implementation("b200"): ...`
 
-Only the names this package implements are swapped (croco; cross_attention / alternating_attention / global_attention);
-"diff_cross_attention" and every other encoder keep the reference's classes.  Nothing here imports `uniception` unless a
+Only the names this package implements are swapped (croco; cross_attention / alternating_attention / global_attention /
+diff_cross_attention); every other encoder keeps the reference's class.  Nothing here imports `uniception` unless a
 "reference" implementation or the hook is asked for -- importing uniception_b200 never pulls the reference in.
 """
 from __future__ import annotations
