@@ -475,10 +475,20 @@ def run_b200(args, wl):
     ms_e2e = timed(step_e2e, args.steps)
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM), CUDA events on the launching stream ----
+    # Each GEMM is timed ALONE on its stream: the per-view decoder streams and the column-sum side stream are switched off for the
+    # instrumented steps, otherwise an event pair around one view's GEMM also spans the other view's kernels that share the GPU
+    # with it (the decoder shapes read 2x too slow, the earlier lines' 0.60-0.63).  The timed region above keeps all streams on.
+    from uniception_b200 import engine as _E
+
+    _vs, _cs = _E.ViewStreams.enabled, _E._ColsumSide.enabled
+    _E.ViewStreams.enabled = _E._ColsumSide.enabled = False
     ops.PROFILE = []
-    for _ in range(0 if args.skip_instrumented else 2):
-        step(a_dev, b_dev)  # eager: per-launch CUDA events
-    torch.cuda.synchronize()
+    try:
+        for _ in range(0 if args.skip_instrumented else 2):
+            step(a_dev, b_dev)  # eager: per-launch CUDA events
+        torch.cuda.synchronize()
+    finally:
+        _E.ViewStreams.enabled, _E._ColsumSide.enabled = _vs, _cs
     gemm_ms = sum(rec[0].elapsed_time(rec[1]) for rec in ops.PROFILE)
     gemm_flop = sum(rec[2] for rec in ops.PROFILE)
     n_gemm = len(ops.PROFILE)
@@ -522,7 +532,9 @@ def run_b200(args, wl):
                                          "algorithmic FLOPs per launch = 2*m*n*k, avg %.3e" % (gemm_flop / max(n_gemm, 1)),
                          "kernel": "uc::gemm2_kernel<EPI,F32,BN> (CTA-pair tcgen05.mma cta_group::2 kind::f16, TMA, TMEM double-buffered "
                                    "epilogue) + uc::gemm_kernel<BN> for narrow n",
-                         "how": f"sum of 2*m*n*k over {n_gemm} uc_gemm launches of 2 instrumented steps / sum of CUDA-event durations on the launching stream",
+                         "how": f"sum of algorithmic FLOPs over {n_gemm} uc_gemm / uc_conv3x3 / uc_patch_embed launches of 2 instrumented steps / sum of their "
+                                "CUDA-event durations on the launching stream (instrumented steps run single-stream, eager, so that every "
+                                "launch is timed alone)",
                          "peak_source": peak_src, "frac_of_burst_peak": achieved / burst if burst else None,
                          "step_tflops": (units_per_s / world) * flop_unit / 1e12,
                          "step_frac_of_peak": (units_per_s / world) * flop_unit / 1e12 / sustained},

@@ -426,19 +426,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t rank = cluster_ctarank();
   const int num_clusters = gridDim.x >> 1;
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);   // leader: its own producer's arrive.expect_tx (bytes of BOTH CTAs)
-      mbar_init(empty_bar(s), 1);  // one multicast commit from the leader's MMA lane
+  if (warp == 0) {
+    // ~40 barriers: initialised by the 32 lanes in parallel (one thread doing them in sequence sits on the launch's critical path)
+    if (lane == 0) tma_prefetch_desc(&tmA);
+    if (lane == 1) tma_prefetch_desc(&tmB);
+    if (lane == 2) tma_prefetch_desc(&tmC);
+    if (lane == 3) tma_prefetch_desc(&tmAux);
+    for (int i = lane; i < 48; i += 32) {
+      // slots: [0, 2 S) full / empty (1: the leader producer's expect_tx / one multicast commit), 2 S + {0,1} tmem_full (1),
+      // 2 S + {2,3} tmem_empty (epilogue warps of BOTH CTAs), 2 S + 4 / + 5 the TMEM address slot (not a barrier),
+      // [2 S + 6, 2 S + 6 + 16) per-epilogue-warp input-tile barriers (1), [40, 48) work-queue ring (1)
+      const bool is_slot = (i == 2 * STAGES + 4) || (i == 2 * STAGES + 5);
+      const bool in_use = i < 2 * STAGES + 6 + 2 * NUM_EPI_WARPS || i >= 40;
+      if (!is_slot && in_use) mbar_init(bar_base + 8u * i, (i == 2 * STAGES + 2 || i == 2 * STAGES + 3) ? 2 * NUM_EPI_WARPS : 1);
     }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 2 * NUM_EPI_WARPS);  // leader: epilogue warps of both CTAs
-    }
-    for (int e = 0; e < NUM_EPI_WARPS; ++e) { mbar_init(ld_bar(e, 0), 1); mbar_init(ld_bar(e, 1), 1); }
-    for (int q = 0; q < 8; ++q) mbar_init(q_bar(q), 1);
     fence_barrier_init();
   }
   cluster_sync_all();  // barrier inits visible to the peer before any remote arrive / TMA credit
