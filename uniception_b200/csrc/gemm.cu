@@ -14,6 +14,10 @@
 
 namespace uc {
 
+// Optional launch-latency trace of the pair kernel (bring-up aid, tools/latency_probe.py --trace): per CTA 8 globaltimer stamps
+// [entry, set-up done, dependency wait done, first operands landed, first accumulator complete, epilogue of last tile done, exit].
+__device__ unsigned long long* g_gemm_trace = nullptr;
+
 namespace {
 
 constexpr int BM = 128;
@@ -425,6 +429,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int num_clusters = gridDim.x >> 1;
+  unsigned long long* const trc = g_gemm_trace ? g_gemm_trace + 16 * blockIdx.x : nullptr;
+  if (trc && threadIdx.x == 0) trc[0] = globaltimer_ns();
 
   if (warp == 0) {
     // ~40 barriers: initialised by the 32 lanes in parallel (one thread doing them in sequence sits on the launch's critical path)
@@ -452,6 +458,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (trc && threadIdx.x == 0) trc[1] = globaltimer_ns();
   pdl_launch_dependents();  // after the TMEM allocation (common.cuh: PDL rules)
   // the launch's work counter is private to it (not produced by the predecessor kernel): the leader's first fetch goes out
   // BEFORE the grid dependency wait, so its round trip hides under the predecessor's tail
@@ -459,6 +466,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   int first_item = cluster_id;  // g.work == nullptr: static round robin (item = cluster + k * clusters), no counters
   if (g.work && warp == 0 && rank == 0 && lane == 0) first_item = atomicAdd(g.work, 1);
   pdl_wait();
+  if (trc && threadIdx.x == 0) trc[2] = globaltimer_ns();
 
   const int total = g.num_m * g.num_n * g.split_k;  // num_m counts 256-row blocks here
 
@@ -615,6 +623,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          if (trc && qn == 0 && kb == kb0 && lane == 0) trc[3] = globaltimer_ns();
           const uint32_t sa = smem_base + stage * G2_STAGE_BYTES;
           const uint32_t sb = sa + G2_A_BYTES;
           const uint64_t adesc = g.a_mn ? umma_desc_mnmajor(sa, 8192) : umma_desc_kmajor(sa);
@@ -726,13 +735,30 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         __syncwarp();
       }
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
+      // Everything the epilogue math reads from global memory is fetched BEFORE the wait for the accumulator, while this warp
+      // has nothing else to do: the row's RoPE positions, and one 16-byte piece per lane of the warp's 128 bias values and of
+      // the row's two RoPE table lines, which pulls those lines into L1 -- epilogue_math's own loads then hit L1 (35 clk) instead
+      // of L2 (300 clk) on the critical path of the first chunk.  (launch-latency trace: ~0.8 us per 32-column chunk before.)
       int pos_y = 0, pos_x = 0;
       if ((epi_flags & UC_EPI_ROPE) && row_ok) {
         pos_y = g.positions[2 * row];
         pos_x = g.positions[2 * row + 1];
       }
+      if (epi_flags & UC_EPI_BIAS) {
+        const int nb = nw + 4 * lane;
+        if (nb < g.n) {
+          float4 warm = __ldg(reinterpret_cast<const float4*>(g.bias + nb));
+          asm volatile("" ::"f"(warm.x), "f"(warm.y), "f"(warm.z), "f"(warm.w));
+        }
+      }
+      if ((epi_flags & UC_EPI_ROPE) && row_ok && nw < g.rope_cols) {
+        float4 wy = __ldg(reinterpret_cast<const float4*>(g.rope_table + (size_t)pos_y * 32));
+        float4 wx = __ldg(reinterpret_cast<const float4*>(g.rope_table + (size_t)pos_x * 32));
+        asm volatile("" ::"f"(wy.x), "f"(wx.x));
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      if (trc && qn == 0 && warp == 2 && lane == 0) trc[4] = globaltimer_ns();
       const uint32_t tbase = tmem_base + (uint32_t(lane_group * 32) << 16) + uint32_t(acc * BN + col_half * (BN / 2));
       auto release_acc = [&]() {  // this warp has read all of its accumulator columns
         tc_fence_before();
@@ -772,6 +798,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           uint32_t(&rc)[32] = (c & 1) ? rb : ra;
           uint32_t(&rn)[32] = (c & 1) ? ra : rb;
           tmem_ld_wait();
+          if (trc && qn == 0 && warp == 2 && lane == 0) trc[7 + 2 * c] = globaltimer_ns();  // chunk c in registers
           if (c + 1 < NCH) tmem_ld32(tbase + 32 * (c + 1), rn);
           else release_acc();
           const int n = nw + c * 32;
@@ -825,6 +852,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                            "r"(prep[4 * j + 2]), "r"(prep[4 * j + 3])
                            : "memory");
           }
+          if (trc && qn == 0 && warp == 2 && lane == 0) trc[8 + 2 * c] = globaltimer_ns();  // chunk c staged
           if (hf == 1) {
             fence_proxy_async_smem();
             __syncwarp();
@@ -858,7 +886,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (trc && warp == 2 && lane == 0) trc[15] = globaltimer_ns();  // tile loop left
     if (lane == 0) tma_store_wait0();  // all bulk stores of this lane have completed before the CTA may exit
+    if (trc && warp == 2 && lane == 0) trc[5] = globaltimer_ns();
   }
 
   tc_fence_before();
@@ -867,6 +897,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tc_fence_after();
     tmem_dealloc2(tmem_base, 512);
   }
+  if (trc && threadIdx.x == 0) trc[6] = globaltimer_ns();
 }
 
 template <int MASK, bool F32, int BN, int CONV = 0>
@@ -896,6 +927,8 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& t
   if ((e & ~(UC_EPI_BIAS | UC_EPI_GELU)) == 0 && (e & UC_EPI_GELU))
     return launch2_inst<UC_EPI_BIAS | UC_EPI_GELU, false, BN>(tmA, tmB, tmC, tmAux, g, grid, stream);
   if (e == UC_EPI_GELU_BWD) return launch2_inst<UC_EPI_GELU_BWD, false, BN>(tmA, tmB, tmC, tmAux, g, grid, stream);
+  // every dgrad (no epilogue at all) and the plain Linear forwards: no run-time flag tests, no aux-tile path in the instance
+  if ((e & ~UC_EPI_BIAS) == 0) return launch2_inst<UC_EPI_BIAS, false, BN>(tmA, tmB, tmC, tmAux, g, grid, stream);
   if ((e & ~kGeneric) == 0) return launch2_inst<kGeneric, false, BN>(tmA, tmB, tmC, tmAux, g, grid, stream);
   return launch2_inst<-1, false, BN>(tmA, tmB, tmC, tmAux, g, grid, stream);
 }
@@ -921,6 +954,9 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, in
 // queue -- a cluster whose SMs are held by somebody else's CTAs (an NCCL all-reduce overlapped with the backward pass, a kernel
 // of another stream) takes fewer tiles instead of forcing a second wave.  Measured at N = 2 (profiles/r02c): no gain over the static split, so nothing switches it on by default.
 static int g_gemm_dynamic = [] { const char* e = getenv("UC_GEMM_DYNAMIC"); return e ? atoi(e) : 0; }();
+extern "C" __attribute__((visibility("default"))) int uc_debug_set_gemm_trace(unsigned long long* buf) {
+  return cudaMemcpyToSymbol(uc::g_gemm_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : UC_ERR_CUDA;
+}
 extern "C" int uc_set_gemm_dynamic(int on) {
   const int prev = g_gemm_dynamic;
   g_gemm_dynamic = on ? 1 : 0;
