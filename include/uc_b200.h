@@ -82,6 +82,9 @@ UC_API uint64_t uc_launch_count(void);
 #define UC_EPI_ATOMIC 32
 #define UC_EPI_RELU 64      /* v = max(v, 0)                      (DPT convs, dpt_block.py:114-177) */
 #define UC_EPI_RELU_BWD 128 /* v *= (aux_in[m,n] > 0)             (aux_in = the ReLU output) */
+#define UC_EPI_RESIDUAL_F32 256 /* with UC_EPI_RESIDUAL and fp32 C: `residual` is fp32 [m][ldc] -- an fp32 residual stream, which
+                                 * is what torch.autocast gives the reference's global / alternating transformers once the fp32
+                                 * view encoding has been added to the bf16 projection (global_attention_transformer.py:338-351) */
 
 typedef struct {
   const void* a;
@@ -95,7 +98,7 @@ typedef struct {
   int32_t split_k;  /* >= 1; 0 = choose */
   int32_t rope_cols;
   const float* bias;          /* [n] fp32 */
-  const void* residual;       /* [m][ldc] bf16 */
+  const void* residual;       /* [m][ldc] bf16 (fp32 with UC_EPI_RESIDUAL_F32) */
   void* aux_out;              /* [m][ldc] bf16 (UC_EPI_GELU pre-activation) */
   const void* aux_in;         /* [m][ldc] bf16 (UC_EPI_GELU_BWD pre-activation) */
   const int32_t* positions;   /* [m][2] int32 (y,x) per row (UC_EPI_ROPE) */

@@ -246,3 +246,69 @@ def test_standalone_dpt_modules_match_fused_head():
     assert O.parity(gw_split, r.conv1.weight.grad)[1] <= 2e-2
     with pytest.raises(AssertionError):  # channel check of dpt.py:198-201
         f(PredictionHeadLayeredInput(list_features=feats[::-1], target_output_shape=(96, 80)))
+
+
+@pytest.mark.parametrize("cls_name", ["MultiViewGlobalAttentionTransformer", "MultiViewAlternatingAttentionTransformer"])
+def test_self_attention_info_sharing_at_size_vs_oracle(cls_name):
+    """SURVEY 8 f2 AT SIZE: the reference's default transformer width (input 1024 -> dim 768, 12 heads, 12 blocks, RoPE) on two
+    views of 32 x 32 tokens (a 2048-token global sequence), forward + every parameter gradient against the fp32 oracle at the
+    1.0 x autocast + 1e-3 bar."""
+    tag = f"{cls_name} 2 x 1024 tokens"
+    torch.manual_seed(7)
+    m = getattr(U, cls_name)(name="mv", input_embed_dim=1024, depth=12, dim=768, num_heads=12,
+                             use_rand_idx_pe_for_non_reference_views=False, custom_positional_encoding=U.RoPE2D(freq=100.0)).to(DEV)
+    g = torch.Generator().manual_seed(99)
+    feats = [torch.randn(1, 1024, 32, 32, generator=g).to(DEV) for _ in range(2)]
+    m.zero_grad(set_to_none=True)
+    out = m(U.MultiViewTransformerInput(features=[f.clone().requires_grad_(True) for f in feats])).features
+    sum(o.sum() for o in out).backward()
+    ours_g = {k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in m.named_parameters()}
+    sd_src = {k: v.detach() for k, v in m.state_dict().items() if k != "view_pos_table"}
+
+    def run(sd):
+        o = O.self_attention_info_sharing(sd, "", feats, 12, 12, alternating="Alternating" in cls_name, base=100.0,
+                                          pe_for_non_ref=m.use_pe_for_non_reference_views)
+        return list(o), sum(t.sum() for t in o)
+
+    out32, g32, out16, g16 = _oracle_runs(run, sd_src)
+    failures = []
+    for v in range(2):
+        assert torch.isfinite(out[v]).all()
+        _check(tag, f"view{v}", O.parity(out[v], out32[v])[1], O.parity(out16[v], out32[v])[1], failures)
+    names = [k for k, _ in m.named_parameters()]
+    st = _grad_report(tag, ours_g, {k: g32[k] for k in names}, {k: g16[k] for k in names})
+    for stage, (e_o, e_l) in st.items():
+        _check(tag, f"grads[{stage}]", e_o, e_l, failures)
+    assert not failures, failures
+
+
+def test_diff_cross_attention_default_width_vs_oracle():
+    """SURVEY 8 f4 AT the reference's default width: DifferentialMultiViewCrossAttentionTransformer(dim 768, 12 heads -> blocks with
+    6 heads: 128-wide self-attention heads, 64-wide differential q / k against 128-wide v), depth 4, RoPE, two views of 16 x 16
+    tokens; forward + every parameter gradient (lambdas and RMS sub-norm included) against the fp32 oracle.  The family runs on
+    the un-fused attention, so the bar is the looser module-level one: 1.5 x autocast + 2e-3."""
+    tag = "DiffCrossAttention 768/12"
+    torch.manual_seed(11)
+    m = U.DifferentialMultiViewCrossAttentionTransformer(name="mvd", input_embed_dim=1024, num_views=2, depth=4, dim=768, num_heads=12,
+                                                         custom_positional_encoding=U.RoPE2D(freq=100.0)).to(DEV)
+    g = torch.Generator().manual_seed(5)
+    feats = [torch.randn(1, 1024, 16, 16, generator=g).to(DEV) for _ in range(2)]
+    m.zero_grad(set_to_none=True)
+    out = m(U.MultiViewTransformerInput(features=[f.clone().requires_grad_(True) for f in feats])).features
+    sum(o.sum() for o in out).backward()
+    ours_g = {k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in m.named_parameters()}
+    sd_src = {k: v.detach() for k, v in m.state_dict().items()}
+
+    def run(sd):
+        o = O.diff_info_sharing(sd, "", feats, 4, 12, base=100.0)
+        return list(o), sum(t.sum() for t in o)
+
+    out32, g32, out16, g16 = _oracle_runs(run, sd_src)
+    for v in range(2):
+        e_o, e_l = O.parity(out[v], out32[v])[1], O.parity(out16[v], out32[v])[1]
+        print(f"{tag} view{v}: ours {e_o:.3e} vs autocast-reference {e_l:.3e}")
+        assert e_o <= 1.5 * e_l + 2e-3, (v, e_o, e_l)
+    names = [k for k, _ in m.named_parameters()]
+    st = _grad_report(tag, ours_g, {k: g32[k] for k in names}, {k: g16[k] for k in names})
+    for stage, (e_o, e_l) in st.items():
+        assert e_o <= 1.5 * e_l + 2e-3, (stage, e_o, e_l)

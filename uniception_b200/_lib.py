@@ -23,7 +23,7 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 UC_DTYPE_BF16, UC_DTYPE_F32, UC_DTYPE_F16 = 0, 1, 2
-EPI_BIAS, EPI_ROPE, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ATOMIC, EPI_RELU, EPI_RELU_BWD = 1, 2, 4, 8, 16, 32, 64, 128
+EPI_BIAS, EPI_ROPE, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ATOMIC, EPI_RELU, EPI_RELU_BWD, EPI_RESIDUAL_F32 = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 

@@ -162,6 +162,13 @@ __device__ __forceinline__ void epilogue_math(const GemmArgs& g, int row, int n,
     if (hin) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) h[j] = hin[j];
+    } else if (epi & UC_EPI_RESIDUAL_F32) {
+      const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.residual) + off);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(q + j);
+        h[4 * j] = t.x; h[4 * j + 1] = t.y; h[4 * j + 2] = t.z; h[4 * j + 3] = t.w;
+      }
     } else {
       load_row32_bf16(g.residual + off, h);
     }
@@ -989,6 +996,8 @@ extern "C" int uc_gemm(const uc_gemm_params* p, uc_stream_t stream_) {
   UC_REQUIRE(!(epi & UC_EPI_ROPE) || (p->positions && p->rope_table && p->rope_cols % 64 == 0), UC_ERR_BAD_SHAPE,
              "uc_gemm: UC_EPI_ROPE needs positions, rope_table and rope_cols %% 64 == 0");
   UC_REQUIRE(!(epi & UC_EPI_ATOMIC) || p->c_dtype == UC_DTYPE_F32, UC_ERR_BAD_DTYPE, "uc_gemm: atomic epilogue needs fp32 C");
+  UC_REQUIRE(!(epi & UC_EPI_RESIDUAL_F32) || ((epi & UC_EPI_RESIDUAL) && p->c_dtype == UC_DTYPE_F32), UC_ERR_BAD_DTYPE,
+             "uc_gemm: UC_EPI_RESIDUAL_F32 needs UC_EPI_RESIDUAL and fp32 C");
   UC_REQUIRE(!p->c_colsum || (p->c_dtype == UC_DTYPE_BF16 && p->n % 8 == 0), UC_ERR_BAD_DTYPE, "uc_gemm: c_colsum needs bf16 C");
 
   const int num_kb = (p->k + BK - 1) / BK;

@@ -157,9 +157,13 @@ def ln_bwd(pk: ParamPack, name: str, dy, x, mean, rstd, dres=None, colsum=None):
     """colsum: fp32 [C] bias-gradient buffer of the Linear that will consume this call's dx as ITS output gradient
     (see `bias_sink`); the column sums of dx are accumulated there by the same kernel."""
     train = pk.requires_grad(name + ".weight")
-    return ops.layernorm_bwd(dy, x, pk.w32(name + ".weight"), mean, rstd,
-                             pk.grad(name + ".weight") if train else None, pk.grad(name + ".bias") if train else None, dres=dres,
-                             dx_colsum=colsum)
+    fused_sum = colsum if x.dtype == torch.bfloat16 else None  # the fused column sums live in the bf16 row kernel only
+    dx = ops.layernorm_bwd(dy, x, pk.w32(name + ".weight"), mean, rstd,
+                           pk.grad(name + ".weight") if train else None, pk.grad(name + ".bias") if train else None, dres=dres,
+                           dx_colsum=fused_sum)
+    if colsum is not None and fused_sum is None:  # fp32 residual stream (global / alternating transformers): one extra pass
+        ops.colsum_(dx, colsum)
+    return dx
 
 
 def has_param(pk: ParamPack, name: str) -> bool:
@@ -175,8 +179,8 @@ def ls_name(pk: ParamPack, block_prefix: str, k: int) -> Optional[str]:
 def out_proj_fwd(pk: ParamPack, name: str, inp, x, ls: Optional[str]):
     """x + [gamma *] Linear(inp): the sub-block's output projection with the residual add.  Returns (new x, z) where z is the
     un-scaled projection (saved for the LayerScale backward) or None."""
-    if ls is None:
-        return linear_fwd(pk, name, inp, residual=x), None
+    if ls is None:  # the stream keeps its dtype: bf16, or fp32 in the transformers whose reference stream is fp32 under autocast
+        return linear_fwd(pk, name, inp, residual=x, out_dtype=x.dtype), None
     z = linear_fwd(pk, name, inp)
     return ops.layerscale_fwd(z, x, pk.w32(ls)), z
 
@@ -707,16 +711,27 @@ def mv_self_attn_fwd(pk: ParamPack, p: str, x_in: torch.Tensor, B: int, nv: int,
     L = nv * n_view + n_extra
     rope = Rope(B * nv, h, w, rope_base, rope_f0, dev) if rope_base is not None else None
     assert rope is None or (n_extra == 0 and n_view == h * w), "RoPE is not defined for additional tokens"
+    # Stream dtype.  The reference adds the fp32 view-encoding table to the (bf16 under autocast) projection, which promotes its
+    # residual stream to fp32 for the rest of the transformer (global_attention_transformer.py:338-351: `x + pe`, then every
+    # `x + attn(...)` stays fp32).  A bf16 stream here measured 1.8x the reference's own autocast error at 12 blocks / 2048
+    # tokens; so with a view encoding the stream is fp32 (fp32 residual in / fp32 out of the two projection GEMMs per block,
+    # LayerNorm reads fp32).  Blocks with LayerScale keep the bf16 stream (uc_layerscale_* is bf16).
+    fp32_stream = view_pe is not None and not has_param(pk, f"{p}self_attention_blocks.0.ls1.gamma")
+    sdt = torch.float32 if fp32_stream else torch.bfloat16
     pe = None
-    if view_pe is not None:  # [V, dim] -> one row per token (zeros for the global extras), bf16 like the stream it is added to
-        rows = view_pe.to(torch.bfloat16).repeat_interleave(n_view, dim=0)
+    if view_pe is not None:  # [V, dim] -> one row per token (zeros for the global extras), in the stream's dtype
+        rows = view_pe.to(sdt).repeat_interleave(n_view, dim=0)
         if n_extra:
             rows = torch.cat([rows, torch.zeros(n_extra, rows.shape[1], dtype=rows.dtype, device=dev)], dim=0)
         pe = rows.repeat(B, 1).contiguous()
     if has_proj_embed:
-        x = linear_fwd(pk, p + "proj_embed", x_in, residual=pe)  # the view encoding rides the GEMM's residual epilogue
+        x = linear_fwd(pk, p + "proj_embed", x_in, residual=pe, out_dtype=sdt)  # the view encoding rides the GEMM's residual epilogue
+    elif pe is None:
+        x = x_in
+    elif fp32_stream:
+        x = x_in.float() + pe
     else:
-        x = x_in if pe is None else ops.elementwise(0, x_in.contiguous(), pe)
+        x = ops.elementwise(0, x_in.contiguous(), pe)
     saved = {"x_in": x_in, "blocks": [], "B": B, "L": L, "nv": nv, "n_view": n_view, "n_extra": n_extra, "rope": rope, "inter": [],
              "softmax_scaling": softmax_scaling}
     nvt = nv * n_view

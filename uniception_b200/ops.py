@@ -83,8 +83,13 @@ def gemm(a, b, out, *, a_layout=0, b_layout=0, bias=None, residual=None, aux_out
         assert aux_in is not None and aux_in.stride(0) == out.stride(0)
         epi |= L.EPI_RELU_BWD
     if residual is not None:
-        assert residual.dtype == torch.bfloat16 and residual.stride(0) == out.stride(0)
+        assert residual.stride(0) == out.stride(0) and residual.stride(1) == 1
         epi |= L.EPI_RESIDUAL
+        if residual.dtype == torch.float32:  # fp32 residual stream: fp32 in, fp32 out
+            assert out.dtype == torch.float32, "an fp32 residual needs an fp32 output"
+            epi |= L.EPI_RESIDUAL_F32
+        else:
+            assert residual.dtype == torch.bfloat16
     if atomic:
         epi |= L.EPI_ATOMIC
     p = L.GemmParams(
