@@ -322,10 +322,6 @@ def conv_out_hw(H: int, W: int, stride: int):
     return (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
 
 
-def _p(t):
-    return _ptr(t) if t is not None else None
-
-
 def softmax_rows_fwd(s: torch.Tensor, valid: int, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """s fp32 [rows, ld] -> bf16 [rows, ld]: softmax(scale * s[:, :valid]) with zeros in the padding columns."""
     _cuda(s)
@@ -358,7 +354,7 @@ def patch_embed(img: torch.Tensor, w32: torch.Tensor, bias: Optional[torch.Tenso
     n = w32.shape[0]
     assert w32.shape[1] == 3 * patch * patch
     out = torch.empty(B * (H // patch) * (W // patch), n, dtype=torch.bfloat16, device=img.device)
-    p = L.PatchEmbedParams(_ptr(img), _ptr(w32), _p(bias), _ptr(out), B, H, W, patch, n)
+    p = L.PatchEmbedParams(_ptr(img), _ptr(w32), _ptr(bias), _ptr(out), B, H, W, patch, n)
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -391,7 +387,7 @@ def conv3x3_fwd(x: torch.Tensor, w16: torch.Tensor, B: int, H: int, W: int, bias
     cin, cout = x.shape[1], w16.shape[0]
     assert w16.shape[1] == 9 * cin
     y = torch.empty(B * H * W, cout, dtype=torch.bfloat16, device=x.device)
-    p = L.Conv3x3Params(0, B, H, W, cin, cout, _ptr(x), _ptr(w16), _ptr(y), None, None, None, _p(bias), _p(residual), None, int(relu))
+    p = L.Conv3x3Params(0, B, H, W, cin, cout, _ptr(x), _ptr(w16), _ptr(y), None, None, None, _ptr(bias), _ptr(residual), None, int(relu))
     _conv_call(p, B, H, W, cin, cout, 0)
     return y
 
@@ -404,7 +400,7 @@ def conv3x3_dgrad(dy: torch.Tensor, w16: torch.Tensor, B: int, H: int, W: int, r
     cin = w16.shape[1] // 9
     assert dy.shape[1] == cout
     dx = torch.empty(B * H * W, cin, dtype=torch.bfloat16, device=dy.device)
-    p = L.Conv3x3Params(1, B, H, W, cin, cout, None, _ptr(w16), None, _ptr(dy), _ptr(dx), None, None, None, _p(relu_out), 0)
+    p = L.Conv3x3Params(1, B, H, W, cin, cout, None, _ptr(w16), None, _ptr(dy), _ptr(dx), None, None, None, _ptr(relu_out), 0)
     _conv_call(p, B, H, W, cin, cout, 1)
     return dx
 

@@ -20,7 +20,7 @@ from __future__ import annotations
 
 import contextlib
 import importlib
-from typing import Dict, Optional, Tuple
+from typing import Dict, Tuple
 
 from . import encoders as _enc
 from . import info_sharing as _info
@@ -28,7 +28,7 @@ from . import info_sharing as _info
 IMPLEMENTATIONS = ("b200", "reference")
 _ENCODER_NAMES = ("croco",)
 _INFO_NAMES = tuple(_info.INFO_SHARING_CLASSES.keys())
-_saved: Dict[str, object] = {}
+_saved: Dict[Tuple[str, str], object] = {}  # ("enc" | "info", registry name) -> the reference's own entry
 _current = "reference"  # what the REFERENCE's registries currently resolve to
 
 
