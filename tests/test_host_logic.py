@@ -126,3 +126,37 @@ def test_adaptors_match_oracle_on_cpu():
     assert torch.allclose(out.value, p) and torch.allclose(out.confidence, c) and ad.fusable()
     d = U.DepthAdaptor(name="d", mode="exp", vmin=-float("inf"), vmax=float("inf"))
     assert torch.allclose(d(U.AdaptorInput(adaptor_feature=x[:, :1], output_shape_hw=(8, 6))).value, O.depth_adaptor(x[:, :1]))
+
+
+def test_diff_attention_family_state_dict_matches_reference():
+    """the DiffAttention transformer's parameter names, shapes and ORDER equal the reference's (drop-in checkpoints)."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import ref_import
+
+    if not ref_import.reference_available():
+        pytest.skip("reference tree not present")
+    ref_import.import_reference()
+    from uniception.models.info_sharing.diff_cross_attention_transformer import (
+        DifferentialMultiViewCrossAttentionTransformer as RefDiff, DifferentialMultiViewCrossAttentionTransformerIFR as RefDiffIFR)
+    from uniception.models.libs.croco.pos_embed import RoPE2D as RefRoPE
+
+    import uniception_b200 as U
+
+    kw = dict(name="d", input_embed_dim=192, num_views=3, depth=2, dim=256, num_heads=4)
+    ours = U.DifferentialMultiViewCrossAttentionTransformer(custom_positional_encoding=U.RoPE2D(freq=100.0), **kw)
+    ref = RefDiff(custom_positional_encoding=RefRoPE(freq=100.0), **kw)
+    assert [(k, tuple(v.shape)) for k, v in ours.state_dict().items()] == [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]
+    ours_ifr = U.DifferentialMultiViewCrossAttentionTransformerIFR(indices=[0, 1], **kw)
+    ref_ifr = RefDiffIFR(indices=[0, 1], **kw)
+    assert list(ours_ifr.state_dict()) == list(ref_ifr.state_dict())
+    # lambda initialisation constants of the reference (transformer_blocks.py:682-683) per depth
+    for i in range(2):
+        assert abs(ours.multi_view_branches[0][i].cross_attn.lambda_init - ref.multi_view_branches[0][i].cross_attn.lambda_init) < 1e-12
+    # head geometry: blocks are built with num_heads // 2 (diff_cross_attention_transformer.py:110-113)
+    blk = ours.multi_view_branches[1][0]
+    assert blk.attn.num_heads == 2 and blk.attn.head_dim == 128 and blk.cross_attn.num_heads == 2 and blk.cross_attn.head_dim == 64
+    with pytest.raises(AssertionError):
+        U.DifferentialMultiViewCrossAttentionTransformer(name="d", input_embed_dim=192, num_views=2, depth=1, dim=256, num_heads=3)
